@@ -112,13 +112,13 @@ def main():
                 "-I%s -I%s -I%s -I%s" % (os.path.join(OUT, "include"), K,
                                          os.path.join(OFST, "include"),
                                          os.path.join(REF, "kaldi", "tools", "CLAPACK")))
-    ldflags = "-pthread -Wl,-rpath,'$$ORIGIN/..' -Wl,-rpath,%s -L%s -L%s -lkaldi_ref -l:%s -ldl -lm" % (
+    ldflags = "-pthread -Wl,--disable-new-dtags -Wl,-rpath,'$$ORIGIN/..' -Wl,-rpath,%s -L%s -L%s -lkaldi_ref -l:%s -ldl -lm" % (
         blas_dir, OUT, blas_dir, os.path.basename(blas))
     n = ["cxx = g++", "cxxflags = " + cxxflags, "",
          "rule cc", "  command = $cxx $cxxflags -MMD -MF $out.d -c $in -o $out",
          "  depfile = $out.d", "  deps = gcc", "  description = CC $out", "",
          "rule solib",
-         "  command = $cxx -shared -o $out @$out.rsp -Wl,-rpath,%s -l:%s -L%s -lpthread -ldl -lm" % (
+         "  command = $cxx -shared -o $out @$out.rsp -Wl,--disable-new-dtags -Wl,-rpath,%s -l:%s -L%s -lpthread -ldl -lm" % (
              blas_dir, os.path.basename(blas), blas_dir),
          "  rspfile = $out.rsp", "  rspfile_content = $in", "  description = SOLIB $out", "",
          "rule link", "  command = $cxx -o $out $in %s" % ldflags, "  description = LINK $out", ""]
