@@ -161,7 +161,7 @@ class SynthSpec:
     prefinal_small: int = 24
     num_phones: int = 20                # non-silence phones; phone 1 is SIL
     variants_per_phone: int = 3         # context-dependent variants -> pdfs
-    output_scale: float = 4.0           # spread of the pseudo log-likelihoods
+    output_scale: float = 1.5           # spread of the pseudo log-likelihoods
     priors: bool = False                # non-empty <Priors> (subtracts log prior)
     log_softmax: bool = False
     # graph
@@ -177,7 +177,7 @@ class SynthSpec:
 TINY = SynthSpec()
 ZAMIA_LIKE = SynthSpec(name="zamia_like", seed=7, ivector_dim=100, num_gauss=512, hidden_dim=1024,
                        bottleneck_dim=128, tdnnf_strides=(1, 1, 1, 0, 3, 3, 3, 3, 3, 3, 3, 3),
-                       prefinal_small=192, num_phones=42, variants_per_phone=36, output_scale=5.0)
+                       prefinal_small=192, num_phones=42, variants_per_phone=36, output_scale=1.5)
 
 # sentences of the reference's tests/en_US-zamia fixture (file stems, "_" -> " ")
 EN_US_SENTENCES = [
@@ -322,7 +322,149 @@ def _write_transition_model(w: KaldiWriter, spec: SynthSpec, rng: np.random.Gene
 
 
 # --------------------------------------------------------------------------------------
-# nnet3
+# nnet3: parameters are drawn first, the BatchNorm statistics are then *calibrated* by running
+# speech-like features through the layers (as training would leave them), and only then is
+# the model written.  `nnet_forward` is the float64 numpy forward of exactly this architecture.
+
+
+def _calib_mfcc(pcm: np.ndarray, spec: "SynthSpec") -> np.ndarray:
+    """Plain numpy MFCC (np.fft; NOT bit-faithful to Kaldi) -- calibration data only."""
+    x = np.asarray(pcm, dtype=np.float64)
+    T = 1 + (len(x) - 400) // 160
+    fr = x[np.arange(T)[:, None] * 160 + np.arange(400)[None, :]]
+    fr = fr - fr.mean(axis=1, keepdims=True)
+    fr = np.concatenate([fr[:, :1] * 0.03, fr[:, 1:] - 0.97 * fr[:, :-1]], axis=1)
+    fr = fr * (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(400) / 399)) ** 0.85
+    pw = np.abs(np.fft.rfft(fr, 512, axis=1)) ** 2
+    nb = spec.num_mel_bins
+    mel = lambda f: 1127.0 * np.log(1.0 + f / 700.0)
+    hi = spec.high_freq if spec.high_freq > 0 else 8000.0 + spec.high_freq
+    edges = np.linspace(mel(spec.low_freq), mel(hi), nb + 2)
+    m = mel(np.arange(257) * (16000.0 / 512))
+    fb = np.zeros((nb, 257))
+    for b in range(nb):
+        l, c, r = edges[b], edges[b + 1], edges[b + 2]
+        up = (m - l) / (c - l)
+        dn = (r - m) / (r - c)
+        fb[b] = np.where((m > l) & (m < r), np.where(m <= c, up, dn), 0.0)
+    lm = np.log(np.maximum(pw @ fb.T, np.finfo(np.float32).eps))
+    dct = np.sqrt(2.0 / nb) * np.cos(np.pi / nb * (np.arange(nb)[None, :] + 0.5) * np.arange(spec.num_ceps)[:, None])
+    dct[0] = np.sqrt(1.0 / nb)
+    return (lm @ dct.T) * (1.0 + 11.0 * np.sin(np.pi * np.arange(spec.num_ceps) / 22.0))
+
+
+def _tdnn_apply(x: np.ndarray, t0: int, W: np.ndarray, b, offsets) -> Tuple[np.ndarray, int]:
+    """x holds times t0..t0+len-1 (dense); returns the valid output range and its first time."""
+    lo, hi = min(offsets), max(offsets)
+    n = x.shape[0] - (hi - lo)
+    k = x.shape[1]
+    y = np.zeros((n, W.shape[0]))
+    for i, o in enumerate(offsets):
+        y += x[o - lo:o - lo + n] @ W[:, i * k:(i + 1) * k].T
+    if b is not None and len(b):
+        y += b
+    return y, t0 - lo
+
+
+def _bn(x, bn):
+    mean, var, eps = bn
+    scale = 1.0 / np.sqrt(np.maximum(var, 0.0) + eps)
+    return x * scale + (-mean * scale)
+
+
+def nnet_forward(P: dict, feats: np.ndarray, ivector: np.ndarray, calibrate: bool = False, branch: str = "chain"):
+    """float64 forward of the synthetic TDNN-F (pseudo log-likelihoods before priors), for every
+    input frame t in [0, T) with the reference's edge handling: input frames outside [0, T) are
+    copies of the first / last frame (nnet3/decodable-online-looped.cc:150-161)."""
+    T = feats.shape[0]
+    L, R = P["left_context"], P["right_context"]
+    idx = np.clip(np.arange(-L, T + R), 0, T - 1)
+    x = feats[idx].astype(np.float64)
+    t0 = -L
+
+    def calib(name, v):
+        if calibrate:
+            P[name] = (v.mean(axis=0), v.var(axis=0) + 1e-3, 1e-3)
+
+    n = x.shape[0] - 2
+    sp = np.concatenate([x[0:n], x[1:n + 1], x[2:n + 2], np.tile(ivector.astype(np.float64), (n, 1))], axis=1)
+    t0 += 1
+    h = sp @ P["lda.W"].T + P["lda.b"]
+    h = np.maximum(h @ P["tdnn1.W"].T + P["tdnn1.b"], 0.0)
+    calib("tdnn1.bn", h)
+    h = _bn(h, P["tdnn1.bn"])
+    for li, (off1, off2) in enumerate(P["tdnnf_offsets"]):
+        nme = "tdnnf%d" % (li + 2)
+        y, ty = _tdnn_apply(h, t0, P[nme + ".lin.W"], None, off1)
+        y, ty = _tdnn_apply(y, ty, P[nme + ".aff.W"], P[nme + ".aff.b"], off2)
+        y = np.maximum(y, 0.0)
+        calib(nme + ".bn", y)
+        y = _bn(y, P[nme + ".bn"])
+        h = 0.66 * h[ty - t0:ty - t0 + y.shape[0]] + y
+        t0 = ty
+    s = h @ P["prefinal-l.W"].T
+    p = "prefinal-" + branch
+    a = np.maximum(s @ P[p + ".aff.W"].T + P[p + ".aff.b"], 0.0)
+    calib(p + ".bn1", a)
+    a = _bn(a, P[p + ".bn1"])
+    a = a @ P[p + ".lin.W"].T
+    calib(p + ".bn2", a)
+    a = _bn(a, P[p + ".bn2"])
+    o = "output" if branch == "chain" else "output-xent"
+    out = a @ P[o + ".W"].T + P[o + ".b"]
+    assert t0 == 0 and out.shape[0] == T, (t0, out.shape, T)
+    return out
+
+
+def make_nnet_params(spec: "SynthSpec", rng: np.random.Generator, num_pdfs: int) -> dict:
+    H, B, D, IV, S = spec.hidden_dim, spec.bottleneck_dim, spec.num_ceps, spec.ivector_dim, spec.prefinal_small
+    P: dict = {}
+    lda_in = 3 * D + IV
+    m1, s1 = mfcc_stats(D)
+    in_mean = np.concatenate([m1, m1, m1, np.zeros(IV)])
+    in_std = np.concatenate([s1, s1, s1, np.ones(IV)])
+    W = rng.standard_normal((lda_in, lda_in)) / math.sqrt(lda_in) / in_std[None, :]
+    P["lda.W"] = W.astype(np.float32)
+    P["lda.b"] = (rng.standard_normal(lda_in) * 0.1 - W @ in_mean).astype(np.float32)
+
+    def mat(o, i, scale=1.0):
+        return (rng.standard_normal((o, i)) * (scale / math.sqrt(i))).astype(np.float32)
+
+    def bn(d):
+        return (np.zeros(d), np.ones(d), 1e-3)
+
+    P["tdnn1.W"], P["tdnn1.b"], P["tdnn1.bn"] = mat(H, lda_in), (rng.standard_normal(H) * 0.1).astype(np.float32), bn(H)
+    offs = []
+    for li, stride in enumerate(spec.tdnnf_strides):
+        nme = "tdnnf%d" % (li + 2)
+        off1 = [-stride, 0] if stride else [0]
+        off2 = [0, stride] if stride else [0]
+        offs.append((off1, off2))
+        P[nme + ".lin.W"] = mat(B, H * len(off1))
+        P[nme + ".aff.W"] = mat(H, B * len(off2), 2.0)
+        P[nme + ".aff.b"] = (rng.standard_normal(H) * 0.1).astype(np.float32)
+        P[nme + ".bn"] = bn(H)
+    P["tdnnf_offsets"] = offs
+    P["prefinal-l.W"] = mat(S, H)
+    for branch in ("chain", "xent"):
+        p = "prefinal-" + branch
+        P[p + ".aff.W"], P[p + ".aff.b"], P[p + ".bn1"] = mat(H, S, 2.0), (rng.standard_normal(H) * 0.1).astype(np.float32), bn(H)
+        P[p + ".lin.W"], P[p + ".bn2"] = mat(S, H), bn(S)
+        o = "output" if branch == "chain" else "output-xent"
+        P[o + ".W"] = mat(num_pdfs, S, spec.output_scale)
+        P[o + ".b"] = (rng.standard_normal(num_pdfs) * 0.1 * spec.output_scale).astype(np.float32)
+    P["left_context"] = 1 + sum(s for s in spec.tdnnf_strides)
+    P["right_context"] = 1 + sum(s for s in spec.tdnnf_strides)
+    # calibrate the BatchNorm statistics on speech-like features, one branch after the other
+    feats = np.concatenate([_calib_mfcc(synth_speech(2.0, 9000 + i), spec) for i in range(3)])
+    iv = rng.standard_normal(IV) * 0.7
+    for branch in ("chain", "xent"):
+        nnet_forward(P, feats, iv, calibrate=True, branch=branch)
+    for k in list(P):
+        if k.endswith(".bn") or k.endswith(".bn1") or k.endswith(".bn2"):
+            mean, var, eps = P[k]
+            P[k] = (mean.astype(np.float32).astype(np.float64), var.astype(np.float32).astype(np.float64), eps)
+    return P
 
 
 def _updatable_prefix(w: KaldiWriter, typ: str):
@@ -332,13 +474,12 @@ def _updatable_prefix(w: KaldiWriter, typ: str):
     w.tok("<LearningRate>"); w.f32(0.001)
 
 
-def _comp_tdnn(w, rng, in_dim, out_dim, offsets, bias=True, scale=1.0):
+def _comp_tdnn(w, W, b, offsets):
     _updatable_prefix(w, "TdnnComponent")
     w.tok("<TimeOffsets>"); w.intvec(offsets)
-    k = in_dim * len(offsets)
-    w.tok("<LinearParams>"); w.mat(rng.standard_normal((out_dim, k)).astype(np.float32) * (scale / math.sqrt(k)))
-    w.tok("<BiasParams>"); w.vec(rng.standard_normal(out_dim).astype(np.float32) * 0.1 if bias else np.zeros(0, np.float32))
-    w.tok("<OrthonormalConstraint>"); w.f32(-1.0 if not bias else 0.0)
+    w.tok("<LinearParams>"); w.mat(W)
+    w.tok("<BiasParams>"); w.vec(b if b is not None else np.zeros(0, np.float32))
+    w.tok("<OrthonormalConstraint>"); w.f32(-1.0 if b is None else 0.0)
     w.tok("<UseNaturalGradient>"); w.boolean(True)
     w.tok("<NumSamplesHistory>"); w.f32(2000.0)
     w.tok("<AlphaInOut>"); w.f32(4.0); w.f32(4.0)
@@ -346,10 +487,10 @@ def _comp_tdnn(w, rng, in_dim, out_dim, offsets, bias=True, scale=1.0):
     w.tok("</TdnnComponent>"); w.nl()
 
 
-def _comp_ngaffine(w, rng, in_dim, out_dim, scale=1.0):
+def _comp_ngaffine(w, W, b):
     _updatable_prefix(w, "NaturalGradientAffineComponent")
-    w.tok("<LinearParams>"); w.mat(rng.standard_normal((out_dim, in_dim)).astype(np.float32) * (scale / math.sqrt(in_dim)))
-    w.tok("<BiasParams>"); w.vec(rng.standard_normal(out_dim).astype(np.float32) * 0.1 * scale)
+    w.tok("<LinearParams>"); w.mat(W)
+    w.tok("<BiasParams>"); w.vec(b)
     w.tok("<RankIn>"); w.i32(20)
     w.tok("<RankOut>"); w.i32(80)
     w.tok("<UpdatePeriod>"); w.i32(4)
@@ -358,9 +499,9 @@ def _comp_ngaffine(w, rng, in_dim, out_dim, scale=1.0):
     w.tok("</NaturalGradientAffineComponent>"); w.nl()
 
 
-def _comp_linear(w, rng, in_dim, out_dim):
+def _comp_linear(w, W):
     _updatable_prefix(w, "LinearComponent")
-    w.tok("<Params>"); w.mat(rng.standard_normal((out_dim, in_dim)).astype(np.float32) / math.sqrt(in_dim))
+    w.tok("<Params>"); w.mat(W)
     w.tok("<OrthonormalConstraint>"); w.f32(-1.0)
     w.tok("<UseNaturalGradient>"); w.boolean(True)
     w.tok("<RankInOut>"); w.i32(20); w.i32(80)
@@ -370,15 +511,10 @@ def _comp_linear(w, rng, in_dim, out_dim):
     w.tok("</LinearComponent>"); w.nl()
 
 
-def _comp_fixed_affine(w, rng, in_dim, out_dim, mean=None, std=None):
-    W = rng.standard_normal((out_dim, in_dim)) / math.sqrt(in_dim)
-    b = rng.standard_normal(out_dim) * 0.1
-    if std is not None:      # whiten: W (x - mean) / std
-        W = W / std[None, :]
-        b = b - W @ mean
+def _comp_fixed_affine(w, W, b):
     w.tok("<FixedAffineComponent>")
-    w.tok("<LinearParams>"); w.mat(W.astype(np.float32))
-    w.tok("<BiasParams>"); w.vec(b.astype(np.float32))
+    w.tok("<LinearParams>"); w.mat(W)
+    w.tok("<BiasParams>"); w.vec(b)
     w.tok("</FixedAffineComponent>"); w.nl()
 
 
@@ -393,16 +529,18 @@ def _comp_nonlin(w, typ, dim):
     w.tok("</%s>" % typ); w.nl()
 
 
-def _comp_batchnorm(w, rng, dim):
+def _comp_batchnorm(w, bn):
+    mean, var, eps = bn
+    dim = len(mean)
     w.tok("<BatchNormComponent>")
     w.tok("<Dim>"); w.i32(dim)
     w.tok("<BlockDim>"); w.i32(dim)
-    w.tok("<Epsilon>"); w.f32(0.001)
+    w.tok("<Epsilon>"); w.f32(eps)
     w.tok("<TargetRms>"); w.f32(1.0)
     w.tok("<TestMode>"); w.boolean(False)
     w.tok("<Count>"); w.f64(10000.0)
-    w.tok("<StatsMean>"); w.vec((0.4 + 0.2 * rng.standard_normal(dim)).astype(np.float32))
-    w.tok("<StatsVar>"); w.vec(rng.uniform(0.2, 0.6, dim).astype(np.float32))
+    w.tok("<StatsMean>"); w.vec(mean.astype(np.float32))
+    w.tok("<StatsVar>"); w.vec(var.astype(np.float32))
     w.tok("</BatchNormComponent>"); w.nl()
 
 
@@ -423,63 +561,57 @@ def _comp_noop(w, dim):
     w.tok("</NoOpComponent>"); w.nl()
 
 
-def _write_nnet3(w: KaldiWriter, spec: SynthSpec, rng: np.random.Generator, num_pdfs: int):
-    H, B, D, IV = spec.hidden_dim, spec.bottleneck_dim, spec.num_ceps, spec.ivector_dim
+def _write_nnet3(w: KaldiWriter, spec: SynthSpec, rng: np.random.Generator, num_pdfs: int) -> dict:
+    H, B, D, IV, S = spec.hidden_dim, spec.bottleneck_dim, spec.num_ceps, spec.ivector_dim, spec.prefinal_small
+    P = make_nnet_params(spec, rng, num_pdfs)
     lines = ["input-node name=ivector dim=%d" % IV, "input-node name=input dim=%d" % D]
     comps = []  # (name, writer-callable)
 
     def node(name, inp):
         lines.append("component-node name=%s component=%s input=%s" % (name, name, inp))
 
-    lda_in = 3 * D + IV
-    m1, s1 = mfcc_stats(D)
-    in_mean = np.concatenate([m1, m1, m1, np.zeros(IV)])
-    in_std = np.concatenate([s1, s1, s1, np.ones(IV)])
-    comps.append(("lda", lambda: _comp_fixed_affine(w, rng, lda_in, lda_in, in_mean, in_std * math.sqrt(lda_in) / 8.0)))
+    comps.append(("lda", lambda: _comp_fixed_affine(w, P["lda.W"], P["lda.b"])))
     node("lda", "Append(Offset(input, -1), input, Offset(input, 1), ReplaceIndex(ivector, t, 0))")
-    comps.append(("tdnn1.affine", lambda: _comp_ngaffine(w, rng, lda_in, H)))
+    comps.append(("tdnn1.affine", lambda: _comp_ngaffine(w, P["tdnn1.W"], P["tdnn1.b"])))
     node("tdnn1.affine", "lda")
     comps.append(("tdnn1.relu", lambda: _comp_nonlin(w, "RectifiedLinearComponent", H)))
     node("tdnn1.relu", "tdnn1.affine")
-    comps.append(("tdnn1.batchnorm", lambda: _comp_batchnorm(w, rng, H)))
+    comps.append(("tdnn1.batchnorm", lambda: _comp_batchnorm(w, P["tdnn1.bn"])))
     node("tdnn1.batchnorm", "tdnn1.relu")
     comps.append(("tdnn1.dropout", lambda: _comp_dropout(w, H)))
     node("tdnn1.dropout", "tdnn1.batchnorm")
     prev = "tdnn1.dropout"
-    for li, stride in enumerate(spec.tdnnf_strides):
+    for li, (off1, off2) in enumerate(P["tdnnf_offsets"]):
         n = "tdnnf%d" % (li + 2)
-        off1 = [-stride, 0] if stride else [0]
-        off2 = [0, stride] if stride else [0]
-        comps.append((n + ".linear", lambda o=off1: _comp_tdnn(w, rng, H, B, o, bias=False)))
+        comps.append((n + ".linear", lambda n=n, o=off1: _comp_tdnn(w, P[n + ".lin.W"], None, o)))
         node(n + ".linear", prev)
-        comps.append((n + ".affine", lambda o=off2: _comp_tdnn(w, rng, B, H, o, bias=True, scale=2.0)))
+        comps.append((n + ".affine", lambda n=n, o=off2: _comp_tdnn(w, P[n + ".aff.W"], P[n + ".aff.b"], o)))
         node(n + ".affine", n + ".linear")
         comps.append((n + ".relu", lambda: _comp_nonlin(w, "RectifiedLinearComponent", H)))
         node(n + ".relu", n + ".affine")
-        comps.append((n + ".batchnorm", lambda: _comp_batchnorm(w, rng, H)))
+        comps.append((n + ".batchnorm", lambda n=n: _comp_batchnorm(w, P[n + ".bn"])))
         node(n + ".batchnorm", n + ".relu")
         comps.append((n + ".dropout", lambda: _comp_dropout(w, H)))
         node(n + ".dropout", n + ".batchnorm")
         comps.append((n + ".noop", lambda: _comp_noop(w, H)))
         node(n + ".noop", "Sum(Scale(0.66, %s), %s.dropout)" % (prev, n))
         prev = n + ".noop"
-    S = spec.prefinal_small
-    comps.append(("prefinal-l", lambda: _comp_linear(w, rng, H, S)))
+    comps.append(("prefinal-l", lambda: _comp_linear(w, P["prefinal-l.W"])))
     node("prefinal-l", prev)
     for branch in ("chain", "xent"):
         p = "prefinal-" + branch
-        comps.append((p + ".affine", lambda: _comp_ngaffine(w, rng, S, H, scale=2.0)))
+        comps.append((p + ".affine", lambda p=p: _comp_ngaffine(w, P[p + ".aff.W"], P[p + ".aff.b"])))
         node(p + ".affine", "prefinal-l")
         comps.append((p + ".relu", lambda: _comp_nonlin(w, "RectifiedLinearComponent", H)))
         node(p + ".relu", p + ".affine")
-        comps.append((p + ".batchnorm1", lambda: _comp_batchnorm(w, rng, H)))
+        comps.append((p + ".batchnorm1", lambda p=p: _comp_batchnorm(w, P[p + ".bn1"])))
         node(p + ".batchnorm1", p + ".relu")
-        comps.append((p + ".linear", lambda: _comp_linear(w, rng, H, S)))
+        comps.append((p + ".linear", lambda p=p: _comp_linear(w, P[p + ".lin.W"])))
         node(p + ".linear", p + ".batchnorm1")
-        comps.append((p + ".batchnorm2", lambda: _comp_batchnorm(w, rng, S)))
+        comps.append((p + ".batchnorm2", lambda p=p: _comp_batchnorm(w, P[p + ".bn2"])))
         node(p + ".batchnorm2", p + ".linear")
         out = "output" if branch == "chain" else "output-xent"
-        comps.append((out + ".affine", lambda: _comp_ngaffine(w, rng, S, num_pdfs, scale=spec.output_scale)))
+        comps.append((out + ".affine", lambda out=out: _comp_ngaffine(w, P[out + ".W"], P[out + ".b"])))
         node(out + ".affine", p + ".batchnorm2")
         if branch == "xent" or spec.log_softmax:
             comps.append((out + ".log-softmax", lambda: _comp_nonlin(w, "LogSoftmaxComponent", num_pdfs)))
@@ -503,8 +635,10 @@ def _write_nnet3(w: KaldiWriter, spec: SynthSpec, rng: np.random.Generator, num_
     if spec.priors:
         p = rng.dirichlet(np.full(num_pdfs, 5.0)).astype(np.float32)
         w.vec(p)
+        P["priors"] = p
     else:
         w.vec(np.zeros(0, np.float32))
+    return P
 
 
 # --------------------------------------------------------------------------------------
@@ -764,6 +898,8 @@ class SynthPaths:
     num_pdfs: int
     num_states: int
     num_arcs: int
+    nnet_params: Optional[dict] = None
+    tid2pdf: Optional[np.ndarray] = None
 
 
 def write_graph(graph_dir: str, spec: SynthSpec, hmm: HmmInfo, aligned: bool = False):
@@ -800,7 +936,7 @@ def write_model(root: str, spec: SynthSpec = TINY, aligned_fst: bool = False) ->
 
     w = KaldiWriter(spec.binary)
     hmm = _write_transition_model(w, spec, rng)
-    _write_nnet3(w, spec, rng, hmm.num_pdfs)
+    nnet_params = _write_nnet3(w, spec, rng, hmm.num_pdfs)
     final_mdl = os.path.join(mdl_dir, "final.mdl")
     w.save(final_mdl)
     _write_ivector_extractor(ie_dir, spec, rng, spec.binary)
@@ -829,7 +965,7 @@ def write_model(root: str, spec: SynthSpec = TINY, aligned_fst: bool = False) ->
             f.write("--cmvn-config=%s/online_cmvn.conf\n--global-cmvn-stats=%s/global_cmvn.stats\n" % (conf, ie_dir))
     words, ns, na = write_graph(graph_dir, spec, hmm, aligned=aligned_fst)
     return SynthPaths(model_dir, graph_dir, final_mdl, online_conf, os.path.join(graph_dir, "HCLG.fst"),
-                      os.path.join(graph_dir, "words.txt"), words, hmm.num_pdfs, ns, na)
+                      os.path.join(graph_dir, "words.txt"), words, hmm.num_pdfs, ns, na, nnet_params, hmm.tid2pdf)
 
 
 # --------------------------------------------------------------------------------------
