@@ -1,0 +1,126 @@
+/* rs_b200.h -- C ABI of the B200 batched utterance decoder (librs_b200.so).
+ *
+ * The reference has no FFI on this path: rhasspy-speech reaches the Kaldi decoder through argv and
+ * stdin/stdout of child processes.  Each entry point below names the process-level interface it
+ * replaces (paths relative to the reference checkout); INTEGRATION.md shows the ctypes binding that
+ * rhasspy_speech/transcribe_wav.py and transcribe_stream.py would use instead of tools.async_run*.
+ *
+ * Ownership: the caller owns every input buffer for the duration of the call; the library owns
+ * models, graphs, decoders and device memory until the matching *_free; results are allocated by
+ * the library and released with rs_result_free.  rs_model / rs_graph are immutable and may be
+ * shared by decoders; an rs_decoder (and its streams) must be used from one thread at a time.
+ *
+ * Errors: functions returning a pointer return NULL, functions returning int return non-zero, and
+ * write a NUL-terminated message into `err` (may be NULL).  The Python layer turns that message into
+ * the RuntimeError the reference raises when a Kaldi binary exits non-zero (rhasspy_speech/tools.py:81-88).
+ */
+#ifndef RS_B200_H_
+#define RS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rs_model rs_model;
+typedef struct rs_graph rs_graph;
+typedef struct rs_decoder rs_decoder;
+typedef struct rs_stream rs_stream;
+
+/* Decoder options = the command-line flags rhasspy passes to online2-wav-nnet3-latgen-faster /
+ * online2-cli-nnet3-decode-faster (rhasspy_speech/transcribe_wav.py:47-60, transcribe_stream.py:56-66)
+ * plus LatticeFasterDecoderConfig defaults (kaldi/src/decoder/lattice-faster-decoder.h:38-92). */
+typedef struct rs_decoder_opts {
+  float beam;           /* --beam            (24.0) */
+  int32_t max_active;   /* --max-active      (7000) */
+  int32_t min_active;   /* --min-active      (200)  */
+  float lattice_beam;   /* --lattice-beam    (8.0); lattice output is a "next" row, kept for the surface */
+  float acoustic_scale; /* --acoustic-scale  (1.0; rhasspy always passes 1.0 to the decoder) */
+  float beam_delta;     /* --beam-delta      (0.5)  */
+  int32_t max_tokens_per_frame; /* device capacity per lane and frame (65536) */
+  int32_t max_tokens_per_utt;   /* traceback arena per lane (4194304) */
+  int32_t max_words;            /* word ids returned per hypothesis (256) */
+  int32_t num_lanes;            /* resident decoder CTAs; 0 = 2 per SM */
+  uint32_t dither_seed;         /* only used when mfcc.conf asks for dither */
+} rs_decoder_opts;
+
+typedef struct rs_result {
+  int32_t n_utts;
+  int32_t *n_hyp;        /* [n_utts] hypotheses per utterance: 0 (nothing decoded) or 1 */
+  int32_t *word_offset;  /* [n_utts + 1] into word_ids */
+  int32_t *word_ids;     /* olabels of the best path, in order (words.txt ids) */
+  float *graph_cost;     /* [n_utts] */
+  float *acoustic_cost;  /* [n_utts] */
+  int32_t *num_frames;   /* [n_utts] decoded (subsampled) frames */
+  int32_t *status;       /* [n_utts] 0 ok; bit0 token capacity, bit1 arena capacity, bit2 no surviving tokens, bit3 word capacity */
+} rs_result;
+
+typedef struct rs_timings {
+  float h2d_ms, feature_ms, nnet_ms, decode_ms, d2h_ms, total_ms; /* CUDA-event times of the last call */
+  double audio_seconds;
+  uint64_t frames_decoded, tokens_expanded, arcs_visited, tokens_created, records_written;
+  uint64_t nnet_flops;    /* algorithmic FLOPs of the acoustic model for the last batch */
+  uint64_t h2d_bytes, d2h_bytes;
+  int32_t kernel_launches;
+} rs_timings;
+
+void rs_decoder_opts_default(rs_decoder_opts *opts);
+
+/* Replaces the per-process model load of online2-wav-nnet3-latgen-faster.cc:150-181 (feature
+ * pipeline info from --config=online.conf, TransitionModel + AmNnetSimple from final.mdl). */
+rs_model *rs_model_load(const char *final_mdl, const char *online_conf, int device, char *err, size_t errlen);
+void rs_model_free(rs_model *m);
+int rs_model_info(const rs_model *m, int32_t *num_pdfs, int32_t *frame_subsampling_factor, int32_t *ivector_dim,
+                  int32_t *feat_dim, int32_t *left_context, int32_t *right_context);
+
+/* Replaces ReadFstKaldiGeneric(HCLG.fst) (online2-wav-nnet3-latgen-faster.cc:181) and the
+ * --word-symbol-table=words.txt argument. */
+rs_graph *rs_graph_load(const char *hclg_fst, const char *words_txt, int device, char *err, size_t errlen);
+void rs_graph_free(rs_graph *g);
+int rs_graph_info(const rs_graph *g, int32_t *num_states, int64_t *num_arcs, int32_t *num_words);
+/* words.txt lookup (utils/int2sym.pl -f 2- words.txt, transcribe_wav.py:77-85); NULL if unknown */
+const char *rs_graph_word(const rs_graph *g, int32_t id);
+
+rs_decoder *rs_decoder_create(rs_model *m, rs_graph *g, const rs_decoder_opts *opts, char *err, size_t errlen);
+void rs_decoder_free(rs_decoder *d);
+
+/* Replaces one run of `online2-wav-nnet3-latgen-faster --online=false ... | lattice-to-nbest --n=1 |
+ * nbest-to-linear` per utterance (transcribe_wav.py:45-75), for n utterances at once.
+ * pcm[i] = 16 kHz mono s16 samples, unscaled as WaveData reads them (feat/wave-reader.cc:153-320). */
+int rs_decode_pcm(rs_decoder *d, const int16_t *const *pcm, const int32_t *num_samples, int32_t n, rs_result **out,
+                  char *err, size_t errlen);
+/* Same, reading RIFF/WAVE PCM16 files ('scp:echo utt WAV|', transcribe_wav.py:59). A sampling-rate
+ * mismatch is an error as in the reference (feat/online-feature.cc:98-103). */
+int rs_decode_wavs(rs_decoder *d, const char *const *paths, int32_t n, rs_result **out, char *err, size_t errlen);
+/* Stage (iii) only, over caller-provided log-likelihood matrices [num_frames[i] x num_pdfs]: what
+ * latgen-faster-mapped does (kaldi/src/bin/latgen-faster-mapped.cc); used by the parity tests. */
+int rs_decode_loglikes(rs_decoder *d, const float *const *loglikes, const int32_t *num_frames, int32_t n,
+                       rs_result **out, char *err, size_t errlen);
+void rs_result_free(rs_result *r);
+
+/* Streaming surface (online2-cli-nnet3-decode-faster fed raw s16le on stdin,
+ * transcribe_stream.py:51-82).  Audio is buffered; the utterance is decoded at finish. */
+rs_stream *rs_stream_open(rs_decoder *d, char *err, size_t errlen);
+int rs_stream_accept(rs_stream *s, const int16_t *pcm, int32_t num_samples, char *err, size_t errlen);
+int rs_stream_finish(rs_stream *s, rs_result **out, char *err, size_t errlen);
+void rs_stream_close(rs_stream *s);
+/* Finish many streams of one decoder in a single batch. */
+int rs_streams_finish(rs_stream *const *streams, int32_t n, rs_result **out, char *err, size_t errlen);
+
+/* Instrumentation of the last decode call on this decoder. */
+int rs_decoder_timings(const rs_decoder *d, rs_timings *t);
+/* Intermediate results of the last rs_decode_pcm / rs_decode_wavs call, for the parity tests:
+ * what = 0 MFCC [T x dim], 1 iVector [1 x dim], 2 log-likelihoods [T/sf x num_pdfs],
+ *        3 CMVN-normalised MFCC, 4 LDA features (normalised stream).
+ * Call with dst == NULL to query rows/cols. */
+int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t *rows, int32_t *cols, char *err,
+                   size_t errlen);
+/* Text description of the compiled acoustic-model plan (one line per launch). */
+const char *rs_model_plan(const rs_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_B200_H_ */

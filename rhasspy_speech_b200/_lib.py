@@ -1,0 +1,280 @@
+"""ctypes binding of librs_b200.so (C ABI in include/rs_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+Python or CPU fallback: if the library is missing, or CUDA is unavailable when a model is loaded,
+the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librs_b200.so")
+
+ERRLEN = 2048
+
+
+class DecoderOpts(C.Structure):
+    _fields_ = [("beam", C.c_float), ("max_active", C.c_int32), ("min_active", C.c_int32), ("lattice_beam", C.c_float),
+                ("acoustic_scale", C.c_float), ("beam_delta", C.c_float), ("max_tokens_per_frame", C.c_int32),
+                ("max_tokens_per_utt", C.c_int32), ("max_words", C.c_int32), ("num_lanes", C.c_int32),
+                ("dither_seed", C.c_uint32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_utts", C.c_int32), ("n_hyp", C.POINTER(C.c_int32)), ("word_offset", C.POINTER(C.c_int32)),
+                ("word_ids", C.POINTER(C.c_int32)), ("graph_cost", C.POINTER(C.c_float)),
+                ("acoustic_cost", C.POINTER(C.c_float)), ("num_frames", C.POINTER(C.c_int32)),
+                ("status", C.POINTER(C.c_int32))]
+
+
+class Timings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("feature_ms", C.c_float), ("nnet_ms", C.c_float), ("decode_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("audio_seconds", C.c_double),
+                ("frames_decoded", C.c_uint64), ("tokens_expanded", C.c_uint64), ("arcs_visited", C.c_uint64),
+                ("tokens_created", C.c_uint64), ("records_written", C.c_uint64), ("nnet_flops", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/rs_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_ERR = [C.c_char_p, C.c_size_t]
+SYMBOLS = [
+    ("rs_decoder_opts_default", None, [C.POINTER(DecoderOpts)]),
+    ("rs_model_load", _P, [C.c_char_p, C.c_char_p, C.c_int] + _ERR),
+    ("rs_model_free", None, [_P]),
+    ("rs_model_info", C.c_int, [_P] + [C.POINTER(C.c_int32)] * 6),
+    ("rs_graph_load", _P, [C.c_char_p, C.c_char_p, C.c_int] + _ERR),
+    ("rs_graph_free", None, [_P]),
+    ("rs_graph_info", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    ("rs_graph_word", C.c_char_p, [_P, C.c_int32]),
+    ("rs_decoder_create", _P, [_P, _P, C.POINTER(DecoderOpts)] + _ERR),
+    ("rs_decoder_free", None, [_P]),
+    ("rs_decode_pcm", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
+    ("rs_decode_wavs", C.c_int, [_P, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
+    ("rs_decode_loglikes", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
+    ("rs_result_free", None, [C.POINTER(Result)]),
+    ("rs_stream_open", _P, [_P] + _ERR),
+    ("rs_stream_accept", C.c_int, [_P, C.c_void_p, C.c_int32] + _ERR),
+    ("rs_stream_finish", C.c_int, [_P, C.POINTER(C.POINTER(Result))] + _ERR),
+    ("rs_stream_close", None, [_P]),
+    ("rs_streams_finish", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
+    ("rs_decoder_timings", C.c_int, [_P, C.POINTER(Timings)]),
+    ("rs_debug_fetch", C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + _ERR),
+    ("rs_model_plan", C.c_char_p, [_P]),
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class RsError(RuntimeError):
+    pass
+
+
+def _check(ok: bool, err):
+    if not ok:
+        raise RsError(err.value.decode(errors="replace"))
+
+
+class Hypotheses:
+    """Python copy of an rs_result."""
+
+    def __init__(self, r: Result):
+        n = r.n_utts
+        self.n_utts = n
+        off = np.ctypeslib.as_array(r.word_offset, shape=(n + 1,)).copy() if n else np.zeros(1, np.int32)
+        total = int(off[-1])
+        ids = np.ctypeslib.as_array(r.word_ids, shape=(max(total, 1),))[:total].copy()
+        self.n_hyp = np.ctypeslib.as_array(r.n_hyp, shape=(max(n, 1),))[:n].copy()
+        self.words: List[Optional[List[int]]] = []
+        for u in range(n):
+            self.words.append([int(x) for x in ids[off[u]:off[u + 1]]] if self.n_hyp[u] else None)
+        self.graph_cost = np.ctypeslib.as_array(r.graph_cost, shape=(max(n, 1),))[:n].copy()
+        self.acoustic_cost = np.ctypeslib.as_array(r.acoustic_cost, shape=(max(n, 1),))[:n].copy()
+        self.num_frames = np.ctypeslib.as_array(r.num_frames, shape=(max(n, 1),))[:n].copy()
+        self.status = np.ctypeslib.as_array(r.status, shape=(max(n, 1),))[:n].copy()
+
+
+class Model:
+    def __init__(self, final_mdl: str, online_conf: str, device: int = 0):
+        self.lib = load_library()
+        err = C.create_string_buffer(ERRLEN)
+        self.h = self.lib.rs_model_load(os.fsencode(final_mdl), os.fsencode(online_conf), device, err, ERRLEN)
+        _check(bool(self.h), err)
+        vals = [C.c_int32() for _ in range(6)]
+        self.lib.rs_model_info(self.h, *[C.byref(v) for v in vals])
+        (self.num_pdfs, self.frame_subsampling_factor, self.ivector_dim, self.feat_dim, self.left_context,
+         self.right_context) = [v.value for v in vals]
+        self.device = device
+
+    def plan(self) -> str:
+        return self.lib.rs_model_plan(self.h).decode()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_model_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Graph:
+    def __init__(self, hclg_fst: str, words_txt: Optional[str], device: int = 0):
+        self.lib = load_library()
+        err = C.create_string_buffer(ERRLEN)
+        self.h = self.lib.rs_graph_load(os.fsencode(hclg_fst), os.fsencode(words_txt) if words_txt else None, device, err, ERRLEN)
+        _check(bool(self.h), err)
+        ns, na, nw = C.c_int32(), C.c_int64(), C.c_int32()
+        self.lib.rs_graph_info(self.h, C.byref(ns), C.byref(na), C.byref(nw))
+        self.num_states, self.num_arcs, self.num_words = ns.value, na.value, nw.value
+
+    def word(self, i: int) -> Optional[str]:
+        w = self.lib.rs_graph_word(self.h, i)
+        return w.decode() if w is not None else None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_graph_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Decoder:
+    def __init__(self, model: Model, graph: Graph, **opts):
+        self.lib = load_library()
+        self.model, self.graph = model, graph
+        o = DecoderOpts()
+        self.lib.rs_decoder_opts_default(C.byref(o))
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError("unknown decoder option " + k)
+            setattr(o, k, v)
+        self.opts = o
+        err = C.create_string_buffer(ERRLEN)
+        self.h = self.lib.rs_decoder_create(model.h, graph.h, C.byref(o), err, ERRLEN)
+        _check(bool(self.h), err)
+
+    def _take(self, rc: int, res, err) -> Hypotheses:
+        _check(rc == 0, err)
+        try:
+            return Hypotheses(res.contents)
+        finally:
+            self.lib.rs_result_free(res)
+
+    def decode_pcm(self, pcm: Sequence[np.ndarray]) -> Hypotheses:
+        arrs = [np.ascontiguousarray(p, dtype=np.int16) for p in pcm]
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        ns = (C.c_int32 * max(n, 1))(*[a.size for a in arrs])
+        res = C.POINTER(Result)()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_decode_pcm(self.h, ptrs, ns, n, C.byref(res), err, ERRLEN)
+        return self._take(rc, res, err)
+
+    def decode_wavs(self, paths: Sequence[str]) -> Hypotheses:
+        n = len(paths)
+        arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+        res = C.POINTER(Result)()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_decode_wavs(self.h, arr, n, C.byref(res), err, ERRLEN)
+        return self._take(rc, res, err)
+
+    def decode_loglikes(self, loglikes: Sequence[np.ndarray]) -> Hypotheses:
+        arrs = [np.ascontiguousarray(m, dtype=np.float32) for m in loglikes]
+        for a in arrs:
+            if a.ndim != 2 or a.shape[1] != self.model.num_pdfs:
+                raise ValueError("log-likelihood matrices must be [frames x %d]" % self.model.num_pdfs)
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        ns = (C.c_int32 * max(n, 1))(*[a.shape[0] for a in arrs])
+        res = C.POINTER(Result)()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_decode_loglikes(self.h, ptrs, ns, n, C.byref(res), err, ERRLEN)
+        return self._take(rc, res, err)
+
+    def timings(self) -> dict:
+        t = Timings()
+        self.lib.rs_decoder_timings(self.h, C.byref(t))
+        return t.as_dict()
+
+    def fetch(self, what: int, utt: int) -> np.ndarray:
+        """0 MFCC, 1 iVector, 2 log-likelihoods, 3 normalised MFCC, 4 LDA features of the last call."""
+        r, c = C.c_int32(), C.c_int32()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_debug_fetch(self.h, what, utt, None, C.byref(r), C.byref(c), err, ERRLEN)
+        _check(rc == 0, err)
+        out = np.zeros((r.value, c.value), dtype=np.float32)
+        if out.size:
+            rc = self.lib.rs_debug_fetch(self.h, what, utt, out.ctypes.data, C.byref(r), C.byref(c), err, ERRLEN)
+            _check(rc == 0, err)
+        return out
+
+    def open_stream(self) -> "Stream":
+        return Stream(self)
+
+    def finish_streams(self, streams: Sequence["Stream"]) -> Hypotheses:
+        n = len(streams)
+        arr = (C.c_void_p * max(n, 1))(*[s.h for s in streams])
+        res = C.POINTER(Result)()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_streams_finish(arr, n, C.byref(res), err, ERRLEN)
+        return self._take(rc, res, err)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_decoder_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Stream:
+    def __init__(self, dec: Decoder):
+        self.dec = dec
+        err = C.create_string_buffer(ERRLEN)
+        self.h = dec.lib.rs_stream_open(dec.h, err, ERRLEN)
+        _check(bool(self.h), err)
+
+    def accept(self, chunk: bytes):
+        n = len(chunk) // 2
+        err = C.create_string_buffer(ERRLEN)
+        buf = (C.c_char * len(chunk)).from_buffer_copy(chunk) if chunk else None
+        rc = self.dec.lib.rs_stream_accept(self.h, C.cast(buf, C.c_void_p) if buf is not None else None, n, err, ERRLEN)
+        _check(rc == 0, err)
+
+    def finish(self) -> Hypotheses:
+        res = C.POINTER(Result)()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.dec.lib.rs_stream_finish(self.h, C.byref(res), err, ERRLEN)
+        return self.dec._take(rc, res, err)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.dec.lib.rs_stream_close(self.h)
+            self.h = None
+
+    __del__ = close

@@ -1,0 +1,1251 @@
+// Host engine + C ABI (include/rs_b200.h): uploads the model tables, lays a batch of utterances out
+// on the global time axis, launches the three stages on one CUDA stream and returns word ids.
+// There is no CPU fallback: every entry point fails loudly if CUDA is unavailable.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "../../include/rs_b200.h"
+#include "engine.h"
+#include "model.h"
+
+namespace rs {
+
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) RS_FAIL("CUDA error: " << cudaGetErrorString(e_) << " at " << #expr); \
+  } while (0)
+
+struct DevBuf {  // grow-only device allocation
+  void *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  void *ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (p) CUDA_OK(cudaFree(p));
+      p = nullptr;
+      size_t want = bytes + bytes / 8 + 256;
+      CUDA_OK(cudaMalloc(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+  template <typename T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  void *ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (p) CUDA_OK(cudaFreeHost(p));
+      p = nullptr;
+      size_t want = bytes + bytes / 8 + 256;
+      CUDA_OK(cudaMallocHost(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+};
+
+template <typename T>
+static T *Upload(const std::vector<T> &v, std::vector<void *> *owned) {
+  void *d = nullptr;
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  CUDA_OK(cudaMalloc(&d, bytes));
+  if (!v.empty()) CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  owned->push_back(d);
+  return reinterpret_cast<T *>(d);
+}
+
+// --------------------------------------------------------------------------------------------
+// feature tables, built with the reference's float expressions (host libm, no FMA contraction):
+// feature-window.cc:109-135, srfft.cc:77-118 / 180-204 / 356-375, mel-computations.cc:33-142,
+// matrix-functions.cc:592-608, mel-computations.cc:253-259.
+struct FeatTables {
+  std::vector<float> window, twiddle, kn, mel_weights, dct, lifter;
+  std::vector<uint16_t> level_offsets, perm;
+  int level_start[12] = {0}, level_count[12] = {0}, twiddle_start[12] = {0};
+  std::vector<int> mel_offset, mel_len, mel_start;
+  int logn = 0;
+};
+
+static void CollectBlocks(int offset, int logn, std::vector<std::vector<uint16_t>> *levels) {
+  if (logn < 1) return;
+  (*levels)[logn].push_back((uint16_t)offset);
+  if (logn < 3) return;
+  int m = 1 << logn;
+  CollectBlocks(offset, logn - 1, levels);
+  CollectBlocks(offset + m / 2, logn - 2, levels);
+  CollectBlocks(offset + 3 * (m / 4), logn - 2, levels);
+}
+
+static void BuildFeatTables(const MfccOptions &o, FeatTables *t) {
+  const int L = o.WindowSize(), N = o.PaddedWindowSize(), NH = N / 2;
+  if (N > 1024 || N < 16) RS_FAIL("unsupported FFT size " << N);
+  if (o.window_type != "povey" && o.window_type != "hamming" && o.window_type != "hanning" && o.window_type != "rectangular")
+    RS_FAIL("unsupported window type " << o.window_type);
+  t->window.resize(L);
+  const double a = 6.283185307179586476925286766559005 / (L - 1);
+  for (int i = 0; i < L; i++) {
+    double x = (double)i;
+    double w = 1.0;
+    if (o.window_type == "povey") w = pow(0.5 - 0.5 * cos(a * x), 0.85);
+    else if (o.window_type == "hamming") w = 0.54 - 0.46 * cos(a * x);
+    else if (o.window_type == "hanning") w = 0.5 - 0.5 * cos(a * x);
+    t->window[i] = (float)w;
+  }
+  int logn = 0;
+  while ((1 << logn) < NH) logn++;
+  t->logn = logn;
+  std::vector<std::vector<uint16_t>> levels(12);
+  CollectBlocks(0, logn, &levels);
+  for (int lv = 0; lv < 12; lv++) {
+    t->level_start[lv] = (int)t->level_offsets.size();
+    t->level_count[lv] = (int)levels[lv].size();
+    t->level_offsets.insert(t->level_offsets.end(), levels[lv].begin(), levels[lv].end());
+  }
+  const double M_2PI_ = 6.283185307179586476925286766559005;
+  for (int lv = 4; lv <= logn; lv++) {
+    int m = 1 << lv, m4 = m / 4, m8 = m / 8, nel = m4 - 2;
+    t->twiddle_start[lv] = (int)t->twiddle.size();
+    std::vector<float> tab(6 * nel);
+    int k = 0;
+    for (int n = 1; n < m4; n++) {
+      if (n == m8) continue;
+      float ang = n * M_2PI_ / m;
+      float c = std::cos(ang), s = std::sin(ang);
+      tab[k] = c;
+      tab[nel + k] = -(s + c);
+      tab[2 * nel + k] = s - c;
+      ang = 3 * n * M_2PI_ / m;
+      c = std::cos(ang);
+      s = std::sin(ang);
+      tab[3 * nel + k] = c;
+      tab[4 * nel + k] = -(s + c);
+      tab[5 * nel + k] = s - c;
+      k++;
+    }
+    t->twiddle.insert(t->twiddle.end(), tab.begin(), tab.end());
+  }
+  {  // bit-reversal: replay the reference's swap sequence on an index vector
+    int lg2 = logn >> 1;
+    if (logn & 1) lg2++;
+    std::vector<int> brseed(1 << lg2, 0);
+    brseed[0] = 0;
+    if (brseed.size() > 1) brseed[1] = 1;
+    for (int j = 2; j <= lg2; j++) {
+      int imax = 1 << (j - 1);
+      for (int i = 0; i < imax; i++) {
+        brseed[i] <<= 1;
+        brseed[i + imax] = brseed[i] + 1;
+      }
+    }
+    std::vector<int> perm(NH);
+    for (int i = 0; i < NH; i++) perm[i] = i;
+    lg2 = logn >> 1;
+    int n = 1 << lg2;
+    for (int off = 1; off < n; off++) {
+      int fj = n * brseed[off], i = off, j = fj;
+      std::swap(perm[i], perm[j]);
+      int xp = i;
+      for (int gno = 1; gno < brseed[off]; gno++) {
+        xp += n;
+        j = fj + brseed[gno];
+        std::swap(perm[xp], perm[j]);
+      }
+    }
+    t->perm.assign(perm.begin(), perm.end());
+  }
+  {  // real-FFT twiddles: kN *= rootN in float (ComplexMul)
+    float x = (float)(M_2PI_ / N * -1);
+    float rre = std::cos(x), rim = std::sin(x);
+    float kre = 1.0f, kim = 0.0f;
+    for (int k = 1; 2 * k <= NH; k++) {
+      float tre = (kre * rre) - (kim * rim);
+      kim = kre * rim + kim * rre;
+      kre = tre;
+      t->kn.push_back(kre);
+      t->kn.push_back(kim);
+    }
+  }
+  {  // mel banks
+    float sample_freq = o.samp_freq, nyquist = 0.5f * sample_freq;
+    float low_freq = o.low_freq, high_freq = o.high_freq > 0.0f ? o.high_freq : nyquist + o.high_freq;
+    if (low_freq < 0.0 || low_freq >= nyquist || high_freq <= 0.0 || high_freq > nyquist || high_freq <= low_freq)
+      RS_FAIL("bad mel options: low-freq " << low_freq << " high-freq " << high_freq);
+    float fft_bin_width = sample_freq / N;
+    auto mel = [](float f) -> float { return 1127.0f * logf(1.0f + f / 700.0f); };
+    float mel_low = mel(low_freq), mel_high = mel(high_freq);
+    float delta = (mel_high - mel_low) / (o.num_bins + 1);
+    for (int b = 0; b < o.num_bins; b++) {
+      float left = mel_low + b * delta, center = mel_low + (b + 1) * delta, right = mel_low + (b + 2) * delta;
+      std::vector<float> w(NH, 0.f);
+      int first = -1, last = -1;
+      for (int i = 0; i < NH; i++) {
+        float freq = fft_bin_width * i;
+        float m = mel(freq);
+        if (m > left && m < right) {
+          float weight;
+          if (m <= center) weight = (m - left) / (center - left);
+          else weight = (right - m) / (right - center);
+          w[i] = weight;
+          if (first == -1) first = i;
+          last = i;
+        }
+      }
+      if (first < 0) RS_FAIL("--num-mel-bins is too large for this window");
+      t->mel_offset.push_back(first);
+      t->mel_len.push_back(last + 1 - first);
+      t->mel_start.push_back((int)t->mel_weights.size());
+      t->mel_weights.insert(t->mel_weights.end(), w.begin() + first, w.begin() + last + 1);
+    }
+  }
+  {
+    int K = o.num_ceps, Nb = o.num_bins;
+    t->dct.assign((size_t)K * Nb, 0.f);
+    float normalizer = std::sqrt(1.0 / static_cast<float>(Nb));
+    for (int j = 0; j < Nb; j++) t->dct[j] = normalizer;
+    normalizer = std::sqrt(2.0 / static_cast<float>(Nb));
+    for (int k = 1; k < K; k++)
+      for (int n = 0; n < Nb; n++)
+        t->dct[(size_t)k * Nb + n] = normalizer * std::cos(static_cast<double>(M_PI) / Nb * (n + 0.5) * k);
+    if (o.cepstral_lifter != 0.0f) {
+      float Q = o.cepstral_lifter;
+      for (int i = 0; i < K; i++) t->lifter.push_back(1.0 + 0.5 * Q * sin(M_PI * i / Q));
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+struct ModelImpl {
+  Model m;
+  int device = 0;
+  std::vector<void *> owned;
+  std::string plan_text;
+  // features
+  FeatTables ft;
+  FeatParams feat{};  // table pointers filled, batch pointers per call
+  // ivector
+  IvecParams ivec{};
+  const double *d_global_cmvn = nullptr, *d_nnet_global_cmvn = nullptr;
+  // nnet
+  std::vector<const float *> d_matrices, d_vectors;
+  uint64_t flops_per_axis_unit = 0;  // sum over gemm steps of 2*n*ktot/step (per time unit of the axis)
+  ~ModelImpl() {
+    for (void *p : owned) cudaFree(p);
+  }
+};
+
+struct GraphImpl {
+  Graph g;
+  int device = 0;
+  std::vector<void *> owned;
+  DevGraph dev{};
+  ~GraphImpl() {
+    for (void *p : owned) cudaFree(p);
+  }
+};
+
+struct StreamImpl;
+
+struct DecoderImpl {
+  ModelImpl *model = nullptr;
+  GraphImpl *graph = nullptr;
+  rs_decoder_opts opts{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_lanes = 0;
+  std::vector<void *> owned;
+  DevBuf d_pcm, d_desc, d_mfcc, d_mfcc_norm, d_xraw, d_xnorm, d_post_idx, d_post_w, d_wf, d_gw, d_linear, d_quad;
+  DevBuf d_out;  // decode outputs
+  std::vector<DevBuf> slots;
+  DevBuf d_tid_pdf;
+  DevBuf d_loglikes_ext;
+  PinBuf h_in, h_out;
+  LaneWorkspace *d_lanes = nullptr;
+  int *d_next_utt = nullptr;
+  std::vector<int4> earc_with_pdf;  // graph arcs with ilabel mapped to pdf for this model
+  const int4 *d_earc = nullptr;
+  rs_timings last{};
+  // layout of the last batch (for rs_debug_fetch)
+  struct Batch {
+    int n = 0, total_frames = 0, axis_len = 0;
+    std::vector<int> num_frames, frame_offset, origin, n_out, ll_row0;
+    bool from_loglikes = false;
+    const float *loglikes = nullptr;
+    int ll_ld = 0;
+  } batch;
+  ~DecoderImpl() {
+    for (void *p : owned) cudaFree(p);
+    for (auto &e : ev)
+      if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+struct StreamImpl {
+  DecoderImpl *dec;
+  std::vector<int16_t> pcm;
+};
+
+static int RoundUp(int x, int m) { return (x + m - 1) / m * m; }
+
+static void UploadModel(ModelImpl *mi) {
+  Model &m = mi->m;
+  auto &own = mi->owned;
+  // --- features
+  BuildFeatTables(m.mfcc, &mi->ft);
+  FeatTables &t = mi->ft;
+  FeatParams &f = mi->feat;
+  f.shift = m.mfcc.WindowShift();
+  f.length = m.mfcc.WindowSize();
+  f.padded = m.mfcc.PaddedWindowSize();
+  f.logn = t.logn;
+  f.preemph = m.mfcc.preemph_coeff;
+  f.dither = m.mfcc.dither;
+  f.energy_floor = m.mfcc.energy_floor;
+  f.remove_dc = m.mfcc.remove_dc_offset;
+  f.use_energy = m.mfcc.use_energy;
+  f.raw_energy = m.mfcc.raw_energy;
+  f.num_bins = m.mfcc.num_bins;
+  f.num_ceps = m.mfcc.num_ceps;
+  f.window = Upload(t.window, &own);
+  f.level_offsets = Upload(t.level_offsets, &own);
+  memcpy(f.level_start, t.level_start, sizeof(f.level_start));
+  memcpy(f.level_count, t.level_count, sizeof(f.level_count));
+  f.twiddle = Upload(t.twiddle, &own);
+  memcpy(f.twiddle_start, t.twiddle_start, sizeof(f.twiddle_start));
+  f.perm = Upload(t.perm, &own);
+  f.kn = Upload(t.kn, &own);
+  f.mel_offset = Upload(t.mel_offset, &own);
+  f.mel_len = Upload(t.mel_len, &own);
+  f.mel_start = Upload(t.mel_start, &own);
+  f.mel_weights = Upload(t.mel_weights, &own);
+  f.dct = Upload(t.dct, &own);
+  f.lifter = t.lifter.empty() ? nullptr : Upload(t.lifter, &own);
+  // --- ivector
+  if (m.has_ivector) {
+    IvecParams &iv = mi->ivec;
+    const int D = m.mfcc.num_ceps, ns = m.ivec.splice_left + 1 + m.ivec.splice_right, K = D * ns;
+    iv.dim = D;
+    iv.left = m.ivec.splice_left;
+    iv.right = m.ivec.splice_right;
+    iv.ldim = m.lda.rows;
+    std::vector<float> lda_t((size_t)K * iv.ldim), lda_bias;
+    for (int j = 0; j < iv.ldim; j++)
+      for (int k = 0; k < K; k++) lda_t[(size_t)k * iv.ldim + j] = m.lda(j, k);
+    if (m.lda.cols == K + 1)
+      for (int j = 0; j < iv.ldim; j++) lda_bias.push_back(m.lda(j, K));
+    iv.lda_t = Upload(lda_t, &own);
+    iv.lda_bias = lda_bias.empty() ? nullptr : Upload(lda_bias, &own);
+    const int G = m.ubm.num_gauss;
+    if (G > 32 * 64) RS_FAIL("UBMs with more than 2048 Gaussians are not supported");
+    if (m.ivec.num_gselect > 8) RS_FAIL("--num-gselect > 8 is not supported");
+    iv.num_gauss = G;
+    iv.gconsts = Upload(m.ubm.gconsts, &own);
+    std::vector<float> mt((size_t)iv.ldim * G), vt((size_t)iv.ldim * G);
+    for (int g = 0; g < G; g++)
+      for (int d = 0; d < iv.ldim; d++) {
+        mt[(size_t)d * G + g] = m.ubm.means_invvars(g, d);
+        vt[(size_t)d * G + g] = m.ubm.inv_vars(g, d);
+      }
+    iv.means_invvars_t = Upload(mt, &own);
+    iv.inv_vars_t = Upload(vt, &own);
+    iv.num_gselect = m.ivec.num_gselect;
+    iv.min_post = m.ivec.min_post;
+    iv.posterior_scale = m.ivec.posterior_scale;
+    iv.ivector_dim = m.ie.ivector_dim;
+    iv.sigma_inv_m = Upload(m.ie.sigma_inv_m, &own);
+    iv.u = Upload(m.ie.u, &own);
+    iv.prior_offset = m.ie.prior_offset;
+    iv.max_count = m.ivec.max_count;
+    iv.num_cg_iters = m.ivec.num_cg_iters;
+    iv.online_cmvn_iextractor = m.ivec.online_cmvn_iextractor;
+    mi->d_global_cmvn = Upload(m.global_cmvn.d, &own);
+  }
+  if (m.nnet_cmvn) mi->d_nnet_global_cmvn = Upload(m.nnet_global_cmvn.d, &own);
+  // --- nnet: fold "subtract log-prior, apply acoustic scale" (decodable-online-looped.cc:218-223) into
+  // the epilogue of the step that writes the output buffer
+  Plan &pl = m.plan;
+  for (int si = (int)pl.steps.size() - 1; si >= 0; si--)
+    if (pl.steps[si].out == pl.output_buffer) {
+      if (!m.log_priors.empty()) {
+        std::vector<float> neg(m.log_priors.size());
+        for (size_t i = 0; i < neg.size(); i++) neg[i] = -m.log_priors[i];
+        pl.vectors.push_back(neg);
+        EpiOp op;
+        op.type = EpiOp::kBias;
+        op.vec0 = (int)pl.vectors.size() - 1;
+        pl.steps[si].ops.push_back(op);
+      }
+      if (m.acoustic_scale != 1.0f) {
+        EpiOp op;
+        op.type = EpiOp::kScale;
+        op.alpha = m.acoustic_scale;
+        pl.steps[si].ops.push_back(op);
+      }
+      break;
+    }
+  for (const auto &mat : pl.matrices) mi->d_matrices.push_back(Upload(mat.d, &own));
+  for (const auto &v : pl.vectors) mi->d_vectors.push_back(Upload(v, &own));
+  for (const Step &st : pl.steps) {
+    if ((int)st.slabs.size() > kMaxSlabs) RS_FAIL("layer " << st.name << " has too many input blocks");
+    if ((int)st.ops.size() > kMaxOps) RS_FAIL("layer " << st.name << " has too many fused operations");
+    if (st.type == Step::kGemm) {
+      uint64_t k = 0;
+      for (const auto &s : st.slabs) k += s.k;
+      mi->flops_per_axis_unit += 2ull * st.n * k * 1000 / pl.buffers[st.out].step;  // x1000 fixed point
+    }
+  }
+  mi->plan_text = DescribePlan(pl);
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+static void SetErr(char *err, size_t errlen, const std::string &msg) {
+  if (err && errlen) {
+    size_t n = std::min(errlen - 1, msg.size());
+    memcpy(err, msg.data(), n);
+    err[n] = 0;
+  }
+}
+
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END(ret)                          \
+  }                                                 \
+  catch (const std::exception &e) {                 \
+    SetErr(err, errlen, e.what());                  \
+    return ret;                                     \
+  }
+
+extern "C" {
+
+void rs_decoder_opts_default(rs_decoder_opts *o) {
+  o->beam = 24.0f;
+  o->max_active = 7000;
+  o->min_active = 200;
+  o->lattice_beam = 8.0f;
+  o->acoustic_scale = 1.0f;
+  o->beam_delta = 0.5f;
+  o->max_tokens_per_frame = 65536;
+  o->max_tokens_per_utt = 4194304;
+  o->max_words = 256;
+  o->num_lanes = 0;
+  o->dither_seed = 0;
+}
+
+rs_model *rs_model_load(const char *final_mdl, const char *online_conf, int device, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    RS_FAIL("no CUDA device available: this library has no CPU path");
+  if (device < 0 || device >= ndev) RS_FAIL("CUDA device " << device << " does not exist (" << ndev << " visible)");
+  CUDA_OK(cudaSetDevice(device));
+  std::unique_ptr<ModelImpl> mi(new ModelImpl());
+  mi->device = device;
+  LoadModel(final_mdl, online_conf, &mi->m);
+  UploadModel(mi.get());
+  return reinterpret_cast<rs_model *>(mi.release());
+  API_GUARD_END(nullptr)
+}
+
+void rs_model_free(rs_model *m) { delete reinterpret_cast<ModelImpl *>(m); }
+
+int rs_model_info(const rs_model *m_, int32_t *num_pdfs, int32_t *sf, int32_t *ivector_dim, int32_t *feat_dim,
+                  int32_t *left_context, int32_t *right_context) {
+  const ModelImpl *mi = reinterpret_cast<const ModelImpl *>(m_);
+  if (!mi) return 1;
+  if (num_pdfs) *num_pdfs = mi->m.trans.num_pdfs;
+  if (sf) *sf = mi->m.frame_subsampling_factor;
+  if (ivector_dim) *ivector_dim = mi->m.has_ivector ? mi->m.ie.ivector_dim : 0;
+  if (feat_dim) *feat_dim = mi->m.mfcc.num_ceps;
+  if (left_context) *left_context = mi->m.plan.left_context;
+  if (right_context) *right_context = mi->m.plan.right_context;
+  return 0;
+}
+
+const char *rs_model_plan(const rs_model *m_) {
+  const ModelImpl *mi = reinterpret_cast<const ModelImpl *>(m_);
+  return mi ? mi->plan_text.c_str() : "";
+}
+
+rs_graph *rs_graph_load(const char *hclg_fst, const char *words_txt, int device, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    RS_FAIL("no CUDA device available: this library has no CPU path");
+  if (device < 0 || device >= ndev) RS_FAIL("CUDA device " << device << " does not exist");
+  CUDA_OK(cudaSetDevice(device));
+  std::unique_ptr<GraphImpl> gi(new GraphImpl());
+  gi->device = device;
+  LoadGraph(hclg_fst, words_txt ? words_txt : "", &gi->g);
+  Graph &g = gi->g;
+  DevGraph &d = gi->dev;
+  d.num_states = g.num_states;
+  d.start = (int)g.start;
+  d.num_earcs = (unsigned)g.e_next.size();
+  d.num_parcs = (unsigned)g.p_next.size();
+  d.e_begin = Upload(g.e_begin, &gi->owned);
+  d.p_begin = Upload(g.p_begin, &gi->owned);
+  d.e_src = Upload(g.e_src, &gi->owned);
+  d.p_src = Upload(g.p_src, &gi->owned);
+  d.final_cost = Upload(g.final_cost, &gi->owned);
+  std::vector<int4> parc(g.p_next.size());
+  for (size_t i = 0; i < parc.size(); i++) {
+    int wbits;
+    memcpy(&wbits, &g.p_weight[i], 4);
+    parc[i] = make_int4(g.p_next[i], 0, wbits, g.p_olabel[i]);
+  }
+  d.parc = Upload(parc, &gi->owned);
+  d.earc = nullptr;  // per decoder: ilabels are mapped through the model's tid -> pdf table
+  return reinterpret_cast<rs_graph *>(gi.release());
+  API_GUARD_END(nullptr)
+}
+
+void rs_graph_free(rs_graph *g) { delete reinterpret_cast<GraphImpl *>(g); }
+
+int rs_graph_info(const rs_graph *g_, int32_t *num_states, int64_t *num_arcs, int32_t *num_words) {
+  const GraphImpl *gi = reinterpret_cast<const GraphImpl *>(g_);
+  if (!gi) return 1;
+  if (num_states) *num_states = gi->g.num_states;
+  if (num_arcs) *num_arcs = (int64_t)gi->g.e_next.size() + (int64_t)gi->g.p_next.size();
+  if (num_words) *num_words = (int32_t)gi->g.words.size();
+  return 0;
+}
+
+const char *rs_graph_word(const rs_graph *g_, int32_t id) {
+  const GraphImpl *gi = reinterpret_cast<const GraphImpl *>(g_);
+  if (!gi || id < 0 || (size_t)id >= gi->g.words.size() || gi->g.words[id].empty()) return nullptr;
+  return gi->g.words[id].c_str();
+}
+
+rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts *opts, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  ModelImpl *mi = reinterpret_cast<ModelImpl *>(m_);
+  GraphImpl *gi = reinterpret_cast<GraphImpl *>(g_);
+  if (!mi || !gi) RS_FAIL("rs_decoder_create: model and graph are required");
+  if (mi->device != gi->device) RS_FAIL("model and graph live on different devices");
+  CUDA_OK(cudaSetDevice(mi->device));
+  std::unique_ptr<DecoderImpl> d(new DecoderImpl());
+  d->model = mi;
+  d->graph = gi;
+  if (opts) d->opts = *opts; else rs_decoder_opts_default(&d->opts);
+  rs_decoder_opts &o = d->opts;
+  if (o.beam <= 0 || o.max_active <= 1 || o.min_active < 0 || o.min_active >= o.max_active)
+    RS_FAIL("bad decoder options (beam/max-active/min-active)");
+  if (o.acoustic_scale != 1.0f && o.acoustic_scale != mi->m.acoustic_scale) {
+    // the scale is folded into the model's output epilogue at load time
+    RS_FAIL("acoustic_scale other than 1.0 is not supported (rhasspy always decodes with --acoustic-scale=1.0)");
+  }
+  if (o.max_tokens_per_frame < 1024) o.max_tokens_per_frame = 1024;
+  if (o.max_words < 1) o.max_words = 1;
+  CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  for (auto &e : d->ev) CUDA_OK(cudaEventCreate(&e));
+  // arcs with ilabel -> pdf (TransitionIdToPdfFast, decodable-online-looped.cc:249-256)
+  const Graph &g = gi->g;
+  const auto &t2p = mi->m.trans.tid2pdf;
+  std::vector<int4> earc(g.e_next.size());
+  for (size_t i = 0; i < earc.size(); i++) {
+    int il = g.e_ilabel[i];
+    if (il <= 0 || il >= (int)t2p.size())
+      RS_FAIL("HCLG has input label " << il << " but the model has only " << t2p.size() - 1 << " transition-ids");
+    int wbits;
+    memcpy(&wbits, &g.e_weight[i], 4);
+    earc[i] = make_int4(g.e_next[i], t2p[il], wbits, g.e_olabel[i]);
+  }
+  d->d_earc = Upload(earc, &d->owned);
+  // lanes
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
+  d->n_lanes = o.num_lanes > 0 ? o.num_lanes : 2 * prop.multiProcessorCount;
+  int hash_size = 1;
+  while (hash_size < 2 * o.max_tokens_per_frame) hash_size <<= 1;
+  const size_t H = hash_size, C = o.max_tokens_per_frame;
+  std::vector<LaneWorkspace> lanes(d->n_lanes);
+  auto dalloc = [&](size_t bytes, int fill) {
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    CUDA_OK(cudaMemset(p, fill, bytes));
+    d->owned.push_back(p);
+    return p;
+  };
+  // one allocation per array kind, sliced per lane
+  const int L = d->n_lanes;
+  int *hkey = (int *)dalloc(sizeof(int) * H * 2 * L, 0xff);
+  unsigned long long *hval = (unsigned long long *)dalloc(sizeof(unsigned long long) * H * 2 * L, 0xff);
+  int *hidx = (int *)dalloc(sizeof(int) * H * 2 * L, 0xff);
+  int *inq = (int *)dalloc(sizeof(int) * H * L, 0);
+  int *ins = (int *)dalloc(sizeof(int) * C * 2 * L, 0);
+  int *tstate = (int *)dalloc(sizeof(int) * C * 2 * L, 0);
+  float *tcost = (float *)dalloc(sizeof(float) * C * 2 * L, 0);
+  int *tslot = (int *)dalloc(sizeof(int) * C * L, 0);
+  unsigned *pfx = (unsigned *)dalloc(sizeof(unsigned) * (C + 1) * L, 0);
+  int *frontier = (int *)dalloc(sizeof(int) * C * 2 * L, 0);
+  int2 *arena = (int2 *)dalloc(sizeof(int2) * (size_t)o.max_tokens_per_utt * L, 0);
+  for (int l = 0; l < L; l++) {
+    LaneWorkspace &w = lanes[l];
+    for (int k = 0; k < 2; k++) {
+      w.hkey[k] = hkey + ((size_t)l * 2 + k) * H;
+      w.hval[k] = hval + ((size_t)l * 2 + k) * H;
+      w.hidx[k] = hidx + ((size_t)l * 2 + k) * H;
+      w.ins_list[k] = ins + ((size_t)l * 2 + k) * C;
+      w.tok_state[k] = tstate + ((size_t)l * 2 + k) * C;
+      w.tok_cost[k] = tcost + ((size_t)l * 2 + k) * C;
+      w.frontier[k] = frontier + ((size_t)l * 2 + k) * C;
+    }
+    w.inq = inq + (size_t)l * H;
+    w.tok_slot = tslot + (size_t)l * C;
+    w.pfx = pfx + (size_t)l * (C + 1);
+    w.arena = arena + (size_t)l * o.max_tokens_per_utt;
+  }
+  d->d_lanes = Upload(lanes, &d->owned);
+  d->d_next_utt = (int *)dalloc(sizeof(int), 0);
+  d->slots.resize(mi->m.plan.num_slots);
+  CUDA_OK(cudaDeviceSynchronize());
+  return reinterpret_cast<rs_decoder *>(d.release());
+  API_GUARD_END(nullptr)
+}
+
+void rs_decoder_free(rs_decoder *d) { delete reinterpret_cast<DecoderImpl *>(d); }
+
+}  // extern "C"
+
+namespace rs {
+
+static rs_result *NewResult(int n) {
+  rs_result *r = new rs_result();
+  r->n_utts = n;
+  r->n_hyp = new int32_t[std::max(n, 1)]();
+  r->word_offset = new int32_t[n + 1]();
+  r->word_ids = nullptr;
+  r->graph_cost = new float[std::max(n, 1)]();
+  r->acoustic_cost = new float[std::max(n, 1)]();
+  r->num_frames = new int32_t[std::max(n, 1)]();
+  r->status = new int32_t[std::max(n, 1)]();
+  return r;
+}
+
+// Runs stage (iii) for the batch laid out in d->batch and collects the results.
+static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, int *d_ll_row0, int *d_n_out, int &launches) {
+  const int n = d->batch.n;
+  const rs_decoder_opts &o = d->opts;
+  const int W = o.max_words;
+  // outputs: words [n*W], n_words [n], status [n], cost [2n], counters [4n] (u64)
+  size_t off_words = 0, off_nw = off_words + sizeof(int) * (size_t)n * W, off_status = off_nw + sizeof(int) * n,
+         off_cost = off_status + sizeof(int) * n, off_cnt = RoundUp((int)(off_cost + sizeof(float) * 2 * n), 8),
+         out_bytes = off_cnt + sizeof(unsigned long long) * 4 * n;
+  char *dout = (char *)d->d_out.ensure(out_bytes);
+  DecodeParams p{};
+  p.g = d->graph->dev;
+  p.g.earc = d->d_earc;
+  p.cfg.beam = o.beam;
+  p.cfg.beam_delta = o.beam_delta;
+  p.cfg.max_active = o.max_active;
+  p.cfg.min_active = o.min_active;
+  p.cfg.tok_cap = o.max_tokens_per_frame;
+  int hash_size = 1;
+  while (hash_size < 2 * o.max_tokens_per_frame) hash_size <<= 1;
+  p.cfg.hash_size = hash_size;
+  p.cfg.arena_cap = o.max_tokens_per_utt;
+  p.cfg.max_words = W;
+  p.loglikes = loglikes;
+  p.ld = ld;
+  p.ll_row0 = d_ll_row0;
+  p.n_frames = d_n_out;
+  p.n_utts = n;
+  p.lanes = d->d_lanes;
+  p.next_utt = d->d_next_utt;
+  p.words = (int *)(dout + off_words);
+  p.n_words = (int *)(dout + off_nw);
+  p.status = (int *)(dout + off_status);
+  p.cost = (float *)(dout + off_cost);
+  p.counters = (unsigned long long *)(dout + off_cnt);
+  CUDA_OK(cudaMemsetAsync(d->d_next_utt, 0, sizeof(int), d->stream));
+  LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream);
+  launches += 1;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(d->ev[4], d->stream));
+  char *hout = (char *)d->h_out.ensure(out_bytes);
+  CUDA_OK(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_OK(cudaEventRecord(d->ev[5], d->stream));
+  CUDA_OK(cudaStreamSynchronize(d->stream));
+  d->last.d2h_bytes = out_bytes;
+  const int *words = (const int *)(hout + off_words), *nw = (const int *)(hout + off_nw), *status = (const int *)(hout + off_status);
+  const float *cost = (const float *)(hout + off_cost);
+  const unsigned long long *cnt = (const unsigned long long *)(hout + off_cnt);
+  rs_result *r = NewResult(n);
+  int total = 0;
+  for (int u = 0; u < n; u++) total += std::max(nw[u], 0);
+  r->word_ids = new int32_t[std::max(total, 1)];
+  int pos = 0;
+  d->last.tokens_expanded = d->last.arcs_visited = d->last.tokens_created = d->last.records_written = 0;
+  d->last.frames_decoded = 0;
+  for (int u = 0; u < n; u++) {
+    r->word_offset[u] = pos;
+    r->n_hyp[u] = nw[u] >= 0 ? 1 : 0;
+    for (int i = 0; i < nw[u]; i++) r->word_ids[pos++] = words[(size_t)u * W + i];
+    r->graph_cost[u] = cost[2 * u];
+    r->acoustic_cost[u] = cost[2 * u + 1];
+    r->num_frames[u] = d->batch.n_out[u];
+    r->status[u] = status[u];
+    d->last.tokens_expanded += cnt[4 * (size_t)u];
+    d->last.arcs_visited += cnt[4 * (size_t)u + 1];
+    d->last.tokens_created += cnt[4 * (size_t)u + 2];
+    d->last.records_written += cnt[4 * (size_t)u + 3];
+    d->last.frames_decoded += d->batch.n_out[u];
+  }
+  r->word_offset[n] = pos;
+  return r;
+}
+
+static void FinishTimings(DecoderImpl *d, int launches) {
+  float ms;
+  rs_timings &t = d->last;
+  cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]);
+  t.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]);
+  t.feature_ms = ms;
+  cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]);
+  t.nnet_ms = ms;
+  cudaEventElapsedTime(&ms, d->ev[3], d->ev[4]);
+  t.decode_ms = ms;
+  cudaEventElapsedTime(&ms, d->ev[4], d->ev[5]);
+  t.d2h_ms = ms;
+  cudaEventElapsedTime(&ms, d->ev[0], d->ev[5]);
+  t.total_ms = ms;
+  t.kernel_launches = launches;
+}
+
+static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int32_t *nsamp, int n) {
+  ModelImpl *mi = d->model;
+  const Model &m = mi->m;
+  const Plan &pl = m.plan;
+  CUDA_OK(cudaSetDevice(mi->device));
+  if (n < 0) RS_FAIL("negative batch size");
+  d->last = rs_timings{};
+  if (n == 0) return NewResult(0);
+  for (int i = 0; i < n; i++)
+    if (nsamp[i] < 0 || (nsamp[i] > 0 && !pcm[i])) RS_FAIL("utterance " << i << ": bad sample buffer");
+  const int sf = m.frame_subsampling_factor, D = m.mfcc.num_ceps;
+  const int shift = m.mfcc.WindowShift(), length = m.mfcc.WindowSize();
+  auto &B = d->batch;
+  B = DecoderImpl::Batch();
+  B.n = n;
+  B.num_frames.resize(n);
+  B.frame_offset.resize(n);
+  B.origin.resize(n);
+  B.n_out.resize(n);
+  B.ll_row0.resize(n);
+  std::vector<int64_t> pcm_offset(n);
+  int64_t total_samples = 0;
+  int total_frames = 0, max_frames = 0;
+  const int L = pl.left_context, R = pl.right_context, align = pl.align;
+  int axis = RoundUp(L, align);
+  double audio_s = 0.0;
+  for (int u = 0; u < n; u++) {
+    pcm_offset[u] = total_samples;
+    total_samples += nsamp[u];
+    // NumFrames with snip_edges (feature-window.cc:30-50)
+    int T = nsamp[u] < length ? 0 : 1 + (nsamp[u] - length) / shift;
+    B.num_frames[u] = T;
+    B.frame_offset[u] = total_frames;
+    total_frames += T;
+    max_frames = std::max(max_frames, T);
+    B.origin[u] = axis;
+    B.n_out[u] = (T + sf - 1) / sf;  // decodable-online-looped.cc:71-73
+    B.ll_row0[u] = axis / sf;
+    axis += RoundUp(T + R + L, align);
+    audio_s += nsamp[u] / (double)m.mfcc.samp_freq;
+  }
+  const int axis_len = axis + align;
+  B.total_frames = total_frames;
+  B.axis_len = axis_len;
+  d->last.audio_seconds = audio_s;
+  // ---- host staging: pcm + descriptor block, one H2D copy each
+  const size_t pcm_bytes = sizeof(int16_t) * (size_t)std::max<int64_t>(total_samples, 1);
+  // descriptor: pcm_offset[n] (i64) | num_frames | frame_offset | origin | n_out | ll_row0 | row_utt[axis_len]
+  const size_t desc_ints = (size_t)2 * n + 5 * (size_t)n + axis_len;
+  char *hin = (char *)d->h_in.ensure(pcm_bytes + 16 + desc_ints * sizeof(int));
+  int16_t *hpcm = (int16_t *)hin;
+  for (int u = 0; u < n; u++)
+    if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
+  size_t desc_off = (pcm_bytes + 15) & ~(size_t)15;
+  int *hdesc = (int *)(hin + desc_off);
+  memcpy(hdesc, pcm_offset.data(), sizeof(int64_t) * n);
+  int *h_nf = hdesc + 2 * n, *h_fo = h_nf + n, *h_or = h_fo + n, *h_no = h_or + n, *h_r0 = h_no + n, *h_ru = h_r0 + n;
+  for (int u = 0; u < n; u++) {
+    h_nf[u] = B.num_frames[u];
+    h_fo[u] = B.frame_offset[u];
+    h_or[u] = B.origin[u];
+    h_no[u] = B.n_out[u];
+    h_r0[u] = B.ll_row0[u];
+  }
+  {
+    int u = 0;
+    for (int t = 0; t < axis_len; t++) {
+      while (u + 1 < n && t >= B.origin[u + 1] - L) u++;
+      h_ru[t] = u;
+    }
+  }
+  int16_t *dpcm = (int16_t *)d->d_pcm.ensure(pcm_bytes);
+  int *ddesc = (int *)d->d_desc.ensure(desc_ints * sizeof(int));
+  CUDA_OK(cudaEventRecord(d->ev[0], d->stream));
+  CUDA_OK(cudaMemcpyAsync(dpcm, hpcm, pcm_bytes, cudaMemcpyHostToDevice, d->stream));
+  CUDA_OK(cudaMemcpyAsync(ddesc, hdesc, desc_ints * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  d->last.h2d_bytes = pcm_bytes + desc_ints * sizeof(int);
+  const int64_t *d_pcm_off = (const int64_t *)ddesc;
+  int *d_nf = ddesc + 2 * n, *d_fo = d_nf + n, *d_or = d_fo + n, *d_no = d_or + n, *d_r0 = d_no + n, *d_ru = d_r0 + n;
+  int launches = 0;
+  // ---- stage (i)
+  const size_t feat_elems = (size_t)std::max(total_frames, 1) * D;
+  float *d_mfcc = (float *)d->d_mfcc.ensure(feat_elems * sizeof(float));
+  {
+    FeatParams f = mi->feat;
+    f.pcm = dpcm;
+    f.pcm_offset = d_pcm_off;
+    f.num_frames = d_nf;
+    f.frame_offset = d_fo;
+    f.mfcc = d_mfcc;
+    f.seed = d->opts.dither_seed;
+    LaunchMfcc(f, n, max_frames, d->stream);
+    launches++;
+  }
+  const float *nnet_feats = d_mfcc;
+  float *d_mfcc_norm = nullptr;
+  if (m.has_ivector || m.nnet_cmvn) d_mfcc_norm = (float *)d->d_mfcc_norm.ensure(feat_elems * sizeof(float));
+  float *d_ivector = nullptr;
+  int ivector_ld = 0;
+  // slot storage for the plan
+  auto slot_ptr = [&](int buffer) -> float * { return d->slots[pl.buffers[buffer].slot].as<float>(); };
+  auto buf_ld = [&](int buffer) { return RoundUp(pl.buffers[buffer].dim, 4); };
+  auto buf_rows = [&](int buffer) { return pl.buffers[buffer].per_utt ? n : axis_len / pl.buffers[buffer].step; };
+  {
+    std::vector<size_t> need(pl.num_slots, 0);
+    for (size_t b = 0; b < pl.buffers.size(); b++) {
+      size_t bytes = (size_t)buf_rows((int)b) * buf_ld((int)b) * sizeof(float);
+      need[pl.buffers[b].slot] = std::max(need[pl.buffers[b].slot], bytes);
+    }
+    for (int s = 0; s < pl.num_slots; s++) d->slots[s].ensure(std::max<size_t>(need[s], 16));
+  }
+  if (m.has_ivector) {
+    CmvnParams c{};
+    c.in = d_mfcc;
+    c.out = d_mfcc_norm;
+    c.num_frames = d_nf;
+    c.frame_offset = d_fo;
+    c.global_stats = mi->d_global_cmvn;
+    c.dim = D;
+    c.cmn_window = m.ivec.cmvn.cmn_window;
+    c.global_frames = m.ivec.cmvn.global_frames;
+    c.normalize_mean = m.ivec.cmvn.normalize_mean;
+    c.normalize_variance = m.ivec.cmvn.normalize_variance;
+    LaunchCmvn(c, n, d->stream);
+    launches++;
+    IvecParams iv = mi->ivec;
+    const int G = iv.num_gauss, LD = iv.ldim, Rv = iv.ivector_dim, P = Rv * (Rv + 1) / 2;
+    iv.mfcc = d_mfcc;
+    iv.mfcc_norm = d_mfcc_norm;
+    iv.num_frames = d_nf;
+    iv.frame_offset = d_fo;
+    iv.n_utts = n;
+    iv.total_frames = total_frames;
+    iv.max_frames = max_frames;
+    const size_t tf = std::max(total_frames, 1);
+    iv.x_raw = (float *)d->d_xraw.ensure(tf * LD * sizeof(float));
+    iv.x_norm = (float *)d->d_xnorm.ensure(tf * LD * sizeof(float));
+    iv.post_idx = (int *)d->d_post_idx.ensure(tf * iv.num_gselect * sizeof(int));
+    iv.post_w = (float *)d->d_post_w.ensure(tf * iv.num_gselect * sizeof(float));
+    iv.wf = (double *)d->d_wf.ensure((size_t)n * G * LD * sizeof(double));
+    iv.gw = (float *)d->d_gw.ensure((size_t)n * G * sizeof(float));
+    iv.linear = (double *)d->d_linear.ensure((size_t)n * Rv * sizeof(double));
+    iv.quad = (double *)d->d_quad.ensure((size_t)n * P * sizeof(double));
+    d_ivector = slot_ptr(pl.ivector_buffer);
+    ivector_ld = buf_ld(pl.ivector_buffer);
+    iv.ivector = d_ivector;
+    iv.ivector_ld = ivector_ld;
+    LaunchIvector(iv, d->stream);
+    launches += 8;
+  }
+  if (m.nnet_cmvn) {
+    // --cmvn-config in online.conf: the nnet input is CMVN-normalised too
+    // (online-nnet2-feature-pipeline.cc:90-147); it may use different options than the iVector one
+    CmvnParams c{};
+    c.in = d_mfcc;
+    c.out = d_mfcc_norm;
+    c.num_frames = d_nf;
+    c.frame_offset = d_fo;
+    c.global_stats = mi->d_nnet_global_cmvn;
+    c.dim = D;
+    c.cmn_window = m.nnet_cmvn_opts.cmn_window;
+    c.global_frames = m.nnet_cmvn_opts.global_frames;
+    c.normalize_mean = m.nnet_cmvn_opts.normalize_mean;
+    c.normalize_variance = m.nnet_cmvn_opts.normalize_variance;
+    LaunchCmvn(c, n, d->stream);
+    launches++;
+    nnet_feats = d_mfcc_norm;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(d->ev[2], d->stream));
+  // ---- stage (ii)
+  {
+    float *in = slot_ptr(pl.input_buffer);
+    const int ild = buf_ld(pl.input_buffer);
+    CUDA_OK(cudaMemsetAsync(in, 0, (size_t)axis_len * ild * sizeof(float), d->stream));
+    AssembleParams a{};
+    a.feats = nnet_feats;
+    a.num_frames = d_nf;
+    a.frame_offset = d_fo;
+    a.origin = d_or;
+    a.dst = in;
+    a.dim = D;
+    a.ld = ild;
+    a.left = L;
+    a.right = R;
+    a.axis_len = axis_len;
+    LaunchAssembleInput(a, n, max_frames + L + R, d->stream);
+    launches++;
+  }
+  for (const Step &st : pl.steps) {
+    GemmParams g{};
+    const PlanBuffer &ob = pl.buffers[st.out];
+    g.out = slot_ptr(st.out);
+    g.out_ld = buf_ld(st.out);
+    g.m = buf_rows(st.out);
+    g.n = st.n;
+    g.out_step = ob.per_utt ? 1 : ob.step;
+    g.row_utt = d_ru;
+    g.n_slabs = (int)st.slabs.size();
+    for (int s = 0; s < g.n_slabs; s++) {
+      const Slab &sl = st.slabs[s];
+      const PlanBuffer &sb = pl.buffers[sl.src];
+      GemmSlab &gs = g.slabs[s];
+      gs.src = slot_ptr(sl.src);
+      gs.ld = buf_ld(sl.src);
+      gs.rows = buf_rows(sl.src);
+      gs.k = sl.k;
+      gs.wcol = sl.wcol;
+      if (sb.per_utt) {
+        gs.num = 1;
+        gs.den = 1;
+        gs.shift = 0;
+      } else {
+        gs.num = ob.step;
+        gs.den = sb.step;
+        gs.shift = sl.t_offset;
+      }
+    }
+    g.n_ops = (int)st.ops.size();
+    for (int i = 0; i < g.n_ops; i++) {
+      const EpiOp &op = st.ops[i];
+      DevOp &dop = g.ops[i];
+      dop.type = op.type;
+      dop.v0 = op.vec0 >= 0 ? mi->d_vectors[op.vec0] : nullptr;
+      dop.v1 = op.vec1 >= 0 ? mi->d_vectors[op.vec1] : nullptr;
+      dop.alpha = op.alpha;
+      dop.buf = nullptr;
+      dop.num = dop.den = 1;
+      if (op.buffer >= 0) {
+        dop.buf = slot_ptr(op.buffer);
+        dop.buf_ld = buf_ld(op.buffer);
+        dop.buf_rows = buf_rows(op.buffer);
+        if (op.type == EpiOp::kAddScaled) {
+          dop.num = ob.step;
+          dop.den = pl.buffers[op.buffer].step;
+        } else {
+          dop.num = ob.step;  // kUttBias: axis time of an output row
+        }
+      }
+    }
+    switch (st.type) {
+      case Step::kGemm:
+      case Step::kUttGemm:
+        g.w = mi->d_matrices[st.weight];
+        g.ktot = st.ktot;
+        LaunchGemm(g, d->stream);
+        break;
+      case Step::kElementwise:
+        for (int s = 0; s < g.n_slabs; s++) g.slabs[s].wcol = 0;
+        LaunchElementwise(g, st.term_scale.data(), st.col_offset, d->stream);
+        break;
+      case Step::kLogSoftmax:
+        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].ld, g.out, g.out_ld, g.m, g.n, d->stream);
+        break;
+    }
+    launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(d->ev[3], d->stream));
+  d->last.nnet_flops = (uint64_t)((double)mi->flops_per_axis_unit / 1000.0 * axis_len);
+  // ---- stage (iii)
+  B.loglikes = slot_ptr(pl.output_buffer);
+  B.ll_ld = buf_ld(pl.output_buffer);
+  rs_result *r = RunDecodeStage(d, B.loglikes, B.ll_ld, d_r0, d_no, launches);
+  FinishTimings(d, launches);
+  return r;
+}
+
+static rs_result *DecodeLoglikes(DecoderImpl *d, const float *const *ll, const int32_t *nframes, int n) {
+  ModelImpl *mi = d->model;
+  CUDA_OK(cudaSetDevice(mi->device));
+  d->last = rs_timings{};
+  if (n <= 0) return NewResult(0);
+  const int P = mi->m.trans.num_pdfs, ld = RoundUp(P, 4);
+  auto &B = d->batch;
+  B = DecoderImpl::Batch();
+  B.n = n;
+  B.from_loglikes = true;
+  B.n_out.resize(n);
+  B.ll_row0.resize(n);
+  B.num_frames.assign(n, 0);
+  B.frame_offset.assign(n, 0);
+  B.origin.assign(n, 0);
+  size_t rows = 0;
+  for (int u = 0; u < n; u++) {
+    if (nframes[u] < 0) RS_FAIL("negative frame count");
+    B.ll_row0[u] = (int)rows;
+    B.n_out[u] = nframes[u];
+    rows += nframes[u];
+  }
+  const size_t ll_bytes = std::max<size_t>(rows, 1) * ld * sizeof(float);
+  char *hin = (char *)d->h_in.ensure(ll_bytes + 2 * sizeof(int) * n);
+  float *hll = (float *)hin;
+  memset(hll, 0, ll_bytes);
+  for (int u = 0; u < n; u++)
+    for (int t = 0; t < nframes[u]; t++)
+      memcpy(hll + ((size_t)B.ll_row0[u] + t) * ld, ll[u] + (size_t)t * P, sizeof(float) * P);
+  int *hdesc = (int *)(hin + ll_bytes);
+  for (int u = 0; u < n; u++) {
+    hdesc[u] = B.ll_row0[u];
+    hdesc[n + u] = B.n_out[u];
+  }
+  float *dll = (float *)d->d_loglikes_ext.ensure(ll_bytes);
+  int *ddesc = (int *)d->d_desc.ensure(2 * sizeof(int) * n);
+  CUDA_OK(cudaEventRecord(d->ev[0], d->stream));
+  CUDA_OK(cudaMemcpyAsync(dll, hll, ll_bytes, cudaMemcpyHostToDevice, d->stream));
+  CUDA_OK(cudaMemcpyAsync(ddesc, hdesc, 2 * sizeof(int) * n, cudaMemcpyHostToDevice, d->stream));
+  for (int k = 1; k <= 3; k++) CUDA_OK(cudaEventRecord(d->ev[k], d->stream));
+  d->last.h2d_bytes = ll_bytes;
+  int launches = 0;
+  B.loglikes = dll;
+  B.ll_ld = ld;
+  rs_result *r = RunDecodeStage(d, dll, ld, ddesc, ddesc + n, launches);
+  FinishTimings(d, launches);
+  return r;
+}
+
+// RIFF/WAVE PCM16 reader (kaldi/src/feat/wave-reader.cc:153-320): mono, 16-bit, no scaling.
+static void ReadWav(const std::string &path, float expect_rate, std::vector<int16_t> *out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) RS_FAIL("cannot open " << path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string b = ss.str();
+  if (b.size() < 12 || b.compare(0, 4, "RIFF") || b.compare(8, 4, "WAVE")) RS_FAIL(path << ": not a RIFF/WAVE file");
+  size_t p = 12;
+  int channels = 0, bits = 0, fmt = 0;
+  uint32_t rate = 0;
+  bool have_fmt = false;
+  while (p + 8 <= b.size()) {
+    std::string id = b.substr(p, 4);
+    uint32_t sz;
+    memcpy(&sz, b.data() + p + 4, 4);
+    p += 8;
+    if (id == "fmt ") {
+      if (p + 16 > b.size()) RS_FAIL(path << ": truncated fmt chunk");
+      uint16_t v16;
+      memcpy(&v16, b.data() + p, 2);
+      fmt = v16;
+      memcpy(&v16, b.data() + p + 2, 2);
+      channels = v16;
+      memcpy(&rate, b.data() + p + 4, 4);
+      memcpy(&v16, b.data() + p + 14, 2);
+      bits = v16;
+      have_fmt = true;
+    } else if (id == "data") {
+      if (!have_fmt) RS_FAIL(path << ": data chunk before fmt chunk");
+      if (fmt != 1 || bits != 16) RS_FAIL(path << ": only 16-bit PCM WAVE files are supported");
+      if (channels != 1) RS_FAIL(path << ": only mono WAVE files are supported (got " << channels << " channels)");
+      if ((float)rate != expect_rate)
+        RS_FAIL(path << ": sampling frequency mismatch, expected " << expect_rate << ", got " << rate);
+      size_t n = std::min<size_t>(sz, b.size() - p);
+      if (sz == 0xffffffffu || sz == 0) n = b.size() - p;  // streamed headers
+      out->resize(n / 2);
+      if (n / 2) memcpy(out->data(), b.data() + p, (n / 2) * 2);
+      return;
+    }
+    p += sz + (sz & 1);
+  }
+  RS_FAIL(path << ": no data chunk");
+}
+
+}  // namespace rs
+
+extern "C" {
+
+int rs_decode_pcm(rs_decoder *d_, const int16_t *const *pcm, const int32_t *num_samples, int32_t n, rs_result **out,
+                  char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d || !out) RS_FAIL("rs_decode_pcm: null argument");
+  *out = DecodePcm(d, pcm, num_samples, n);
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_decode_wavs(rs_decoder *d_, const char *const *paths, int32_t n, rs_result **out, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d || !out) RS_FAIL("rs_decode_wavs: null argument");
+  std::vector<std::vector<int16_t>> data(n);
+  std::vector<const int16_t *> ptrs(n);
+  std::vector<int32_t> ns(n);
+  for (int i = 0; i < n; i++) {
+    ReadWav(paths[i], d->model->m.mfcc.samp_freq, &data[i]);
+    ptrs[i] = data[i].data();
+    ns[i] = (int32_t)data[i].size();
+  }
+  *out = DecodePcm(d, ptrs.data(), ns.data(), n);
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_decode_loglikes(rs_decoder *d_, const float *const *loglikes, const int32_t *num_frames, int32_t n, rs_result **out,
+                       char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d || !out) RS_FAIL("rs_decode_loglikes: null argument");
+  *out = DecodeLoglikes(d, loglikes, num_frames, n);
+  return 0;
+  API_GUARD_END(1)
+}
+
+void rs_result_free(rs_result *r) {
+  if (!r) return;
+  delete[] r->n_hyp;
+  delete[] r->word_offset;
+  delete[] r->word_ids;
+  delete[] r->graph_cost;
+  delete[] r->acoustic_cost;
+  delete[] r->num_frames;
+  delete[] r->status;
+  delete r;
+}
+
+rs_stream *rs_stream_open(rs_decoder *d_, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d) RS_FAIL("rs_stream_open: null decoder");
+  StreamImpl *s = new StreamImpl();
+  s->dec = d;
+  return reinterpret_cast<rs_stream *>(s);
+  API_GUARD_END(nullptr)
+}
+
+int rs_stream_accept(rs_stream *s_, const int16_t *pcm, int32_t num_samples, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  StreamImpl *s = reinterpret_cast<StreamImpl *>(s_);
+  if (!s || num_samples < 0 || (num_samples && !pcm)) RS_FAIL("rs_stream_accept: bad argument");
+  s->pcm.insert(s->pcm.end(), pcm, pcm + num_samples);
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_streams_finish(rs_stream *const *streams, int32_t n, rs_result **out, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  if (n < 0 || !out || (n && !streams)) RS_FAIL("rs_streams_finish: bad argument");
+  if (n == 0) {
+    *out = NewResult(0);
+    return 0;
+  }
+  DecoderImpl *d = reinterpret_cast<StreamImpl *>(streams[0])->dec;
+  std::vector<const int16_t *> ptrs(n);
+  std::vector<int32_t> ns(n);
+  for (int i = 0; i < n; i++) {
+    StreamImpl *s = reinterpret_cast<StreamImpl *>(streams[i]);
+    if (s->dec != d) RS_FAIL("rs_streams_finish: streams belong to different decoders");
+    ptrs[i] = s->pcm.data();
+    ns[i] = (int32_t)s->pcm.size();
+  }
+  *out = DecodePcm(d, ptrs.data(), ns.data(), n);
+  for (int i = 0; i < n; i++) reinterpret_cast<StreamImpl *>(streams[i])->pcm.clear();
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_stream_finish(rs_stream *s, rs_result **out, char *err, size_t errlen) {
+  rs_stream *arr[1] = {s};
+  return rs_streams_finish(arr, 1, out, err, errlen);
+}
+
+void rs_stream_close(rs_stream *s) { delete reinterpret_cast<StreamImpl *>(s); }
+
+int rs_decoder_timings(const rs_decoder *d_, rs_timings *t) {
+  const DecoderImpl *d = reinterpret_cast<const DecoderImpl *>(d_);
+  if (!d || !t) return 1;
+  *t = d->last;
+  return 0;
+}
+
+int rs_debug_fetch(rs_decoder *d_, int32_t what, int32_t utt, float *dst, int32_t *rows, int32_t *cols, char *err,
+                   size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d) RS_FAIL("rs_debug_fetch: null decoder");
+  const auto &B = d->batch;
+  if (utt < 0 || utt >= B.n) RS_FAIL("rs_debug_fetch: utterance index out of range");
+  const Model &m = d->model->m;
+  CUDA_OK(cudaSetDevice(d->model->device));
+  const float *src = nullptr;
+  int r = 0, c = 0, ld = 0;
+  if (what == 2) {
+    r = B.n_out[utt];
+    c = m.trans.num_pdfs;
+    ld = B.ll_ld;
+    src = B.loglikes + (size_t)B.ll_row0[utt] * ld;
+  } else {
+    if (B.from_loglikes) RS_FAIL("rs_debug_fetch: the last call did not run the feature stages");
+    if (what == 0 || what == 3) {
+      r = B.num_frames[utt];
+      c = ld = m.mfcc.num_ceps;
+      const DevBuf &b = what == 0 ? d->d_mfcc : d->d_mfcc_norm;
+      if (!b.p) RS_FAIL("rs_debug_fetch: buffer not available");
+      src = b.as<float>() + (size_t)B.frame_offset[utt] * ld;
+    } else if (what == 1) {
+      if (!m.has_ivector) RS_FAIL("rs_debug_fetch: model has no iVector input");
+      r = 1;
+      c = m.ie.ivector_dim;
+      ld = RoundUp(c, 4);
+      src = d->slots[m.plan.buffers[m.plan.ivector_buffer].slot].as<float>() + (size_t)utt * ld;
+    } else if (what == 4) {
+      if (!m.has_ivector) RS_FAIL("rs_debug_fetch: model has no iVector input");
+      r = B.num_frames[utt];
+      c = ld = m.lda.rows;
+      src = d->d_xnorm.as<float>() + (size_t)B.frame_offset[utt] * ld;
+    } else {
+      RS_FAIL("rs_debug_fetch: unknown item " << what);
+    }
+  }
+  if (rows) *rows = r;
+  if (cols) *cols = c;
+  if (dst && r > 0)
+    CUDA_OK(cudaMemcpy2D(dst, sizeof(float) * c, src, sizeof(float) * ld, sizeof(float) * c, r, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END(1)
+}
+
+}  // extern "C"

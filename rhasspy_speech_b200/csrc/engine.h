@@ -1,0 +1,185 @@
+// Device-side parameter blocks and launchers shared by the stage kernels and the host engine.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace rs {
+
+// ---------------------------------------------------------------------------- stage (i) MFCC
+struct FeatParams {
+  // batch
+  const int16_t *pcm;        // all utterances back to back
+  const int64_t *pcm_offset; // [n_utts] first sample of each utterance
+  const int *num_frames;     // [n_utts]
+  const int *frame_offset;   // [n_utts] first row of each utterance in `mfcc`
+  float *mfcc;               // [total_frames, num_ceps]
+  // options
+  int shift, length, padded, logn;  // logn = log2(padded / 2)
+  float preemph, dither, energy_floor;
+  int remove_dc, use_energy, raw_energy;
+  uint32_t seed;
+  int num_bins, num_ceps;
+  // tables (device)
+  const float *window;          // [length]
+  const uint16_t *level_offsets;  // split-radix block offsets, grouped by log2(block size)
+  int level_start[12], level_count[12];
+  const float *twiddle;         // per level: cn, spcn, smcn, c3n, spc3n, smc3n (each m/4-2 long)
+  int twiddle_start[12];
+  const uint16_t *perm;         // bit-reversal permutation of the complex FFT output [padded/2]
+  const float *kn;              // real-FFT twiddles (re, im) for k = 1 .. padded/4
+  const int *mel_offset, *mel_len, *mel_start;  // [num_bins]
+  const float *mel_weights;
+  const float *dct;             // [num_ceps, num_bins]
+  const float *lifter;          // [num_ceps] or null
+};
+void LaunchMfcc(const FeatParams &p, int n_utts, int max_frames, cudaStream_t stream);
+
+// --------------------------------------------------------------------- stage (i) CMVN + iVector
+struct CmvnParams {
+  const float *in;   // [total_frames, dim]
+  float *out;        // [total_frames, dim]
+  const int *num_frames, *frame_offset;
+  const double *global_stats;  // [2, dim+1]
+  int dim, cmn_window, global_frames;
+  int normalize_mean, normalize_variance;
+};
+void LaunchCmvn(const CmvnParams &p, int n_utts, cudaStream_t stream);
+
+struct IvecParams {
+  const float *mfcc, *mfcc_norm;      // [total_frames, dim]
+  const int *num_frames, *frame_offset;
+  int n_utts, total_frames, max_frames;
+  int dim, left, right;               // splice
+  const float *lda_t;                 // [K = dim*(left+1+right)][ldim]  (transposed), bias may be null
+  const float *lda_bias;
+  int ldim;                           // LDA output dim == UBM dim
+  float *x_raw, *x_norm;              // [total_frames, ldim]
+  // UBM
+  int num_gauss;
+  const float *gconsts;               // [G]
+  const float *means_invvars_t;       // [ldim][G]
+  const float *inv_vars_t;            // [ldim][G]
+  int num_gselect;
+  float min_post, posterior_scale;
+  int *post_idx;                      // [total_frames, num_gselect]  (-1 = unused)
+  float *post_w;                      // [total_frames, num_gselect]
+  // extractor
+  int ivector_dim;
+  const double *sigma_inv_m;          // [G][ldim][R]
+  const double *u;                    // [G][R(R+1)/2]
+  double prior_offset;
+  float max_count;
+  int num_cg_iters;
+  int online_cmvn_iextractor;
+  double *wf;                         // [n_utts][G][ldim] weighted feature sums
+  float *gw;                          // [n_utts][G] per-Gaussian total weights (float, as the reference)
+  double *linear;                     // [n_utts][R]
+  double *quad;                       // [n_utts][R(R+1)/2] packed lower triangle
+  float *ivector;                     // [n_utts][ivector_ld] nnet input (prior offset removed)
+  int ivector_ld;
+};
+void LaunchIvector(const IvecParams &p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------ stage (ii) nnet
+constexpr int kMaxSlabs = 8;
+constexpr int kMaxOps = 8;
+struct GemmSlab {
+  const float *src;
+  int ld;        // row stride of src in floats
+  int rows;      // valid rows of src (indices are clamped into [0, rows))
+  int k;         // columns used
+  int wcol;      // first weight column
+  int num, den;  // src_row = (out_row * num + shift) / den   (den divides exactly on valid rows)
+  int shift;
+};
+struct DevOp {
+  int type;            // EpiOp::Type
+  const float *v0, *v1;
+  float alpha;
+  const float *buf;    // kAddScaled: other activation buffer ; kUttBias: [n_utts, ld]
+  int buf_ld, buf_rows;
+  int num, den;        // kAddScaled: other_row = out_row * num / den ; kUttBias: axis time = out_row * num
+};
+struct GemmParams {
+  GemmSlab slabs[kMaxSlabs];
+  int n_slabs;
+  const float *w;  // [n, ktot] row-major
+  int ktot;
+  float *out;
+  int out_ld;
+  int m, n;        // output rows / columns
+  DevOp ops[kMaxOps];
+  int n_ops;
+  const int *row_utt;  // [axis_len] utterance owning each time step (for kUttBias)
+  int out_step;
+};
+void LaunchGemm(const GemmParams &p, cudaStream_t stream);
+void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int col_offset, cudaStream_t stream);
+void LaunchLogSoftmax(const float *in, int in_ld, float *out, int out_ld, int rows, int n, cudaStream_t stream);
+
+struct AssembleParams {
+  const float *feats;  // [total_frames, dim]
+  const int *num_frames, *frame_offset, *origin;  // per utt
+  float *dst;          // nnet input buffer on the global axis [axis_len, ld]
+  int dim, ld, left, right, axis_len;
+};
+void LaunchAssembleInput(const AssembleParams &p, int n_utts, int max_rows, cudaStream_t stream);
+
+// ------------------------------------------------------------------------ stage (iii) decoder
+struct DevGraph {
+  int num_states;
+  int start;
+  unsigned num_earcs, num_parcs;
+  const unsigned *e_begin, *p_begin;  // [S+1]
+  const int4 *earc;                   // {next, pdf, weight bits, olabel}
+  const int *e_src;
+  const int4 *parc;                   // {next, 0, weight bits, olabel}
+  const int *p_src;
+  const float *final_cost;
+};
+
+struct DecodeConfig {
+  float beam, beam_delta;
+  int max_active, min_active;
+  int tok_cap;      // max tokens inserted per frame per lane
+  int hash_size;    // power of two >= 2 * tok_cap ; identity addressing if num_states <= hash_size
+  int arena_cap;    // max tokens per utterance (traceback records)
+  int max_words;
+};
+
+struct LaneWorkspace {  // one per resident CTA; all pointers are device memory
+  int *hkey[2];
+  unsigned long long *hval[2];
+  int *hidx[2];
+  int *inq;          // frontier membership flag per slot (shared by both tables, always cleared)
+  int *ins_list[2];  // slots inserted into table k, in insertion order
+  int *tok_state[2];
+  float *tok_cost[2];
+  int *tok_slot;     // scratch: slot of each alive token of the frame being finalised
+  unsigned *pfx;     // [tok_cap + 1] exclusive prefix of emitting out-degrees
+  int *frontier[2];
+  int2 *arena;       // {prev token gid, arc id}
+};
+
+struct DecodeParams {
+  DevGraph g;
+  DecodeConfig cfg;
+  const float *loglikes;  // [rows, ld]
+  int ld;
+  const int *ll_row0;     // [n_utts] first row of each utterance
+  const int *n_frames;    // [n_utts]
+  int n_utts;
+  LaneWorkspace *lanes;   // [gridDim.x]
+  int *next_utt;          // work counter
+  // outputs
+  int *words;             // [n_utts, max_words]
+  int *n_words;           // [n_utts]  (-1 = nothing decoded)
+  float *cost;            // [n_utts, 2] graph, acoustic
+  int *status;            // [n_utts] 0 ok, bit0 token overflow, bit1 arena overflow, bit2 no tokens, bit3 word overflow
+  unsigned long long *counters;  // [n_utts, 4] tokens expanded, arcs visited, tokens created, records written
+};
+void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream);
+int DecodeCtaThreads();
+
+}  // namespace rs

@@ -1,0 +1,471 @@
+// Stage (i), second half: online CMVN, splice + LDA, UBM posteriors, iVector statistics and the
+// conjugate-gradient solve -- the work of OnlineIvectorFeature in the reference:
+//   kaldi/src/feat/online-feature.cc:337-452      OnlineCmvn (+ transform/cmvn.cc:64-115 ApplyCmvn)
+//   kaldi/src/feat/online-feature.cc:504-554      OnlineSpliceFrames, OnlineTransform (LDA)
+//   kaldi/src/gmm/diag-gmm.cc:546-562             DiagGmm::LogLikelihoods
+//   kaldi/src/hmm/posterior.cc:440-508            VectorToPosteriorEntry
+//   kaldi/src/online2/online-ivector-feature.cc:188-279, 327-355   scheduling (offline: one update
+//                                                 over all frames, then one CG from the prior)
+//   kaldi/src/ivector/ivector-extractor.cc:611-668, 732-756        AccStats, GetIvector
+//   kaldi/src/matrix/optimization.cc:453-560      LinearCgd
+#include <cfloat>
+
+#include "engine.h"
+
+namespace rs {
+
+// ------------------------------------------------------------------------------------ CMVN
+// One thread per (utterance, dim): the sliding-window sums are sequential in double exactly as
+// ComputeStatsForFrame accumulates them (add frame t, then subtract frame t - cmn_window).
+__global__ void cmvn_kernel(CmvnParams p) {
+  const int u = blockIdx.x, d = threadIdx.x;
+  if (d >= p.dim) return;
+  const int T = p.num_frames[u];
+  const float *in = p.in + (size_t)p.frame_offset[u] * p.dim;
+  float *out = p.out + (size_t)p.frame_offset[u] * p.dim;
+  const double g0 = p.global_stats[d], g1 = p.global_stats[(p.dim + 1) + d], gcount = p.global_stats[p.dim];
+  double s0 = 0.0, s1 = 0.0, cnt = 0.0;
+  for (int t = 0; t < T; t++) {
+    double x = (double)in[(size_t)t * p.dim + d];
+    s0 += x;
+    if (p.normalize_variance) s1 += x * x;
+    cnt += 1.0;
+    int prev = t - p.cmn_window;
+    if (prev >= 0) {
+      double y = (double)in[(size_t)prev * p.dim + d];
+      s0 -= y;
+      if (p.normalize_variance) s1 -= y * y;
+      cnt -= 1.0;
+    }
+    // SmoothOnlineCmvnStats with no speaker stats (spk == utt in the reference's invocation)
+    double a0 = s0, a1 = s1, c = cnt;
+    if (c < (double)p.cmn_window) {
+      double cg = (double)p.cmn_window - c;
+      if (cg > (double)p.global_frames) cg = (double)p.global_frames;
+      if (cg > 0.0) {
+        double f = cg / gcount;
+        a0 += f * g0;
+        a1 += f * g1;
+        c += f * gcount;
+      }
+    }
+    float xin = in[(size_t)t * p.dim + d], y;
+    if (!p.normalize_mean) {
+      y = xin;
+    } else if (!p.normalize_variance) {
+      float alpha = (float)(-1.0 / c);          // VectorBase<float>::AddVec(float alpha, Vector<double>)
+      float off = (float)((double)alpha * a0);
+      y = __fadd_rn(xin, off);
+    } else {
+      double mean = a0 / c;
+      double var = a1 / c - mean * mean;
+      if (var < 1.0e-20) var = 1.0e-20;
+      double scale = 1.0 / sqrt(var);
+      float sc = (float)scale, off = (float)(-(mean * scale));
+      y = __fadd_rn(__fmul_rn(xin, sc), off);
+    }
+    out[(size_t)t * p.dim + d] = y;
+  }
+}
+
+void LaunchCmvn(const CmvnParams &p, int n_utts, cudaStream_t stream) {
+  if (n_utts == 0) return;
+  int threads = ((p.dim + 31) / 32) * 32;
+  cmvn_kernel<<<n_utts, threads, 0, stream>>>(p);
+}
+
+// ---------------------------------------------------------------------------- splice + LDA
+// CTA = 16 frames of one utterance; the spliced window (16 + left + right frames) is staged in
+// shared memory for both the raw and the normalised stream; thread (f, j) -> one output each.
+constexpr int kLdaFrames = 16;
+__global__ void __launch_bounds__(256) splice_lda_kernel(IvecParams p) {
+  extern __shared__ float sm[];
+  const int u = blockIdx.y;
+  const int T = p.num_frames[u];
+  const int t0 = blockIdx.x * kLdaFrames;
+  if (t0 >= T) return;
+  const int W = kLdaFrames + p.left + p.right;
+  float *sraw = sm, *snorm = sm + (size_t)W * p.dim;
+  const size_t base = (size_t)p.frame_offset[u];
+  for (int i = threadIdx.x; i < W * p.dim; i += blockDim.x) {
+    int w = i / p.dim, d = i - w * p.dim;
+    int t = t0 - p.left + w;
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);  // OnlineSpliceFrames clamps at both ends
+    sraw[i] = p.mfcc[(base + t) * p.dim + d];
+    snorm[i] = p.mfcc_norm[(base + t) * p.dim + d];
+  }
+  __syncthreads();
+  const int K = p.dim * (p.left + 1 + p.right);
+  for (int o = threadIdx.x; o < kLdaFrames * p.ldim; o += blockDim.x) {
+    int f = o / p.ldim, j = o - f * p.ldim;
+    if (t0 + f >= T) continue;
+    const float *xr = sraw + (size_t)f * p.dim, *xn = snorm + (size_t)f * p.dim;
+    float ar = 0.f, an = 0.f;
+    for (int k = 0; k < K; k++) {
+      float w = p.lda_t[(size_t)k * p.ldim + j];
+      ar = fmaf(w, xr[k], ar);
+      an = fmaf(w, xn[k], an);
+    }
+    if (p.lda_bias) {
+      ar += p.lda_bias[j];
+      an += p.lda_bias[j];
+    }
+    p.x_raw[(base + t0 + f) * p.ldim + j] = ar;
+    p.x_norm[(base + t0 + f) * p.ldim + j] = an;
+  }
+}
+
+// -------------------------------------------------------------------- UBM posteriors (warp/frame)
+constexpr int kMaxGaussPerLane = 64;  // up to 2048 Gaussians
+__global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.total_frames) return;
+  float *x = sm + (size_t)warp * p.ldim * 2, *xsq = x + p.ldim;
+  for (int d = lane; d < p.ldim; d += 32) {
+    float v = p.x_norm[(size_t)row * p.ldim + d];
+    x[d] = v;
+    xsq[d] = __fmul_rn(v, v);
+  }
+  __syncwarp();
+  const int G = p.num_gauss;
+  float ll[kMaxGaussPerLane];
+  float mx = -FLT_MAX;
+#pragma unroll 1
+  for (int i = 0; i < kMaxGaussPerLane; i++) {
+    int g = lane + i * 32;
+    if (g >= G) break;
+    float a1 = 0.f, a2 = 0.f;
+    for (int d = 0; d < p.ldim; d++) {
+      a1 = fmaf(x[d], p.means_invvars_t[(size_t)d * G + g], a1);
+      a2 = fmaf(xsq[d], p.inv_vars_t[(size_t)d * G + g], a2);
+    }
+    float v = __fadd_rn(__fadd_rn(p.gconsts[g], a1), __fmul_rn(-0.5f, a2));
+    ll[i] = v;
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  // GetMinPost with weight 1.0 (online-ivector-feature.cc:188-199)
+  float min_post = p.min_post > 0.99f ? 0.99f : p.min_post;
+  const float cut = min_post != 0.f ? __fadd_rn(mx, logf(min_post)) : -FLT_MAX;
+  // posteriors of the candidates; everything else is marked -1
+  int any = 0;
+#pragma unroll 1
+  for (int i = 0; i < kMaxGaussPerLane; i++) {
+    int g = lane + i * 32;
+    if (g >= G) break;
+    float v = ll[i];
+    if (min_post != 0.f && v > cut) {
+      ll[i] = (float)exp((double)__fsub_rn(v, mx));
+      any = 1;
+    } else {
+      ll[i] = -1.f;
+    }
+  }
+  any = __any_sync(0xffffffffu, any);
+  if (!any) {  // min_post == 0 or nothing above the threshold: all Gaussians are candidates
+#pragma unroll 1
+    for (int i = 0; i < kMaxGaussPerLane; i++) {
+      int g = lane + i * 32;
+      if (g >= G) break;
+      float a1 = 0.f, a2 = 0.f;
+      for (int d = 0; d < p.ldim; d++) {
+        a1 = fmaf(x[d], p.means_invvars_t[(size_t)d * G + g], a1);
+        a2 = fmaf(xsq[d], p.inv_vars_t[(size_t)d * G + g], a2);
+      }
+      float v = __fadd_rn(__fadd_rn(p.gconsts[g], a1), __fmul_rn(-0.5f, a2));
+      ll[i] = expf(__fsub_rn(v, mx));
+    }
+  }
+  // top num_gselect by posterior, in decreasing order (ties: lowest Gaussian index)
+  const int ng = p.num_gselect < G ? p.num_gselect : G;
+  float sel_post[8];
+  int sel_idx[8];
+  int nsel = 0;
+  for (int s = 0; s < ng && s < 8; s++) {
+    float best = -1.f;
+    int bi = 0x7fffffff;
+#pragma unroll 1
+    for (int i = 0; i < kMaxGaussPerLane; i++) {
+      int g = lane + i * 32;
+      if (g >= G) break;
+      if (ll[i] > best) {
+        best = ll[i];
+        bi = g;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (best < 0.f) break;
+    sel_post[nsel] = best;
+    sel_idx[nsel] = bi;
+    nsel++;
+    if ((bi & 31) == lane) ll[bi >> 5] = -1.f;
+  }
+  // prune + renormalise (posterior.cc:490-505), all lanes redundantly
+  float tot = 0.f;
+  for (int s = 0; s < nsel; s++) tot = __fadd_rn(tot, sel_post[s]);
+  const float cutoff = __fmul_rn(min_post, tot);
+  while (nsel > 1 && sel_post[nsel - 1] < cutoff) {
+    tot = __fsub_rn(tot, sel_post[nsel - 1]);
+    nsel--;
+  }
+  const float inv_tot = (float)(1.0 / (double)tot);
+  const float sc = p.posterior_scale;  // * weight (1.0)
+  if (lane < p.num_gselect) {
+    int idx = -1;
+    float w = 0.f;
+    if (lane < nsel) {
+      idx = sel_idx[lane];
+      w = __fmul_rn(__fmul_rn(sel_post[lane], inv_tot), sc);
+    }
+    p.post_idx[(size_t)row * p.num_gselect + lane] = idx;
+    p.post_w[(size_t)row * p.num_gselect + lane] = w;
+  }
+}
+
+// ---------------------------------------------------------------------------- statistics
+// wf[u][g][:] += w * x_t  (double; order-insensitive at 1e-16) ; gw[u][g] = float sum over frames in
+// frame order (GaussInfo::tot_weight is a float accumulated in frame order).
+__global__ void __launch_bounds__(256) ivec_acc_kernel(IvecParams p) {
+  const int u = blockIdx.y;
+  const int T = p.num_frames[u];
+  const size_t base = (size_t)p.frame_offset[u];
+  const float *feats = p.online_cmvn_iextractor ? p.x_norm : p.x_raw;
+  const int D = p.ldim, S = p.num_gselect;
+  double *wf = p.wf + (size_t)u * p.num_gauss * D;
+  const int per = S * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)T * per;
+       i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i / per), r = (int)(i - (long long)t * per);
+    int s = r / D, d = r - s * D;
+    int g = p.post_idx[(base + t) * S + s];
+    if (g < 0) continue;
+    double w = (double)p.post_w[(base + t) * S + s];
+    atomicAdd(&wf[(size_t)g * D + d], w * (double)feats[(base + t) * D + d]);
+  }
+}
+
+__global__ void __launch_bounds__(256) ivec_gw_kernel(IvecParams p) {
+  const int u = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = p.num_frames[u], S = p.num_gselect;
+  const size_t base = (size_t)p.frame_offset[u];
+  extern __shared__ int spost[];  // tile of posteriors: idx then weight bits
+  float acc = 0.f;
+  const int tile = 256;
+  for (int t0 = 0; t0 < T * S; t0 += tile) {
+    int n = min(tile, T * S - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      spost[i] = p.post_idx[base * S + t0 + i];
+      spost[tile + i] = __float_as_int(p.post_w[base * S + t0 + i]);
+    }
+    __syncthreads();
+    if (g < p.num_gauss)
+      for (int i = 0; i < n; i++)
+        if (spost[i] == g) acc = __fadd_rn(acc, __int_as_float(spost[tile + i]));
+  }
+  if (g < p.num_gauss) p.gw[(size_t)u * p.num_gauss + g] = acc;
+}
+
+// linear[u][r] = prior + sum_g sum_d sigma_inv_m[g][d][r] * wf[u][g][d]
+// quad[u][k]   = prior + sum_g gw[u][g] * U[g][k]
+// One CTA per (column tile, group of UT utterances); the extractor tables are read once per group.
+constexpr int kUT = 8;
+__global__ void __launch_bounds__(128) ivec_linear_kernel(IvecParams p) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int u0 = blockIdx.y * kUT;
+  const int R = p.ivector_dim, GD = p.num_gauss * p.ldim;
+  extern __shared__ double swf[];  // [kUT][chunk]
+  const int chunk = 256;
+  double acc[kUT];
+#pragma unroll
+  for (int j = 0; j < kUT; j++) acc[j] = 0.0;
+  for (int k0 = 0; k0 < GD; k0 += chunk) {
+    int n = min(chunk, GD - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kUT * n; i += blockDim.x) {
+      int j = i / n, k = i - j * n;
+      swf[j * chunk + k] = (u0 + j < p.n_utts) ? p.wf[(size_t)(u0 + j) * GD + k0 + k] : 0.0;
+    }
+    __syncthreads();
+    if (r < R) {
+      for (int k = 0; k < n; k++) {
+        double m = p.sigma_inv_m[(size_t)(k0 + k) * R + r];
+#pragma unroll
+        for (int j = 0; j < kUT; j++) acc[j] = fma(m, swf[j * chunk + k], acc[j]);
+      }
+    }
+  }
+  if (r < R)
+    for (int j = 0; j < kUT; j++)
+      if (u0 + j < p.n_utts) p.linear[(size_t)(u0 + j) * R + r] = acc[j];
+}
+
+__global__ void __launch_bounds__(128) ivec_quad_kernel(IvecParams p) {
+  const int R = p.ivector_dim, P = R * (R + 1) / 2, G = p.num_gauss;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int u0 = blockIdx.y * kUT;
+  extern __shared__ double sgw[];  // [kUT][G]
+  for (int i = threadIdx.x; i < kUT * G; i += blockDim.x) {
+    int j = i / G, g = i - j * G;
+    sgw[i] = (u0 + j < p.n_utts) ? (double)p.gw[(size_t)(u0 + j) * G + g] : 0.0;
+  }
+  __syncthreads();
+  if (k >= P) return;
+  double acc[kUT];
+#pragma unroll
+  for (int j = 0; j < kUT; j++) acc[j] = 0.0;
+  for (int g = 0; g < G; g++) {
+    double uv = p.u[(size_t)g * P + k];
+#pragma unroll
+    for (int j = 0; j < kUT; j++) acc[j] = fma(sgw[j * G + g], uv, acc[j]);
+  }
+  for (int j = 0; j < kUT; j++)
+    if (u0 + j < p.n_utts) p.quad[(size_t)(u0 + j) * P + k] = acc[j];
+}
+
+// ------------------------------------------------------------------------------- CG solve
+// One CTA per utterance: adds the prior terms (ivector-extractor.cc:786-798, 652-667), then
+// LinearCgd in double with the reference's residual-recompute rule.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(128) ivec_cg_kernel(IvecParams p) {
+  const int u = blockIdx.x, R = p.ivector_dim, P = R * (R + 1) / 2;
+  extern __shared__ double sh[];
+  double *A = sh;            // [R*R] dense symmetric
+  double *b = A + (size_t)R * R, *x = b + R, *r = x + R, *pv = r + R, *Ap = pv + R, *red = Ap + R;
+  const int tid = threadIdx.x;
+  // total weight (double sum of the float per-Gaussian totals)
+  double tw = 0.0;
+  for (int g = tid; g < p.num_gauss; g += blockDim.x) tw += (double)p.gw[(size_t)u * p.num_gauss + g];
+  tw = block_sum(tw, red);
+  double prior_scale_change = 0.0;
+  if (p.max_count > 0.f) {
+    double mc = (double)p.max_count;
+    double old_scale = fmax(0.0, mc) / mc, new_scale = fmax(tw, mc) / mc;
+    prior_scale_change = new_scale - old_scale;
+  }
+  const double *q = p.quad + (size_t)u * P;
+  for (int i = tid; i < R * R; i += blockDim.x) {
+    int a = i / R, c = i - a * R;
+    int hi = a > c ? a : c, lo = a > c ? c : a;
+    double v = q[(size_t)hi * (hi + 1) / 2 + lo];
+    if (a == c) v += 1.0 + prior_scale_change;
+    A[i] = v;
+  }
+  for (int i = tid; i < R; i += blockDim.x) {
+    double v = p.linear[(size_t)u * R + i];
+    if (i == 0) v += p.prior_offset + p.prior_offset * prior_scale_change;
+    b[i] = v;
+    x[i] = i == 0 ? p.prior_offset : 0.0;
+  }
+  __syncthreads();
+  const bool have_data = tw > 0.0;
+  auto matvec = [&](const double *v, double *out) {  // out = A v
+    for (int i = tid; i < R; i += blockDim.x) {
+      double acc = 0.0;
+      const double *row = A + (size_t)i * R;
+      for (int k = 0; k < R; k++) acc = fma(row[k], v[k], acc);
+      out[i] = acc;
+    }
+    __syncthreads();
+  };
+  auto dot = [&](const double *a, const double *c) {
+    double v = 0.0;
+    for (int i = tid; i < R; i += blockDim.x) v += a[i] * c[i];
+    return block_sum(v, red);
+  };
+  if (have_data) {
+    matvec(x, Ap);
+    for (int i = tid; i < R; i += blockDim.x) {
+      pv[i] = b[i] - Ap[i];
+      r[i] = -pv[i];
+    }
+    __syncthreads();
+    double r_cur = dot(r, r), r_init = r_cur, r_recompute = r_cur;
+    const double max_err_sq = DBL_MIN, rf = 0.01 * 0.01, inv_rf = 1.0 / rf;
+    for (int k = 0; k < R + 5 && k != p.num_cg_iters; k++) {
+      matvec(pv, Ap);
+      double alpha = -dot(pv, r) / dot(pv, Ap);
+      for (int i = tid; i < R; i += blockDim.x) {
+        x[i] += alpha * pv[i];
+        r[i] += alpha * Ap[i];
+      }
+      __syncthreads();
+      double r_next = dot(r, r);
+      if (r_next < rf * r_recompute || r_next > inv_rf * r_recompute) {
+        matvec(x, Ap);
+        for (int i = tid; i < R; i += blockDim.x) r[i] = Ap[i] - b[i];
+        __syncthreads();
+        r_next = dot(r, r);
+        r_recompute = r_next;
+      }
+      if (r_next <= max_err_sq) break;
+      double beta = r_next / r_cur;
+      for (int i = tid; i < R; i += blockDim.x) pv[i] = beta * pv[i] - r[i];
+      __syncthreads();
+      r_cur = r_next;
+    }
+    (void)r_init;
+  }
+  // nnet input: float copy, prior offset removed from the first element
+  // (online-ivector-feature.cc:344-347)
+  for (int i = tid; i < R; i += blockDim.x) {
+    float f = (float)x[i];
+    if (i == 0) f = (float)((double)f - p.prior_offset);
+    p.ivector[(size_t)u * p.ivector_ld + i] = f;
+  }
+}
+
+void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
+  if (p.n_utts == 0) return;
+  const int G = p.num_gauss, D = p.ldim, R = p.ivector_dim, P = R * (R + 1) / 2;
+  if (p.total_frames > 0) {
+    dim3 g1((p.max_frames + kLdaFrames - 1) / kLdaFrames, p.n_utts);
+    size_t sm1 = (size_t)2 * (kLdaFrames + p.left + p.right) * p.dim * sizeof(float);
+    splice_lda_kernel<<<g1, 256, sm1, stream>>>(p);
+    size_t sm2 = (size_t)8 * 2 * D * sizeof(float);
+    ubm_post_kernel<<<(p.total_frames + 7) / 8, 256, sm2, stream>>>(p);
+  }
+  cudaMemsetAsync(p.wf, 0, (size_t)p.n_utts * G * D * sizeof(double), stream);
+  if (p.total_frames > 0) {
+    int per_utt_blocks = (p.max_frames * p.num_gselect * D + 255) / 256;
+    if (per_utt_blocks > 64) per_utt_blocks = 64;
+    if (per_utt_blocks < 1) per_utt_blocks = 1;
+    ivec_acc_kernel<<<dim3(per_utt_blocks, p.n_utts), 256, 0, stream>>>(p);
+  }
+  ivec_gw_kernel<<<dim3((G + 255) / 256, p.n_utts), 256, 2 * 256 * sizeof(int), stream>>>(p);
+  int groups = (p.n_utts + kUT - 1) / kUT;
+  ivec_linear_kernel<<<dim3((R + 127) / 128, groups), 128, (size_t)kUT * 256 * sizeof(double), stream>>>(p);
+  ivec_quad_kernel<<<dim3((P + 127) / 128, groups), 128, (size_t)kUT * G * sizeof(double), stream>>>(p);
+  size_t sm3 = ((size_t)R * R + 5 * R + 8) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ivec_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  ivec_cg_kernel<<<p.n_utts, 128, sm3, stream>>>(p);
+}
+
+}  // namespace rs

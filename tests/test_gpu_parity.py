@@ -1,0 +1,128 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, stage by stage and end to end.
+
+The oracle is (a) the reference binaries in oracle/_ref (built from /root/reference by
+oracle/build_ref.py; they travel to the GPU box) and (b) the numpy restatement oracle/kaldi_np.py.
+Tolerances are stated per test; word sequences and frame counts must be identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from rhasspy_speech_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_run
+    if not ref_run.available():
+        pytest.skip("oracle/_ref not built")
+    return ref_run
+
+
+@pytest.fixture(scope="module")
+def tiny(lib, tiny_model):
+    m = lib.Model(tiny_model.final_mdl, tiny_model.online_conf, 0)
+    g = lib.Graph(tiny_model.hclg, tiny_model.words_txt, 0)
+    return m, g, lib.Decoder(m, g)
+
+
+def _write_wavs(synth, tmp, utts):
+    paths = []
+    for i, pcm in enumerate(utts):
+        p = os.path.join(str(tmp), "u%03d.wav" % i)
+        synth.write_wav(p, pcm)
+        paths.append(p)
+    return paths
+
+
+def test_mfcc_matches_reference(tiny, tiny_model, utterances, ref, synth, tmp_path):
+    _, _, dec = tiny
+    hyp = dec.decode_pcm(utterances)
+    conf = os.path.join(tiny_model.model_dir, "model", "online", "conf", "mfcc.conf")
+    feats = ref.mfcc(conf, _write_wavs(synth, tmp_path, utterances))
+    for u, f in enumerate(feats):
+        got = dec.fetch(0, u)
+        assert got.shape == f.shape
+        # window + FFT are bit-exact by construction; the mel/DCT dot products differ in summation
+        # order from OpenBLAS: a few ulp of C0 (~1e2)
+        assert np.abs(got - f).max() <= 2e-4, np.abs(got - f).max()
+    assert hyp.n_utts == len(utterances)
+
+
+def test_ivector_matches_oracle(tiny, tiny_model, utterances):
+    from oracle import kaldi_np as K
+    _, _, dec = tiny
+    dec.decode_pcm(utterances)
+    conf = os.path.join(tiny_model.model_dir, "model", "online", "conf")
+    s = K.IvectorSetup.from_conf(os.path.join(conf, "ivector_extractor.conf"))
+    for u in range(len(utterances)):
+        mf = dec.fetch(0, u)
+        want = K.ivector_offline(s, mf)
+        got = dec.fetch(1, u)[0]
+        assert np.abs(got - want).max() <= 1e-4, np.abs(got - want).max()
+        # CMVN'd features and LDA features, against the restatement on the same MFCCs
+        norm = K.online_cmvn(mf, s.global_cmvn, s.cmvn)
+        assert np.abs(dec.fetch(3, u) - norm).max() <= 1e-5
+        lda = K.lda_feats(s, mf, True)
+        assert np.abs(dec.fetch(4, u) - lda).max() <= 2e-4
+
+
+def test_loglikes_match_reference(tiny, tiny_model, utterances, ref, synth):
+    _, _, dec = tiny
+    dec.decode_pcm(utterances)
+    feats = [dec.fetch(0, u) for u in range(len(utterances))]
+    ivs = [dec.fetch(1, u)[0] for u in range(len(utterances))]
+    want = ref.nnet_loglikes(tiny_model.final_mdl, feats, ivs, frame_subsampling_factor=3)
+    for u, w in enumerate(want):
+        got = dec.fetch(2, u)
+        assert got.shape == w.shape, (got.shape, w.shape)
+        assert np.abs(got - w).max() <= 1e-4, np.abs(got - w).max()   # north-star tolerance
+        f64 = synth.nnet_forward(tiny_model.nnet_params, feats[u].astype(np.float64), ivs[u].astype(np.float64))[::3]
+        assert np.abs(got - f64).max() <= 1e-4
+
+
+def test_decoder_matches_reference_on_loglikes(tiny, tiny_model, utterances, ref):
+    _, _, dec = tiny
+    dec.decode_pcm(utterances)
+    lls = [dec.fetch(2, u) for u in range(len(utterances))]
+    # sharper and flatter score distributions move the beam pruning
+    for scale in (1.0, 0.3, 3.0):
+        mats = [np.ascontiguousarray(l * np.float32(scale)) for l in lls]
+        want = ref.decode_loglikes(tiny_model.final_mdl, tiny_model.hclg, mats)
+        got = dec.decode_loglikes(mats)
+        for u in range(len(mats)):
+            assert got.words[u] == want.get("utt%05d-1" % u), (scale, u, got.words[u], want.get("utt%05d-1" % u))
+
+
+def test_transcripts_match_reference(tiny, tiny_model, utterances, ref, synth, tmp_path):
+    _, graph, dec = tiny
+    wavs = _write_wavs(synth, tmp_path, utterances)
+    want, _, _ = ref.transcribe_wavs(tiny_model.final_mdl, tiny_model.online_conf, tiny_model.hclg, tiny_model.words_txt, wavs)
+    got = dec.decode_wavs(wavs)
+    assert list(got.status) == [0] * len(wavs)
+    for u in range(len(wavs)):
+        assert got.words[u] == want.get("utt%05d-1" % u), (u, got.words[u], want.get("utt%05d-1" % u))
+
+
+def test_edge_cases(tiny, utterances):
+    """Empty, too-short (< one window), exactly one window, and ragged batches."""
+    _, _, dec = tiny
+    one = utterances[0]
+    batch = [np.zeros(0, np.int16), one[:399], one[:400], one[:401], one, one[:8000]]
+    hyp = dec.decode_pcm(batch)
+    assert list(hyp.n_hyp[:2]) == [0, 0] and hyp.words[0] is None and hyp.words[1] is None
+    assert list(hyp.num_frames) == [0, 0, 1, 1, (1 + (len(one) - 400) // 160 + 2) // 3, (1 + (8000 - 400) // 160 + 2) // 3]
+    # batching must not change a result: decode the same utterances one by one
+    for u in (2, 4, 5):
+        single = dec.decode_pcm([batch[u]])
+        assert single.words[0] == hyp.words[u]
+    assert dec.decode_pcm([]).n_utts == 0
