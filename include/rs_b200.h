@@ -120,6 +120,13 @@ int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t
 /* Text description of the compiled acoustic-model plan (one line per launch). */
 const char *rs_model_plan(const rs_model *m);
 
+/* Host-only validation of the artefacts (no GPU needed): parse final.mdl + online.conf and every
+ * file they name / HCLG.fst + words.txt exactly as the loaders above do, and report what was found.
+ * rs_model_check writes a summary + the compiled plan into `out`; rs_graph_check fills
+ * counts[6] = {states, emitting arcs, epsilon-input arcs, start state, final states, word symbols}. */
+int rs_model_check(const char *final_mdl, const char *online_conf, char *out, size_t outlen, char *err, size_t errlen);
+int rs_graph_check(const char *hclg_fst, const char *words_txt, int64_t *counts, char *err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,12 @@ def main():
         n.append("build %s: cc %s" % (o, s))
         n.append("build %s: link %s | %s" % (e, o, lib))
         targets.append(e)
+    # intermediate-value probe (our own source, linked against the reference library)
+    probe_o = os.path.join(OUT, "obj", "bin__ref-probe.o")
+    probe_e = os.path.join(OUT, "bin", "ref-probe")
+    n.append("build %s: cc %s" % (probe_o, os.path.join(HERE, "ref_probe.cc")))
+    n.append("build %s: link %s | %s" % (probe_e, probe_o, lib))
+    targets.append(probe_e)
     n.append("default " + " ".join(targets))
     with open(os.path.join(OUT, "build.ninja"), "w") as f:
         f.write("\n".join(n) + "\n")

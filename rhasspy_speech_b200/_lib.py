@@ -69,6 +69,8 @@ SYMBOLS = [
     ("rs_decoder_timings", C.c_int, [_P, C.POINTER(Timings)]),
     ("rs_debug_fetch", C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + _ERR),
     ("rs_model_plan", C.c_char_p, [_P]),
+    ("rs_model_check", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t] + _ERR),
+    ("rs_graph_check", C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)] + _ERR),
 ]
 
 _lib = None
@@ -99,23 +101,47 @@ def _check(ok: bool, err):
         raise RsError(err.value.decode(errors="replace"))
 
 
+def model_check(final_mdl: str, online_conf: str) -> str:
+    """Host-only parse of the model artefacts; returns a summary and the compiled plan (no GPU needed)."""
+    lib = load_library()
+    out = C.create_string_buffer(1 << 16)
+    err = C.create_string_buffer(ERRLEN)
+    rc = lib.rs_model_check(os.fsencode(final_mdl), os.fsencode(online_conf), out, len(out), err, ERRLEN)
+    _check(rc == 0, err)
+    return out.value.decode()
+
+
+def graph_check(hclg_fst: str, words_txt: Optional[str]) -> dict:
+    lib = load_library()
+    counts = (C.c_int64 * 6)()
+    err = C.create_string_buffer(ERRLEN)
+    rc = lib.rs_graph_check(os.fsencode(hclg_fst), os.fsencode(words_txt) if words_txt else None, counts, err, ERRLEN)
+    _check(rc == 0, err)
+    return dict(zip(("states", "emitting_arcs", "epsilon_arcs", "start", "final_states", "words"), [int(x) for x in counts]))
+
+
 class Hypotheses:
     """Python copy of an rs_result."""
 
     def __init__(self, r: Result):
         n = r.n_utts
         self.n_utts = n
-        off = np.ctypeslib.as_array(r.word_offset, shape=(n + 1,)).copy() if n else np.zeros(1, np.int32)
-        total = int(off[-1])
-        ids = np.ctypeslib.as_array(r.word_ids, shape=(max(total, 1),))[:total].copy()
-        self.n_hyp = np.ctypeslib.as_array(r.n_hyp, shape=(max(n, 1),))[:n].copy()
+
+        def arr(ptr, count):
+            if count <= 0 or not ptr:
+                return np.zeros(0, dtype=np.ctypeslib.as_array((ptr._type_ * 1)()).dtype)
+            return np.ctypeslib.as_array(ptr, shape=(count,)).copy()
+
+        off = arr(r.word_offset, n + 1) if n else np.zeros(1, np.int32)
+        ids = arr(r.word_ids, int(off[-1]))
+        self.n_hyp = arr(r.n_hyp, n)
         self.words: List[Optional[List[int]]] = []
         for u in range(n):
             self.words.append([int(x) for x in ids[off[u]:off[u + 1]]] if self.n_hyp[u] else None)
-        self.graph_cost = np.ctypeslib.as_array(r.graph_cost, shape=(max(n, 1),))[:n].copy()
-        self.acoustic_cost = np.ctypeslib.as_array(r.acoustic_cost, shape=(max(n, 1),))[:n].copy()
-        self.num_frames = np.ctypeslib.as_array(r.num_frames, shape=(max(n, 1),))[:n].copy()
-        self.status = np.ctypeslib.as_array(r.status, shape=(max(n, 1),))[:n].copy()
+        self.graph_cost = arr(r.graph_cost, n)
+        self.acoustic_cost = arr(r.acoustic_cost, n)
+        self.num_frames = arr(r.num_frames, n)
+        self.status = arr(r.status, n)
 
 
 class Model:

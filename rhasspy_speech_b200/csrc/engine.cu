@@ -1194,6 +1194,38 @@ int rs_stream_finish(rs_stream *s, rs_result **out, char *err, size_t errlen) {
 
 void rs_stream_close(rs_stream *s) { delete reinterpret_cast<StreamImpl *>(s); }
 
+int rs_model_check(const char *final_mdl, const char *online_conf, char *out, size_t outlen, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  Model m;
+  LoadModel(final_mdl, online_conf, &m);
+  std::ostringstream os;
+  os << "pdfs " << m.trans.num_pdfs << " tids " << m.trans.tid2pdf.size() - 1 << " sf " << m.frame_subsampling_factor
+     << " feat_dim " << m.mfcc.num_ceps << " ivector_dim " << (m.has_ivector ? m.ie.ivector_dim : 0) << " num_gauss "
+     << (m.has_ivector ? m.ubm.num_gauss : 0) << " priors " << m.log_priors.size() << "\n"
+     << DescribePlan(m.plan);
+  SetErr(out, outlen, os.str());
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_graph_check(const char *hclg_fst, const char *words_txt, int64_t *counts, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  Graph g;
+  LoadGraph(hclg_fst, words_txt ? words_txt : "", &g);
+  if (counts) {
+    counts[0] = g.num_states;
+    counts[1] = (int64_t)g.e_next.size();
+    counts[2] = (int64_t)g.p_next.size();
+    counts[3] = g.start;
+    int64_t nf = 0;
+    for (float f : g.final_cost) nf += std::isfinite(f);
+    counts[4] = nf;
+    counts[5] = (int64_t)g.words.size();
+  }
+  return 0;
+  API_GUARD_END(1)
+}
+
 int rs_decoder_timings(const rs_decoder *d_, rs_timings *t) {
   const DecoderImpl *d = reinterpret_cast<const DecoderImpl *>(d_);
   if (!d || !t) return 1;

@@ -21,6 +21,7 @@ namespace rs {
 
 constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
 constexpr int kGemmThreads = 256;
+constexpr int kChunkTiles = 4;  // 4 x BK = 64 products per first-level sum
 
 __device__ __forceinline__ float apply_ops(float v, int r, int c, const GemmParams &p) {
 #pragma unroll 1
@@ -140,11 +141,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
     }
   };
 
-  float acc[8][8];
+  // Two-level summation: products are accumulated in `part` over kChunkTiles k-tiles (64 terms) and
+  // then folded into `acc`, the way a K-blocked BLAS kernel folds register sums into C.  This keeps
+  // the rounding error of long dot products (K up to 2048) at the level of the reference's sgemm.
+  float acc[8][8], part[8][8];
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; j++) acc[i][j] = part[i][j] = 0.f;
   const int tx = tid & 15, ty = tid >> 4;
 
   set_slab(0);
@@ -165,7 +169,16 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
 #pragma unroll
       for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; j++) part[i][j] = fmaf(a[i], b[j], part[i][j]);
+    }
+    if ((it % kChunkTiles) == kChunkTiles - 1 || it + 1 == n_tiles) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          acc[i][j] += part[i][j];
+          part[i][j] = 0.f;
+        }
     }
     if (it + 1 < n_tiles) store_tile(buf ^ 1);
     __syncthreads();

@@ -1,0 +1,280 @@
+"""Python surface of the decoder: drop-in for rhasspy-speech's transcribers on the hot path.
+
+Mirrors, with the same names, argument meaning and error behaviour:
+
+* ``rhasspy_speech.transcribe_wav.KaldiNnet3WavTranscriber``      (reference transcribe_wav.py:15-105)
+* ``rhasspy_speech.transcribe_stream.KaldiNnet3StreamTranscriber``  (reference transcribe_stream.py:18-129)
+* the legacy ``rhasspy_speech.KaldiTranscriber`` spelling used by the reference's own tests
+  (tests/test_en_US-zamia.py:7,46-57).
+
+Where the reference spawns ``online2-wav-nnet3-latgen-faster | lattice-to-nbest | nbest-to-linear``
+(or ``online2-cli-nnet3-decode-faster``) per call, these classes call the C ABI of librs_b200.so once;
+models and graphs are loaded once per (model_dir, graph_dir) and stay resident on the GPU.  The
+intermediate the reference passes around -- ``nbest_stdout``, a Kaldi text Int32Vector archive with
+one ``utt-<k> id id ... \\n`` line per hypothesis (kaldi/src/util/kaldi-holder-inl.h:244-251,
+latbin/lattice-to-nbest.cc:104-107) -- is reproduced byte for byte so the unchanged tail of the
+reference (int2sym, ``get_fuzzy_text``, ``decode_meta``) can consume it.
+
+There is no CPU fallback: without the CUDA library or a GPU these classes raise.
+"""
+from __future__ import annotations
+
+import asyncio
+import base64
+import json
+import re
+import threading
+from pathlib import Path
+from typing import AsyncIterable, Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+from . import _lib
+
+OUTPUT_PREFIX = "__output:"             # reference hassil_fst.py:32-33
+SENTENCE_OUTPUT = "__sentence_output:"
+
+_ENGINES: Dict[Tuple, "_Engine"] = {}
+_ENGINES_LOCK = threading.Lock()
+
+
+def decode_meta_single(text: str) -> str:
+    return base64.b32decode(text.encode("utf-8")).strip().decode("utf-8")
+
+
+def decode_meta(text: str) -> str:
+    """Restatement of reference hassil_fst.py:849-868 (output words carry base32 JSON metadata)."""
+    slots: Dict[str, str] = {}
+
+    def handle_match(m: "re.Match") -> str:
+        data = json.loads(decode_meta_single(m.group(1)))
+        slot_name = data.get("list")
+        slot_value = data["text"]
+        if slot_name:
+            slots[slot_name] = slot_value
+        return slot_value
+
+    text = re.sub(re.escape(OUTPUT_PREFIX) + "([0-9A-Z=]+)", handle_match, text)
+    match = re.search(re.escape(SENTENCE_OUTPUT) + "([0-9A-Z=]+)", text)
+    if match is None:
+        return text
+    return decode_meta_single(match.group(1)).format(**slots)
+
+
+class _Engine:
+    """One resident (model, graph, decoder) triple; serialises calls (an rs_decoder is single-threaded)."""
+
+    def __init__(self, final_mdl: Path, online_conf: Path, hclg: Path, words_txt: Path, device: int, **opts):
+        for f in (final_mdl, online_conf, hclg, words_txt):
+            if not Path(f).is_file():
+                # the reference fails with the Kaldi binary's stderr; keep its exception type and prefix
+                raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: cannot open %s" % f)
+        self.model = _lib.Model(str(final_mdl), str(online_conf), device)
+        self.graph = _lib.Graph(str(hclg), str(words_txt), device)
+        self.decoder = _lib.Decoder(self.model, self.graph, **opts)
+        self.lock = threading.Lock()
+
+    def words(self, ids: Sequence[int]) -> str:
+        out = []
+        for i in ids:
+            w = self.graph.word(i)
+            if w is None:
+                raise RuntimeError("Unexpected error running command int2sym.pl: undefined symbol %d" % i)
+            out.append(w)
+        return " ".join(out)
+
+
+def _engine(final_mdl: Path, online_conf: Path, graph_dir: Path, device: int, max_active: int, beam: float,
+            lattice_beam: float) -> _Engine:
+    key = (str(final_mdl), str(online_conf), str(graph_dir), device, max_active, float(beam), float(lattice_beam))
+    with _ENGINES_LOCK:
+        eng = _ENGINES.get(key)
+        if eng is None:
+            try:
+                eng = _Engine(final_mdl, online_conf, graph_dir / "HCLG.fst", graph_dir / "words.txt", device,
+                              max_active=max_active, beam=beam, lattice_beam=lattice_beam)
+            except _lib.RsError as e:
+                raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
+            _ENGINES[key] = eng
+        return eng
+
+
+def nbest_text(hyp: "_lib.Hypotheses", utt: int) -> bytes:
+    """The ``nbest-to-linear ... ark,t:-`` bytes for one utterance: ``utt-1 12 45 7 \\n`` (each id is
+    followed by a space); empty when nothing was decoded, as when the reference's lattice is empty."""
+    if hyp.words[utt] is None:
+        return b""
+    return ("utt-1 " + "".join("%d " % w for w in hyp.words[utt]) + "\n").encode()
+
+
+async def _fuzzy(nbest_stdout: bytes, lang_dir: Path, tools) -> Optional[Tuple[str, float]]:
+    """Out-of-vocabulary rejection (reference transcribe_util.py:11-88) is kept on the reference's own
+    OpenFst tools: a 'next' row of the scope table.  Without G.fuzzy.fst it is a no-op, as there."""
+    if not (lang_dir / "G.fuzzy.fst").exists():
+        return None
+    if tools is None or not hasattr(tools, "async_run_pipeline"):
+        raise RuntimeError("Unexpected error running command fstcompile: G.fuzzy.fst is present but no KaldiTools were given")
+    from rhasspy_speech.transcribe_util import get_fuzzy_text  # the unchanged reference tail
+    return await get_fuzzy_text(nbest_stdout, lang_dir, tools)
+
+
+class _Base:
+    def __init__(self, model_dir, graph_dir, tools=None, max_active: int = 7000, lattice_beam: float = 8.0,
+                 acoustic_scale: float = 1.0, beam: float = 24.0, device: int = 0):
+        self.model_dir = Path(model_dir)
+        self.graph_dir = Path(graph_dir)
+        self.tools = tools
+        self.max_active = max_active
+        self.lattice_beam = lattice_beam
+        # as in the reference, this scale is only applied when ranking n-best lists (lattice-to-nbest
+        # --acoustic-scale, transcribe_wav.py:65); the search always runs at 1.0 (:54)
+        self.acoustic_scale = acoustic_scale
+        self.beam = beam
+        self.device = device
+
+    def _paths(self) -> Tuple[Path, Path]:
+        return (self.model_dir / "model" / "model" / "final.mdl", self.model_dir / "model" / "online" / "conf" / "online.conf")
+
+    def _get_engine(self) -> _Engine:
+        final_mdl, online_conf = self._paths()
+        return _engine(final_mdl, online_conf, self.graph_dir, self.device, self.max_active, self.beam, self.lattice_beam)
+
+    def _check_nbest(self, nbest: int):
+        if nbest != 1 or self.acoustic_scale != 1.0:
+            raise NotImplementedError("n-best > 1 and lattice rescaling need the lattice output (scope row f1); "
+                                      "the GPU decoder returns the single best path")
+
+    async def _finish(self, eng: _Engine, nbest_stdout: bytes, lang_dir, max_fuzzy_cost, require_fuzzy) -> List[str]:
+        lang_dir = Path(lang_dir)
+        fuzzy_result = await _fuzzy(nbest_stdout, lang_dir, self.tools)
+        if fuzzy_result is not None:
+            text, cost = fuzzy_result
+            if cost <= max_fuzzy_cost:  # TypeError when max_fuzzy_cost is None, exactly as the reference
+                return [decode_meta(text)]
+        if require_fuzzy:
+            return []
+        texts: List[str] = []
+        for line in nbest_stdout.decode().splitlines():
+            if line.startswith("utt-"):
+                parts = line.strip().split()
+                if len(parts) > 1:      # the reference drops hypotheses without words (transcribe_wav.py:99-103)
+                    texts.append(decode_meta(eng.words([int(x) for x in parts[1:]])))
+        return texts
+
+
+class KaldiNnet3WavTranscriber(_Base):
+    async def async_transcribe(self, wav_path, lang_dir, nbest: int = 1, max_fuzzy_cost: Optional[float] = None,
+                               require_fuzzy: bool = False) -> List[str]:
+        self._check_nbest(nbest)
+        eng = self._get_engine()
+        loop = asyncio.get_running_loop()
+
+        def run():
+            with eng.lock:
+                try:
+                    return eng.decoder.decode_wavs([str(wav_path)])
+                except _lib.RsError as e:
+                    raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
+        hyp = await loop.run_in_executor(None, run)
+        return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)
+
+    async def async_transcribe_many(self, wav_paths: Sequence, lang_dir, max_fuzzy_cost: Optional[float] = None,
+                                    require_fuzzy: bool = False) -> List[List[str]]:
+        """Batched extension: one GPU batch for all files; element i equals async_transcribe(wav_paths[i])."""
+        eng = self._get_engine()
+        loop = asyncio.get_running_loop()
+
+        def run():
+            with eng.lock:
+                try:
+                    return eng.decoder.decode_wavs([str(p) for p in wav_paths])
+                except _lib.RsError as e:
+                    raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
+        hyp = await loop.run_in_executor(None, run)
+        return [await self._finish(eng, nbest_text(hyp, u), lang_dir, max_fuzzy_cost, require_fuzzy)
+                for u in range(len(wav_paths))]
+
+    async def async_transcribe_rescore(self, *args, **kwargs):
+        raise NotImplementedError("lattice rescoring (reference transcribe_wav.py:107-232) is scope row f3")
+
+
+class KaldiNnet3StreamTranscriber(_Base):
+    async def async_transcribe(self, audio_stream: AsyncIterable[Optional[bytes]], lang_dir, nbest: int = 1,
+                               max_fuzzy_cost: Optional[float] = None, require_fuzzy: bool = False) -> List[str]:
+        """audio_stream yields raw 16 kHz mono s16le chunks of any size (reference transcribe_stream.py:38-82)."""
+        self._check_nbest(nbest)
+        eng = self._get_engine()
+        stream = eng.decoder.open_stream()
+        try:
+            pending = b""
+            async for chunk in audio_stream:
+                if not chunk:
+                    continue
+                data = pending + chunk
+                keep = len(data) & ~1
+                pending = data[keep:]
+                if keep:
+                    stream.accept(data[:keep])
+            loop = asyncio.get_running_loop()
+
+            def run():
+                with eng.lock:
+                    return stream.finish()
+            hyp = await loop.run_in_executor(None, run)
+        finally:
+            stream.close()
+        return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)
+
+    async def async_transcribe_rescore(self, *args, **kwargs):
+        raise NotImplementedError("lattice rescoring (reference transcribe_stream.py:131-243) is scope row f3")
+
+
+class KaldiTranscriber:
+    """Legacy synchronous spelling: ``KaldiTranscriber(model_dir, graph_dir, kaldi_bin_dir).transcribe_wav(path) -> str``
+    (reference tests/test_en_US-zamia.py:46-57; there ``model_dir`` already points at ``<model>/model``)."""
+
+    def __init__(self, model_dir, graph_dir, kaldi_bin_dir=None, max_active: int = 7000, lattice_beam: float = 8.0,
+                 acoustic_scale: float = 1.0, beam: float = 24.0, device: int = 0):
+        self.model_dir = Path(model_dir)
+        self.graph_dir = Path(graph_dir)
+        self.kaldi_bin_dir = kaldi_bin_dir
+        self.max_active, self.lattice_beam, self.acoustic_scale, self.beam, self.device = max_active, lattice_beam, acoustic_scale, beam, device
+
+    def _get_engine(self) -> _Engine:
+        return _engine(self.model_dir / "model" / "final.mdl", self.model_dir / "online" / "conf" / "online.conf",
+                       self.graph_dir, self.device, self.max_active, self.beam, self.lattice_beam)
+
+    def _text(self, eng: _Engine, hyp, utt: int) -> str:
+        return decode_meta(eng.words(hyp.words[utt])) if hyp.words[utt] else ""
+
+    def transcribe_wav(self, wav_path) -> str:
+        eng = self._get_engine()
+        with eng.lock:
+            try:
+                hyp = eng.decoder.decode_wavs([str(wav_path)])
+            except _lib.RsError as e:
+                raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
+        return self._text(eng, hyp, 0)
+
+    def transcribe_wavs(self, wav_paths: Sequence) -> List[str]:
+        eng = self._get_engine()
+        with eng.lock:
+            hyp = eng.decoder.decode_wavs([str(p) for p in wav_paths])
+        return [self._text(eng, hyp, u) for u in range(len(wav_paths))]
+
+    def transcribe_stream(self, chunks: Iterable[bytes]) -> str:
+        eng = self._get_engine()
+        stream = eng.decoder.open_stream()
+        try:
+            pending = b""
+            for chunk in chunks:
+                if not chunk:
+                    continue
+                data = pending + chunk
+                keep = len(data) & ~1
+                pending = data[keep:]
+                if keep:
+                    stream.accept(data[:keep])
+            with eng.lock:
+                hyp = stream.finish()
+        finally:
+            stream.close()
+        return self._text(eng, hyp, 0)

@@ -1,0 +1,15 @@
+"""Two passes of the bench workload (reduced batch) for ncu launch lists / full captures."""
+import os, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rhasspy_speech_b200 import _lib, synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+tmp = tempfile.mkdtemp()
+p = synth.write_model(tmp, synth.ZAMIA_LIKE)
+utts = synth.make_utterances(n, seed=1234)
+model = _lib.Model(p.final_mdl, p.online_conf, 0)
+graph = _lib.Graph(p.hclg, p.words_txt, 0)
+dec = _lib.Decoder(model, graph)
+for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
+    hyp = dec.decode_pcm(utts)
+    print(dec.timings())

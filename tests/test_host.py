@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: the C ABI surface, the loaders / plan compiler inside the
+library (rs_model_check / rs_graph_check), the Python mirror of the reference's transcriber API."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from rhasspy_speech_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    """Every function include/rs_b200.h declares is exported by librs_b200.so and bound."""
+    with open(os.path.join(ROOT, "include", "rs_b200.h")) as f:
+        hdr = f.read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rs_[a-z_0-9]+)\s*\(", hdr))
+    bound = {name for name, _, _ in lib.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    dll = ctypes.CDLL(lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), name
+
+
+def test_no_cpu_fallback(lib, tiny_model):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lib.RsError, match="no CUDA device"):
+        lib.Model(tiny_model.final_mdl, tiny_model.online_conf, 0)
+    with pytest.raises(lib.RsError, match="no CUDA device"):
+        lib.Graph(tiny_model.hclg, tiny_model.words_txt, 0)
+
+
+def test_model_loader_and_plan(lib, tiny_model, synth):
+    txt = lib.model_check(tiny_model.final_mdl, tiny_model.online_conf)
+    head = txt.splitlines()[0]
+    assert "pdfs %d " % tiny_model.num_pdfs in head and " sf 3 " in head and "ivector_dim 30" in head
+    # context of the TINY net: lda (+-1) and tdnnf strides 1, 0, 3, 3  => 1 + 7 = 8 on each side
+    assert "context -8/+8" in txt and "align 3" in txt
+    # every TDNN-F layer is one GEMM launch with the ReLU, BatchNorm and bypass fused in
+    assert txt.count("gemm tdnnf") == 8 and txt.count("addscaled(0.66") == 4
+    assert "elementwise" not in txt and "logsoftmax" not in txt      # the xent branch is not computed
+    assert "uttgemm lda.utt" in txt                                  # iVector part of the first layer
+
+
+def test_model_loader_text_format(lib, synth, tmp_path):
+    """Kaldi text-mode files parse to the same plan as binary ones."""
+    import dataclasses
+    spec = dataclasses.replace(synth.TINY, binary=False, priors=True)
+    p = synth.write_model(str(tmp_path), spec)
+    txt = lib.model_check(p.final_mdl, p.online_conf)
+    assert "priors %d" % p.num_pdfs in txt.splitlines()[0]
+    assert "context -8/+8" in txt
+
+
+def test_model_loader_errors(lib, tiny_model, tmp_path):
+    with pytest.raises(lib.RsError, match="cannot open"):
+        lib.model_check(str(tmp_path / "missing.mdl"), tiny_model.online_conf)
+    bad = tmp_path / "online.conf"
+    bad.write_text("--feature-type=plp\n")
+    with pytest.raises(lib.RsError, match="feature-type"):
+        lib.model_check(tiny_model.final_mdl, str(bad))
+    junk = tmp_path / "HCLG.fst"
+    junk.write_bytes(b"not an fst at all, really")
+    with pytest.raises(lib.RsError, match="magic"):
+        lib.graph_check(str(junk), None)
+
+
+def test_graph_loader(lib, tiny_model, synth, tmp_path):
+    c = lib.graph_check(tiny_model.hclg, tiny_model.words_txt)
+    assert c["states"] == tiny_model.num_states
+    assert c["emitting_arcs"] + c["epsilon_arcs"] == tiny_model.num_arcs
+    assert c["epsilon_arcs"] > 0 and c["final_states"] > 0 and c["start"] == 0
+    assert c["words"] == len(tiny_model.words) + 2      # <eps> ... #0
+    # the aligned ConstFst variant (version 1) reads identically
+    p2 = synth.write_model(str(tmp_path), synth.TINY, aligned_fst=True)
+    assert lib.graph_check(p2.hclg, p2.words_txt) == c
+
+
+def test_python_surface_mirrors_reference():
+    """Same constructor / method signatures as reference transcribe_wav.py:16-42, transcribe_stream.py:19-45."""
+    import rhasspy_speech_b200 as pkg
+    for cls in (pkg.KaldiNnet3WavTranscriber, pkg.KaldiNnet3StreamTranscriber):
+        params = list(inspect.signature(cls.__init__).parameters)
+        assert params[:8] == ["self", "model_dir", "graph_dir", "tools", "max_active", "lattice_beam", "acoustic_scale", "beam"]
+        d = inspect.signature(cls.__init__).parameters
+        assert (d["max_active"].default, d["lattice_beam"].default, d["acoustic_scale"].default, d["beam"].default) == (7000, 8.0, 1.0, 24.0)
+        tp = list(inspect.signature(cls.async_transcribe).parameters)
+        assert tp[2:] == ["lang_dir", "nbest", "max_fuzzy_cost", "require_fuzzy"]
+        assert inspect.iscoroutinefunction(cls.async_transcribe) and inspect.iscoroutinefunction(cls.async_transcribe_rescore)
+    legacy = list(inspect.signature(pkg.KaldiTranscriber.__init__).parameters)
+    assert legacy[:4] == ["self", "model_dir", "graph_dir", "kaldi_bin_dir"]
+    assert hasattr(pkg.KaldiTranscriber, "transcribe_wav") and hasattr(pkg.KaldiTranscriber, "transcribe_stream")
+
+
+def test_decode_meta_and_nbest_text():
+    import base64
+    import json
+    from rhasspy_speech_b200 import transcribe as T
+    enc = lambda s: base64.b32encode(s.encode()).decode()
+    assert T.decode_meta("turn on the light") == "turn on the light"
+    word = T.OUTPUT_PREFIX + enc(json.dumps({"text": "kitchen", "list": "area"}))
+    sent = T.SENTENCE_OUTPUT + enc("lights on in {area}")
+    assert T.decode_meta("turn on " + word) == "turn on kitchen"
+    assert T.decode_meta("turn on " + word + " " + sent) == "lights on in kitchen"
+
+    class H:
+        words = [[12, 45, 7], None, []]
+    assert T.nbest_text(H, 0) == b"utt-1 12 45 7 \n"       # kaldi-holder-inl.h:244-251: each int is followed by a space
+    assert T.nbest_text(H, 1) == b""
+    assert T.nbest_text(H, 2) == b"utt-1 \n"
+
+
+def test_shard_utterances_balances_audio():
+    from rhasspy_speech_b200.shard import shard_utterances
+    rng = np.random.default_rng(3)
+    dur = rng.uniform(0.8, 5.0, 2048).tolist()
+    for world in (1, 2, 4, 8):
+        parts = shard_utterances(dur, world)
+        assert sorted(i for p in parts for i in p) == list(range(2048))
+        loads = [sum(dur[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= 5.0
+    assert shard_utterances([], 4) == [[], [], [], []]
