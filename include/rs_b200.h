@@ -117,6 +117,16 @@ int rs_decoder_timings(const rs_decoder *d, rs_timings *t);
  * Call with dst == NULL to query rows/cols. */
 int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t *rows, int32_t *cols, char *err,
                    size_t errlen);
+/* Test hook for the affine-layer kernels: one TDNN-style layer (TdnnComponent::Propagate,
+ * kaldi/src/nnet3/nnet-tdnn-component.cc:181-211) on a caller-provided activation matrix.
+ *   out[r, :] = sum_i src[r * stride + offsets[i], :] * w[:, i*k : (i+1)*k]^T (+ bias) (ReLU)
+ * src [rows x k], w [n x (k * n_offsets)], out [max(rows / stride, 1) x n], all row-major fp32.
+ * path 0 = fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel, 2 = same with the split (two-plane) store.
+ * Rows whose source row falls outside [0, rows) are unspecified (clamped by path 0, zero by 1/2).
+ * iters > 0 additionally times that many launches (CUDA events) and returns the mean in *ms. */
+int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offsets, int n_offsets, int stride,
+                  const float *w, int n, const float *bias, int relu, int path, int iters, float *out, float *ms,
+                  char *err, size_t errlen);
 /* Text description of the compiled acoustic-model plan (one line per launch). */
 const char *rs_model_plan(const rs_model *m);
 

@@ -68,6 +68,8 @@ SYMBOLS = [
     ("rs_streams_finish", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
     ("rs_decoder_timings", C.c_int, [_P, C.POINTER(Timings)]),
     ("rs_debug_fetch", C.c_int, [_P, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + _ERR),
+    ("rs_debug_gemm", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float)] + _ERR),
     ("rs_model_plan", C.c_char_p, [_P]),
     ("rs_model_check", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t] + _ERR),
     ("rs_graph_check", C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)] + _ERR),
@@ -118,6 +120,28 @@ def graph_check(hclg_fst: str, words_txt: Optional[str]) -> dict:
     rc = lib.rs_graph_check(os.fsencode(hclg_fst), os.fsencode(words_txt) if words_txt else None, counts, err, ERRLEN)
     _check(rc == 0, err)
     return dict(zip(("states", "emitting_arcs", "epsilon_arcs", "start", "final_states", "words"), [int(x) for x in counts]))
+
+
+def debug_gemm(src: np.ndarray, w: np.ndarray, offsets: Sequence[int] = (0,), stride: int = 1,
+               bias: Optional[np.ndarray] = None, relu: bool = False, path: int = 1, iters: int = 0, device: int = 0):
+    """One TDNN-style layer through the affine-layer kernels (rs_debug_gemm); returns (out, ms_per_launch)."""
+    lib = load_library()
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    rows, k = src.shape
+    n = w.shape[0]
+    assert w.shape[1] == k * len(offsets)
+    offs = (C.c_int * len(offsets))(*[int(o) for o in offsets])
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    m = max(rows // stride, 1)
+    out = np.zeros((m, n), dtype=np.float32)
+    ms = C.c_float()
+    err = C.create_string_buffer(ERRLEN)
+    rc = lib.rs_debug_gemm(device, src.ctypes.data, rows, k, offs, len(offsets), stride, w.ctypes.data, n,
+                           None if b is None else b.ctypes.data, int(relu), path, iters, out.ctypes.data, C.byref(ms),
+                           err, ERRLEN)
+    _check(rc == 0, err)
+    return out, ms.value
 
 
 class Hypotheses:

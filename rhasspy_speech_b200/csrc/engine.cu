@@ -11,6 +11,7 @@
 #include "../../include/rs_b200.h"
 #include "engine.h"
 #include "model.h"
+#include "nnet_tc.h"
 
 namespace rs {
 
@@ -242,6 +243,18 @@ struct ModelImpl {
   const double *d_global_cmvn = nullptr, *d_nnet_global_cmvn = nullptr;
   // nnet
   std::vector<const float *> d_matrices, d_vectors;
+  // tensor-core path (nnet_tc.cu): per plan step, the packed + split weights and their tensor maps
+  struct TcStep {
+    bool ok = false;
+    const float *w_hi = nullptr, *w_lo = nullptr;
+    int kp = 0, bn = 0;
+    std::vector<int> k0;
+    CUtensorMap map_hi, map_lo;
+  };
+  bool use_tc = true;
+  std::vector<TcStep> tc_steps;
+  std::vector<char> split;  // per plan buffer: stored as two TF32 planes
+  int num_sms = 0;
   uint64_t flops_per_axis_unit = 0;  // sum over gemm steps of 2*n*ktot/step (per time unit of the axis)
   ~ModelImpl() {
     for (void *p : owned) cudaFree(p);
@@ -399,7 +412,47 @@ static void UploadModel(ModelImpl *mi) {
       break;
     }
   for (const auto &mat : pl.matrices) mi->d_matrices.push_back(Upload(mat.d, &own));
-  for (const auto &v : pl.vectors) mi->d_vectors.push_back(Upload(v, &own));
+  for (const auto &v : pl.vectors) {
+    std::vector<float> padded(v);  // the epilogues read bias / scale vectors as float4
+    padded.resize((v.size() + 3) / 4 * 4, 0.f);
+    mi->d_vectors.push_back(Upload(padded, &own));
+  }
+  // --- tensor-core layers: every time-axis GEMM whose slabs are integer-strided row views
+  {
+    const char *env = getenv("RS_B200_GEMM");
+    mi->use_tc = !(env && std::string(env) == "simt");
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
+    mi->num_sms = prop.multiProcessorCount;
+    if (mi->use_tc && prop.major != 10)
+      RS_FAIL("this library is built for sm_100a (B200); device " << mi->device << " is sm_" << prop.major << prop.minor);
+    mi->tc_steps.resize(pl.steps.size());
+    mi->split.assign(pl.buffers.size(), 0);
+    for (size_t si = 0; mi->use_tc && si < pl.steps.size(); si++) {
+      const Step &st = pl.steps[si];
+      if (st.type != Step::kGemm || (int)st.slabs.size() > kTcMaxSlabs) continue;
+      const PlanBuffer &ob = pl.buffers[st.out];
+      bool ok = !ob.per_utt;
+      for (const Slab &sl : st.slabs) {
+        const PlanBuffer &sb = pl.buffers[sl.src];
+        if (sb.per_utt || ob.step % sb.step != 0 || sl.t_offset % sb.step != 0 || sl.k > sb.dim || sl.src == pl.output_buffer)
+          ok = false;
+      }
+      if (!ok) continue;
+      ModelImpl::TcStep &ts = mi->tc_steps[si];
+      std::vector<std::pair<int, int>> cols;
+      for (const Slab &sl : st.slabs) cols.push_back({sl.wcol, sl.k});
+      std::vector<float> hi, lo;
+      TcPackWeights(pl.matrices[st.weight].d.data(), st.n, st.ktot, cols, &hi, &lo, &ts.k0, &ts.kp);
+      ts.w_hi = Upload(hi, &own);
+      ts.w_lo = Upload(lo, &own);
+      ts.bn = TcTileN(st.n);
+      TcEncodeMap(&ts.map_hi, ts.w_hi, st.n, ts.kp, ts.kp, ts.bn);
+      TcEncodeMap(&ts.map_lo, ts.w_lo, st.n, ts.kp, ts.kp, ts.bn);
+      ts.ok = true;
+      for (const Slab &sl : st.slabs) mi->split[sl.src] = 1;
+    }
+  }
   for (const Step &st : pl.steps) {
     if ((int)st.slabs.size() > kMaxSlabs) RS_FAIL("layer " << st.name << " has too many input blocks");
     if ((int)st.ops.size() > kMaxOps) RS_FAIL("layer " << st.name << " has too many fused operations");
@@ -834,10 +887,14 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   auto slot_ptr = [&](int buffer) -> float * { return d->slots[pl.buffers[buffer].slot].as<float>(); };
   auto buf_ld = [&](int buffer) { return RoundUp(pl.buffers[buffer].dim, 4); };
   auto buf_rows = [&](int buffer) { return pl.buffers[buffer].per_utt ? n : axis_len / pl.buffers[buffer].step; };
+  // split buffers hold two planes back to back: hi at slot_ptr, lo right behind it
+  auto slot_lo = [&](int buffer) -> float * {
+    return mi->split[buffer] ? slot_ptr(buffer) + (size_t)buf_rows(buffer) * buf_ld(buffer) : nullptr;
+  };
   {
     std::vector<size_t> need(pl.num_slots, 0);
     for (size_t b = 0; b < pl.buffers.size(); b++) {
-      size_t bytes = (size_t)buf_rows((int)b) * buf_ld((int)b) * sizeof(float);
+      size_t bytes = (size_t)buf_rows((int)b) * buf_ld((int)b) * sizeof(float) * (mi->split[b] ? 2 : 1);
       need[pl.buffers[b].slot] = std::max(need[pl.buffers[b].slot], bytes);
     }
     for (int s = 0; s < pl.num_slots; s++) d->slots[s].ensure(std::max<size_t>(need[s], 16));
@@ -905,8 +962,9 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   {
     float *in = slot_ptr(pl.input_buffer);
     const int ild = buf_ld(pl.input_buffer);
-    CUDA_OK(cudaMemsetAsync(in, 0, (size_t)axis_len * ild * sizeof(float), d->stream));
+    CUDA_OK(cudaMemsetAsync(in, 0, (size_t)axis_len * ild * sizeof(float) * (mi->split[pl.input_buffer] ? 2 : 1), d->stream));
     AssembleParams a{};
+    a.dst_lo = slot_lo(pl.input_buffer);
     a.feats = nnet_feats;
     a.num_frames = d_nf;
     a.frame_offset = d_fo;
@@ -920,10 +978,12 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     LaunchAssembleInput(a, n, max_frames + L + R, d->stream);
     launches++;
   }
-  for (const Step &st : pl.steps) {
+  for (size_t step_i = 0; step_i < pl.steps.size(); step_i++) {
+    const Step &st = pl.steps[step_i];
     GemmParams g{};
     const PlanBuffer &ob = pl.buffers[st.out];
     g.out = slot_ptr(st.out);
+    g.out_lo = slot_lo(st.out);
     g.out_ld = buf_ld(st.out);
     g.m = buf_rows(st.out);
     g.n = st.n;
@@ -935,6 +995,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
       const PlanBuffer &sb = pl.buffers[sl.src];
       GemmSlab &gs = g.slabs[s];
       gs.src = slot_ptr(sl.src);
+      gs.src_lo = slot_lo(sl.src);
       gs.ld = buf_ld(sl.src);
       gs.rows = buf_rows(sl.src);
       gs.k = sl.k;
@@ -961,6 +1022,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
       dop.num = dop.den = 1;
       if (op.buffer >= 0) {
         dop.buf = slot_ptr(op.buffer);
+        dop.buf_lo = slot_lo(op.buffer);
         dop.buf_ld = buf_ld(op.buffer);
         dop.buf_rows = buf_rows(op.buffer);
         if (op.type == EpiOp::kAddScaled) {
@@ -974,6 +1036,39 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     switch (st.type) {
       case Step::kGemm:
       case Step::kUttGemm:
+        if (mi->tc_steps[step_i].ok) {
+          // tcgen05 path: each slab is a (row-strided, row-shifted) TMA view of its source planes
+          const ModelImpl::TcStep &ts = mi->tc_steps[step_i];
+          TcParams t{};
+          t.w_hi = ts.map_hi;
+          t.w_lo = ts.map_lo;
+          t.n_slabs = g.n_slabs;
+          t.bn = ts.bn;
+          for (int s = 0; s < g.n_slabs; s++) {
+            const Slab &sl = st.slabs[s];
+            const PlanBuffer &sb = pl.buffers[sl.src];
+            const int stride = ob.step / sb.step, sh = sl.t_offset / sb.step;
+            const int rem = ((sh % stride) + stride) % stride;
+            const int ld = buf_ld(sl.src), rows = buf_rows(sl.src);
+            const long long view_rows = rows > rem ? (rows - 1 - rem) / stride + 1 : 0;
+            TcEncodeMap(&t.a_hi[s], slot_ptr(sl.src) + (size_t)rem * ld, view_rows, sl.k, (long long)stride * ld, kTcBM);
+            TcEncodeMap(&t.a_lo[s], slot_lo(sl.src) + (size_t)rem * ld, view_rows, sl.k, (long long)stride * ld, kTcBM);
+            t.slabs[s].kblocks = (sl.k + kTcBK - 1) / kTcBK;
+            t.slabs[s].wk0 = ts.k0[s];
+            t.slabs[s].yshift = (sh - rem) / stride;
+          }
+          t.out_hi = g.out;
+          t.out_lo = g.out_lo;
+          t.out_ld = g.out_ld;
+          t.m = g.m;
+          t.n = g.n;
+          t.n_ops = g.n_ops;
+          for (int i = 0; i < g.n_ops; i++) t.ops[i] = g.ops[i];
+          t.row_utt = g.row_utt;
+          TcConfigure(&t);
+          LaunchGemmTc(t, mi->num_sms, d->stream);
+          break;
+        }
         g.w = mi->d_matrices[st.weight];
         g.ktot = st.ktot;
         LaunchGemm(g, d->stream);
@@ -983,7 +1078,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
         LaunchElementwise(g, st.term_scale.data(), st.col_offset, d->stream);
         break;
       case Step::kLogSoftmax:
-        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].ld, g.out, g.out_ld, g.m, g.n, d->stream);
+        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].src_lo, g.slabs[0].ld, g.out, g.out_ld, g.m, g.n, d->stream);
         break;
     }
     launches++;
@@ -1222,6 +1317,140 @@ int rs_graph_check(const char *hclg_fst, const char *words_txt, int64_t *counts,
     counts[4] = nf;
     counts[5] = (int64_t)g.words.size();
   }
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offsets, int n_offsets, int stride,
+                  const float *w, int n, const float *bias, int relu, int path, int iters, float *out, float *ms,
+                  char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  if (!src || !w || !out || rows < 1 || k < 1 || n < 1 || n_offsets < 1 || n_offsets > kTcMaxSlabs || stride < 1)
+    RS_FAIL("rs_debug_gemm: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) RS_FAIL("no such CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  std::vector<void *> owned;
+  struct Free {
+    std::vector<void *> *v;
+    ~Free() {
+      for (void *p : *v) cudaFree(p);
+    }
+  } free_all{&owned};
+  const int ld = RoundUp(k, 4), m = std::max(rows / stride, 1), ktot = k * n_offsets, out_ld = RoundUp(n, 4);
+  const bool tc = path != 0, split_out = path == 2;
+  std::vector<float> hi((size_t)rows * ld, 0.f), lo((size_t)rows * ld, 0.f);
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < k; c++) {
+      if (tc) TcSplitHost(src[(size_t)r * k + c], &hi[(size_t)r * ld + c], &lo[(size_t)r * ld + c]);
+      else hi[(size_t)r * ld + c] = src[(size_t)r * k + c];
+    }
+  float *d_hi = Upload(hi, &owned), *d_lo = tc ? Upload(lo, &owned) : nullptr;
+  std::vector<float> zeros((size_t)m * out_ld, 0.f);
+  float *d_out = Upload(zeros, &owned), *d_out_lo = split_out ? Upload(zeros, &owned) : nullptr;
+  std::vector<float> bias_pad;
+  const float *d_bias = nullptr;
+  if (bias) {
+    bias_pad.assign(bias, bias + n);
+    bias_pad.resize(out_ld, 0.f);
+    d_bias = Upload(bias_pad, &owned);
+  }
+  GemmParams g{};
+  g.n_slabs = n_offsets;
+  for (int s = 0; s < n_offsets; s++) {
+    GemmSlab &gs = g.slabs[s];
+    gs.src = d_hi;
+    gs.src_lo = d_lo;
+    gs.ld = ld;
+    gs.rows = rows;
+    gs.k = k;
+    gs.wcol = s * k;
+    gs.num = stride;
+    gs.den = 1;
+    gs.shift = offsets[s];
+  }
+  g.out = d_out;
+  g.out_lo = d_out_lo;
+  g.out_ld = out_ld;
+  g.m = m;
+  g.n = n;
+  g.out_step = stride;
+  if (d_bias) {
+    g.ops[g.n_ops].type = EpiOp::kBias;
+    g.ops[g.n_ops].v0 = d_bias;
+    g.n_ops++;
+  }
+  if (relu) g.ops[g.n_ops++].type = EpiOp::kRelu;
+  TcParams t{};
+  if (tc) {
+    if (prop.major != 10) RS_FAIL("the tensor-core path needs sm_100a");
+    std::vector<std::pair<int, int>> cols;
+    for (int s = 0; s < n_offsets; s++) cols.push_back({s * k, k});
+    std::vector<float> whi, wlo;
+    std::vector<int> k0;
+    int kp = 0;
+    TcPackWeights(w, n, ktot, cols, &whi, &wlo, &k0, &kp);
+    const float *d_whi = Upload(whi, &owned), *d_wlo = Upload(wlo, &owned);
+    t.bn = TcTileN(n);
+    TcEncodeMap(&t.w_hi, d_whi, n, kp, kp, t.bn);
+    TcEncodeMap(&t.w_lo, d_wlo, n, kp, kp, t.bn);
+    t.n_slabs = n_offsets;
+    for (int s = 0; s < n_offsets; s++) {
+      const int sh = offsets[s], rem = ((sh % stride) + stride) % stride;
+      const long long view_rows = rows > rem ? (rows - 1 - rem) / stride + 1 : 0;
+      TcEncodeMap(&t.a_hi[s], d_hi + (size_t)rem * ld, view_rows, k, (long long)stride * ld, kTcBM);
+      TcEncodeMap(&t.a_lo[s], d_lo + (size_t)rem * ld, view_rows, k, (long long)stride * ld, kTcBM);
+      t.slabs[s].kblocks = (k + kTcBK - 1) / kTcBK;
+      t.slabs[s].wk0 = k0[s];
+      t.slabs[s].yshift = (sh - rem) / stride;
+    }
+    t.out_hi = d_out;
+    t.out_lo = d_out_lo;
+    t.out_ld = out_ld;
+    t.m = m;
+    t.n = n;
+    t.n_ops = g.n_ops;
+    for (int i = 0; i < g.n_ops; i++) t.ops[i] = g.ops[i];
+    TcConfigure(&t);
+  } else {
+    std::vector<float> wv(w, w + (size_t)n * ktot);
+    g.w = Upload(wv, &owned);
+    g.ktot = ktot;
+  }
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  auto launch = [&]() {
+    if (tc) LaunchGemmTc(t, prop.multiProcessorCount, 0);
+    else LaunchGemm(g, 0);
+  };
+  launch();  // warm-up (and the result)
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  if (iters > 0) {
+    CUDA_OK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; i++) launch();
+    CUDA_OK(cudaEventRecord(e1, 0));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t_ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&t_ms, e0, e1));
+    if (ms) *ms = t_ms / iters;
+  } else if (ms) {
+    *ms = 0.f;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  std::vector<float> h((size_t)m * out_ld), hl;
+  CUDA_OK(cudaMemcpy(h.data(), d_out, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  if (split_out) {
+    hl.resize(h.size());
+    CUDA_OK(cudaMemcpy(hl.data(), d_out_lo, hl.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  for (int r = 0; r < m; r++)
+    for (int c = 0; c < n; c++)
+      out[(size_t)r * n + c] = h[(size_t)r * out_ld + c] + (split_out ? hl[(size_t)r * out_ld + c] : 0.f);
   return 0;
   API_GUARD_END(1)
 }

@@ -86,6 +86,7 @@ constexpr int kMaxSlabs = 8;
 constexpr int kMaxOps = 8;
 struct GemmSlab {
   const float *src;
+  const float *src_lo;  // second plane of a split buffer (value = src + src_lo), or null
   int ld;        // row stride of src in floats
   int rows;      // valid rows of src (indices are clamped into [0, rows))
   int k;         // columns used
@@ -98,6 +99,7 @@ struct DevOp {
   const float *v0, *v1;
   float alpha;
   const float *buf;    // kAddScaled: other activation buffer ; kUttBias: [n_utts, ld]
+  const float *buf_lo; // kAddScaled: second plane of a split buffer, or null
   int buf_ld, buf_rows;
   int num, den;        // kAddScaled: other_row = out_row * num / den ; kUttBias: axis time = out_row * num
 };
@@ -107,6 +109,7 @@ struct GemmParams {
   const float *w;  // [n, ktot] row-major
   int ktot;
   float *out;
+  float *out_lo;   // not null: store the result split into two TF32 planes (see nnet_tc.cu)
   int out_ld;
   int m, n;        // output rows / columns
   DevOp ops[kMaxOps];
@@ -116,12 +119,14 @@ struct GemmParams {
 };
 void LaunchGemm(const GemmParams &p, cudaStream_t stream);
 void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int col_offset, cudaStream_t stream);
-void LaunchLogSoftmax(const float *in, int in_ld, float *out, int out_ld, int rows, int n, cudaStream_t stream);
+void LaunchLogSoftmax(const float *in, const float *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
+                      cudaStream_t stream);
 
 struct AssembleParams {
   const float *feats;  // [total_frames, dim]
   const int *num_frames, *frame_offset, *origin;  // per utt
   float *dst;          // nnet input buffer on the global axis [axis_len, ld]
+  float *dst_lo;       // not null: split store
   int dim, ld, left, right, axis_len;
 };
 void LaunchAssembleInput(const AssembleParams &p, int n_utts, int max_rows, cudaStream_t stream);

@@ -44,6 +44,7 @@ __device__ __forceinline__ float apply_ops(float v, int r, int c, const GemmPara
         long long orow = ((long long)r * op.num) / op.den;
         if (orow >= op.buf_rows) orow = op.buf_rows - 1;
         float o = op.buf[(size_t)orow * op.buf_ld + c];
+        if (op.buf_lo) o = __fadd_rn(o, op.buf_lo[(size_t)orow * op.buf_ld + c]);
         v = __fadd_rn(op.alpha == 1.f ? o : __fmul_rn(op.alpha, o), v);
         break;
       }
@@ -65,6 +66,15 @@ __device__ __forceinline__ long long slab_row(const GemmSlab &s, int r) {
   return q;
 }
 
+// x = hi + lo with hi on the TF32 grid (the layout the tensor-core layers read, nnet_tc.cu)
+__device__ __forceinline__ void split_store(float *hi_p, float *lo_p, float x) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  const float hi = __uint_as_float(h);
+  *hi_p = hi;
+  *lo_p = __fsub_rn(x, hi);
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constant__ GemmParams p) {
   __shared__ __align__(16) float As[2][BK][BM + PAD];
@@ -80,12 +90,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
   float4 ra[2], rb[2];
   int cur_slab = 0, cur_k0 = 0;
   const float *arow[2] = {nullptr, nullptr};
+  const float *arow_lo[2] = {nullptr, nullptr};
   auto set_slab = [&](int s) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       int r = row0 + lrow + h * 64;
       if (r >= p.m) r = p.m - 1;
-      arow[h] = p.slabs[s].src + (size_t)slab_row(p.slabs[s], r) * p.slabs[s].ld;
+      const size_t off = (size_t)slab_row(p.slabs[s], r) * p.slabs[s].ld;
+      arow[h] = p.slabs[s].src + off;
+      arow_lo[h] = p.slabs[s].src_lo ? p.slabs[s].src_lo + off : nullptr;
     }
   };
   auto load_tile = [&]() {
@@ -101,6 +114,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
         if (k + 1 < sl.k) v.y = arow[h][k + 1];
         if (k + 2 < sl.k) v.z = arow[h][k + 2];
         if (k + 3 < sl.k) v.w = arow[h][k + 3];
+      }
+      if (arow_lo[h]) {  // split buffer: value = hi + lo (exact)
+        if (k + 0 < sl.k) v.x = __fadd_rn(v.x, arow_lo[h][k + 0]);
+        if (k + 1 < sl.k) v.y = __fadd_rn(v.y, arow_lo[h][k + 1]);
+        if (k + 2 < sl.k) v.z = __fadd_rn(v.z, arow_lo[h][k + 2]);
+        if (k + 3 < sl.k) v.w = __fadd_rn(v.w, arow_lo[h][k + 3]);
       }
       ra[h] = v;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,7 +215,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = (c + j < p.n) ? apply_ops(acc[i][jh * 4 + j], r, c + j, p) : 0.f;
       float *o = p.out + (size_t)r * p.out_ld + c;
-      if (c + 3 < p.n && (p.out_ld & 3) == 0) {
+      if (p.out_lo) {
+        float *ol = p.out_lo + (size_t)r * p.out_ld + c;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (c + j < p.n) split_store(o + j, ol + j, v[j]);
+      } else if (c + 3 < p.n && (p.out_ld & 3) == 0) {
         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
@@ -234,12 +258,16 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const __grid_constant_
   float v = 0.f;
   for (int s = 0; s < p.n_slabs; s++) {
     const GemmSlab &sl = p.slabs[s];
-    float x = sl.src[(size_t)slab_row(sl, r) * sl.ld + sl.wcol + c];
+    const size_t idx = (size_t)slab_row(sl, r) * sl.ld + sl.wcol + c;
+    float x = sl.src[idx];
+    if (sl.src_lo) x = __fadd_rn(x, sl.src_lo[idx]);
     float t = sc.s[s] == 1.f ? x : __fmul_rn(sc.s[s], x);
     v = s == 0 ? t : __fadd_rn(v, t);
   }
   v = apply_ops(v, r, c, p);
-  p.out[(size_t)r * p.out_ld + col_offset + c] = v;
+  const size_t oidx = (size_t)r * p.out_ld + col_offset + c;
+  if (p.out_lo) split_store(p.out + oidx, p.out_lo + oidx, v);
+  else p.out[oidx] = v;
 }
 
 void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int col_offset, cudaStream_t stream) {
@@ -251,23 +279,27 @@ void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int co
 }
 
 // --------------------------------------------------------------------------- log-softmax (warp/row)
-__global__ void __launch_bounds__(256) logsoftmax_kernel(const float *in, int in_ld, float *out, int out_ld, int rows, int n) {
+__global__ void __launch_bounds__(256) logsoftmax_kernel(const float *in, const float *in_lo, int in_ld, float *out, int out_ld,
+                                                         int rows, int n) {
   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float *x = in + (size_t)row * in_ld;
+  const float *xl = in_lo ? in_lo + (size_t)row * in_ld : nullptr;
+  auto at = [&](int c) { return xl ? __fadd_rn(x[c], xl[c]) : x[c]; };
   float mx = -3.4e38f;
-  for (int c = lane; c < n; c += 32) mx = fmaxf(mx, x[c]);
+  for (int c = lane; c < n; c += 32) mx = fmaxf(mx, at(c));
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float s = 0.f;
-  for (int c = lane; c < n; c += 32) s += expf(x[c] - mx);
+  for (int c = lane; c < n; c += 32) s += expf(at(c) - mx);
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float lse = mx + logf(s);
-  for (int c = lane; c < n; c += 32) out[(size_t)row * out_ld + c] = x[c] - lse;
+  for (int c = lane; c < n; c += 32) out[(size_t)row * out_ld + c] = at(c) - lse;
 }
 
-void LaunchLogSoftmax(const float *in, int in_ld, float *out, int out_ld, int rows, int n, cudaStream_t stream) {
+void LaunchLogSoftmax(const float *in, const float *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
+                      cudaStream_t stream) {
   if (rows <= 0) return;
-  logsoftmax_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(in, in_ld, out, out_ld, rows, n);
+  logsoftmax_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(in, in_lo, in_ld, out, out_ld, rows, n);
 }
 
 // --------------------------------------------------------------------------- input assembly
@@ -285,7 +317,9 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
     int row = p.origin[u] + t;
     if (row < 0 || row >= p.axis_len) continue;
     int tc = t < 0 ? 0 : (t >= T ? T - 1 : t);
-    p.dst[(size_t)row * p.ld + d] = p.feats[((size_t)p.frame_offset[u] + tc) * p.dim + d];
+    const float x = p.feats[((size_t)p.frame_offset[u] + tc) * p.dim + d];
+    if (p.dst_lo) split_store(p.dst + (size_t)row * p.ld + d, p.dst_lo + (size_t)row * p.ld + d, x);
+    else p.dst[(size_t)row * p.ld + d] = x;
   }
 }
 

@@ -1,0 +1,501 @@
+// Stage (ii) on the 5th-generation tensor cores: the affine layers of the TDNN(-F) forward
+// (TdnnComponent::Propagate, kaldi/src/nnet3/nnet-tdnn-component.cc:181-211, and the Affine /
+// Linear components of nnet3/nnet-simple-component.cc, which the reference runs as cblas_sgemm,
+// kaldi/src/matrix/kaldi-matrix.cc:171-183) as ONE persistent, warp-specialised kernel per layer:
+//
+//   warp 0      TMA producer : cp.async.bulk.tensor tiles of the activations (one tensor map per
+//                              time-offset slab: the TDNN splice is a row-shifted / row-strided view
+//                              of the producing layer's buffer, never materialised) and of the weights
+//   warp 1      MMA issuer   : tcgen05.mma.kind::tf32, accumulators in TMEM (two buffers, so the
+//                              epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 2..5  epilogue     : tcgen05.ld -> bias / ReLU / BatchNorm scale+offset / bypass add in
+//                              the reference's order -> split store
+//
+// Numerics.  The reference computes in fp32; the tolerance on the log-likelihoods is 1e-4.  A plain
+// TF32 product (10-bit mantissa) is ~1e-3, so every operand is carried as two TF32 planes
+//   x = hi + lo,  hi = rna_tf32(x),  lo = x - hi   (exact in fp32; the tensor core drops lo's low bits)
+// and a product is three MMAs into the same fp32 TMEM accumulator: hi*hi + hi*lo + lo*hi.  The
+// dropped terms are O(2^-21) relative per product and unbiased.  Activations are stored by the
+// producing epilogue already split (the two planes ARE the buffer: hi + lo reproduces the fp32
+// value bit for bit), weights are split once at model load.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "engine.h"
+#include "model.h"
+#include "nnet_tc.h"
+
+namespace rs {
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Spins on the barrier's phase; a wait longer than ~2 s of SM clocks means a broken pipeline
+// (bad descriptor, lost arrive): trap instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 0xfff) == 0xfff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {
+        printf("gemm_tc_kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major operand tile [rows x 32 floats] written by TMA with
+// the 128-byte swizzle: 8-row groups are 1024 B apart (SBO), one swizzle atom along K (LBO unused).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3ffff) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
+  d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+// x = hi + lo with hi on the TF32 grid (round to nearest, ties away) and lo the exact remainder
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = __fsub_rn(x, hi);
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+// Accumulation.  The tensor core adds each MMA (8 products per output) into the fp32 TMEM
+// accumulator with truncation, not round-to-nearest (measured: the error of a K = 2048 dot product
+// accumulated entirely in TMEM grows linearly with K and is biased towards zero, ~1e-5 relative).
+// So TMEM only ever holds the partial sum of ONE 32-wide K block: per block the issuer starts a
+// fresh accumulator, adds the eight small cross terms first (while the accumulator is ~2^-11 of its
+// final size their truncation is negligible) and the four hi*hi terms last, and hands the block to
+// the epilogue warps, which add it into fp32 registers with round-to-nearest -- the same blocked
+// summation a CPU sgemm micro-kernel performs.  Four TMEM sets of bn columns form the ring between
+// the MMA warp and the two epilogue groups; the groups alternate tiles, so the bias / ReLU /
+// BatchNorm / bypass / split-store tail of tile i overlaps the main loop of tile i+1.
+constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
+
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t stage_bytes = 2u * kStageABytes + 2u * b_bytes;
+  const uint32_t bar0 = smem0 + (uint32_t)p.stages * stage_bytes;
+  // barriers: full[stages] | empty[stages] | set_full[4] | set_empty[4] | tmem slot
+  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
+  auto setf_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + a); };
+  auto sete_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 4 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 4; a++) {
+      mbar_init(setf_bar(a), 1);
+      mbar_init(sete_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  int total_kb = 0;
+  for (int s = 0; s < p.n_slabs; s++) total_kb += p.slabs[s].kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
+        for (int s = 0; s < p.n_slabs; s++) {
+          const TcSlab sl = p.slabs[s];
+          for (int kb = 0; kb < sl.kblocks; kb++) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, fb = full_bar(stage);
+            mbar_expect_tx(fb, stage_bytes);
+            tma_load_2d(sa, &p.a_hi[s], kb * kTcBK, m0 + sl.yshift, fb);
+            tma_load_2d(sa + kStageABytes, &p.a_lo[s], kb * kTcBK, m0 + sl.yshift, fb);
+            tma_load_2d(sa + 2 * kStageABytes, &p.w_hi, sl.wk0 + kb * kTcBK, n0, fb);
+            tma_load_2d(sa + 2 * kStageABytes + b_bytes, &p.w_lo, sl.wk0 + kb * kTcBK, n0, fb);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, set_phase = 0;  // bit s of set_phase: parity of TMEM set s
+      int group = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, group ^= 1) {
+        for (int kb = 0; kb < total_kb; kb++) {
+          const int set = 2 * group + (kb & 1);
+          mbar_wait(sete_bar(set), ((set_phase >> set) & 1u) ^ 1u);
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(set * p.bn);
+          const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+          const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kStageABytes);
+          const uint64_t b_hi = smem_desc_sw128(sa + 2 * kStageABytes), b_lo = smem_desc_sw128(sa + 2 * kStageABytes + b_bytes);
+#pragma unroll
+          for (int k = 0; k < kTcBK / 8; k++) {  // cross terms first: 8 tf32 = 32 bytes per step inside the swizzle atom
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
+            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+          }
+#pragma unroll
+          for (int k = 0; k < kTcBK / 8; k++) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+          tc_commit(setf_bar(set));     // partial sum of this K block complete
+          set_phase ^= 1u << set;
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------- epilogue groups (warps 2..5 and 6..9)
+    const int group = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint32_t set_phase = 0;  // bit 0 / 1: parity of this group's two TMEM sets
+    for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
+      float acc[kTcMaxBN];
+#pragma unroll
+      for (int j = 0; j < kTcMaxBN; j++) acc[j] = 0.f;
+      for (int kb = 0; kb < total_kb; kb++) {
+        const int sl = kb & 1, set = 2 * group + sl;
+        mbar_wait(setf_bar(set), (set_phase >> sl) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn);
+#pragma unroll
+        for (int jc = 0; jc < kTcMaxBN / 32; jc++)
+          if (jc * 32 < p.bn) {
+            uint32_t raw[32];
+            tmem_ld32(taddr + jc * 32, raw);
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[jc * 32 + j] = __fadd_rn(acc[jc * 32 + j], __uint_as_float(raw[j]));
+          }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sete_bar(set));
+        set_phase ^= 1u << sl;
+      }
+      const int r = m0 + q * 32 + lane;
+      const bool row_ok = r < p.m;
+      const int rr = row_ok ? r : p.m - 1;
+#pragma unroll
+      for (int jc = 0; jc < kTcMaxBN / 32; jc++) {
+        const int c0 = n0 + jc * 32;
+        if (jc * 32 >= p.bn || c0 >= p.n) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = acc[jc * 32 + j];
+        for (int i = 0; i < p.n_ops; i++) {
+          const DevOp &op = p.ops[i];
+          switch (op.type) {
+            case EpiOp::kBias:
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c0 + j < p.n) {
+                  const float4 b = __ldg(reinterpret_cast<const float4 *>(op.v0 + c0 + j));
+                  v[j] = __fadd_rn(v[j], b.x);
+                  v[j + 1] = __fadd_rn(v[j + 1], b.y);
+                  v[j + 2] = __fadd_rn(v[j + 2], b.z);
+                  v[j + 3] = __fadd_rn(v[j + 3], b.w);
+                }
+              break;
+            case EpiOp::kRelu:
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : 0.f;
+              break;
+            case EpiOp::kScaleOffset:
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c0 + j < p.n) {
+                  const float4 s = __ldg(reinterpret_cast<const float4 *>(op.v0 + c0 + j));
+                  const float4 o = __ldg(reinterpret_cast<const float4 *>(op.v1 + c0 + j));
+                  v[j] = __fadd_rn(__fmul_rn(v[j], s.x), o.x);
+                  v[j + 1] = __fadd_rn(__fmul_rn(v[j + 1], s.y), o.y);
+                  v[j + 2] = __fadd_rn(__fmul_rn(v[j + 2], s.z), o.z);
+                  v[j + 3] = __fadd_rn(__fmul_rn(v[j + 3], s.w), o.w);
+                }
+              break;
+            case EpiOp::kScale:
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = __fmul_rn(v[j], op.alpha);
+              break;
+            case EpiOp::kAddScaled: {
+              long long orow = ((long long)rr * op.num) / op.den;
+              if (orow >= op.buf_rows) orow = op.buf_rows - 1;
+              const float *bh = op.buf + (size_t)orow * op.buf_ld + c0;
+              const float *bl = op.buf_lo ? op.buf_lo + (size_t)orow * op.buf_ld + c0 : nullptr;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c0 + j < p.n) {
+                  float4 o = *reinterpret_cast<const float4 *>(bh + j);
+                  if (bl) {
+                    const float4 l = *reinterpret_cast<const float4 *>(bl + j);
+                    o.x = __fadd_rn(o.x, l.x);
+                    o.y = __fadd_rn(o.y, l.y);
+                    o.z = __fadd_rn(o.z, l.z);
+                    o.w = __fadd_rn(o.w, l.w);
+                  }
+                  if (op.alpha != 1.f) {
+                    o.x = __fmul_rn(op.alpha, o.x);
+                    o.y = __fmul_rn(op.alpha, o.y);
+                    o.z = __fmul_rn(op.alpha, o.z);
+                    o.w = __fmul_rn(op.alpha, o.w);
+                  }
+                  v[j] = __fadd_rn(o.x, v[j]);
+                  v[j + 1] = __fadd_rn(o.y, v[j + 1]);
+                  v[j + 2] = __fadd_rn(o.z, v[j + 2]);
+                  v[j + 3] = __fadd_rn(o.w, v[j + 3]);
+                }
+              break;
+            }
+            case EpiOp::kUttBias: {
+              const int u = p.row_utt[(size_t)rr * op.num];
+              const float *b = op.buf + (size_t)u * op.buf_ld + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c0 + j < p.n) {
+                  const float4 o = *reinterpret_cast<const float4 *>(b + j);
+                  v[j] = __fadd_rn(v[j], o.x);
+                  v[j + 1] = __fadd_rn(v[j + 1], o.y);
+                  v[j + 2] = __fadd_rn(v[j + 2], o.z);
+                  v[j + 3] = __fadd_rn(v[j + 3], o.w);
+                }
+              break;
+            }
+          }
+        }
+        if (row_ok) {
+          float *oh = p.out_hi + (size_t)r * p.out_ld + c0;
+          if (p.out_lo) {
+            float *ol = p.out_lo + (size_t)r * p.out_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (c0 + j < p.n) {
+                float4 h, l;
+                split_tf32(v[j], h.x, l.x);
+                split_tf32(v[j + 1], h.y, l.y);
+                split_tf32(v[j + 2], h.z, l.z);
+                split_tf32(v[j + 3], h.w, l.w);
+                *reinterpret_cast<float4 *>(oh + j) = h;
+                *reinterpret_cast<float4 *>(ol + j) = l;
+              }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (c0 + j < p.n) *reinterpret_cast<float4 *>(oh + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn GetEncodeTiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) RS_FAIL("cuTensorMapEncodeTiled is not available from the CUDA driver");
+  return fn;
+}
+
+}  // namespace
+
+// 2-D fp32 tensor [rows x cols], row pitch `pitch_floats`, box = 32 columns x box_rows, 128-byte
+// swizzle, out-of-bounds elements read as zero.
+void TcEncodeMap(CUtensorMap *map, const float *base, long long rows, int cols, long long pitch_floats, int box_rows) {
+  if (rows < 1) rows = 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_floats * 4) % 16) RS_FAIL("tensor map operand is not 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_floats * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = GetEncodeTiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS)
+    RS_FAIL("cuTensorMapEncodeTiled failed (" << (int)rc << ") rows " << rows << " cols " << cols << " pitch " << pitch_floats);
+}
+
+void TcSplitHost(float x, float *hi, float *lo) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  uint32_t h = (u + 0x1000u) & 0xffffe000u;  // round to nearest, ties away (cvt.rna.tf32.f32)
+  if ((u & 0x7f800000u) == 0x7f800000u) h = u;  // inf / nan unchanged
+  memcpy(hi, &h, 4);
+  *lo = x - *hi;
+}
+
+int TcTileN(int n) {
+  const int tiles = (n + kTcMaxBN - 1) / kTcMaxBN;  // fewest tiles, then the smallest tile that covers n
+  const int per = (n + tiles - 1) / tiles;
+  return (per + 31) / 32 * 32;
+}
+
+void TcPackWeights(const float *w, int n, int ktot, const std::vector<std::pair<int, int>> &slabs, std::vector<float> *hi,
+                   std::vector<float> *lo, std::vector<int> *k0, int *kp) {
+  int total = 0;
+  k0->clear();
+  for (const auto &s : slabs) {
+    k0->push_back(total);
+    total += (s.second + kTcBK - 1) / kTcBK * kTcBK;
+  }
+  *kp = total;
+  hi->assign((size_t)n * total, 0.f);
+  lo->assign((size_t)n * total, 0.f);
+  for (size_t si = 0; si < slabs.size(); si++) {
+    const int wcol = slabs[si].first, k = slabs[si].second;
+    if (wcol + k > ktot) RS_FAIL("weight slab out of range");
+    for (int r = 0; r < n; r++)
+      for (int c = 0; c < k; c++)
+        TcSplitHost(w[(size_t)r * ktot + wcol + c], &(*hi)[(size_t)r * total + (*k0)[si] + c], &(*lo)[(size_t)r * total + (*k0)[si] + c]);
+  }
+}
+
+static int g_tc_smem_limit = 0;
+
+void TcConfigure(TcParams *p) {
+  if (g_tc_smem_limit == 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    g_tc_smem_limit = v;
+  }
+  const int stage_bytes = 2 * kStageABytes + 2 * p->bn * 128;
+  int stages = (g_tc_smem_limit - 1024 - 256) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) RS_FAIL("not enough shared memory for the tensor-core GEMM pipeline");
+  p->stages = stages;
+  int cols = 32;
+  while (cols < 4 * p->bn) cols <<= 1;
+  p->tmem_cols = cols;
+  p->tiles_m = (p->m + kTcBM - 1) / kTcBM;
+  p->tiles_n = (p->n + p->bn - 1) / p->bn;
+}
+
+void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream) {
+  if (p.m <= 0 || p.n <= 0) return;
+  const int stage_bytes = 2 * kStageABytes + 2 * p.bn * 128;
+  const int smem = 1024 + p.stages * stage_bytes + 8 * (2 * p.stages + 8) + 16;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tc_smem_limit);
+    if (e != cudaSuccess) RS_FAIL("cudaFuncSetAttribute(gemm_tc_kernel): " << cudaGetErrorString(e));
+    configured = g_tc_smem_limit;
+  }
+  int grid = p.tiles_m * p.tiles_n;
+  if (grid > num_sms) grid = num_sms;
+  gemm_tc_kernel<<<grid, kTcThreads, smem, stream>>>(p);
+}
+
+}  // namespace rs

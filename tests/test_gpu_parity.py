@@ -126,3 +126,27 @@ def test_edge_cases(tiny, utterances):
         single = dec.decode_pcm([batch[u]])
         assert single.words[0] == hyp.words[u]
     assert dec.decode_pcm([]).n_utts == 0
+
+
+@pytest.mark.parametrize("k,n,offsets,stride", [(40, 220, (-1, 0, 1), 1), (1024, 128, (-3, 0), 1), (128, 1024, (0, 1), 3),
+                                                (192, 3026, (0,), 1), (36, 40, (-2, -1, 0, 1), 2)])
+def test_tensor_core_layer_matches_fp64(lib, k, n, offsets, stride):
+    """The tcgen05 3xTF32 layer kernel against an fp64 product: error at the fp32 level, far inside 1e-4."""
+    rng = np.random.default_rng(k * 131 + n)
+    rows = 700
+    src = rng.standard_normal((rows, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k * len(offsets))) / np.sqrt(k * len(offsets))).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    m = rows // stride
+    r = np.arange(m) * stride
+    want = np.zeros((m, n))
+    valid = np.ones(m, dtype=bool)
+    for i, o in enumerate(offsets):
+        idx = r + o
+        valid &= (idx >= 0) & (idx < rows)
+        want += src[np.clip(idx, 0, rows - 1)].astype(np.float64) @ w[:, i * k:(i + 1) * k].astype(np.float64).T
+    want = np.maximum(want + bias, 0)
+    for path in (0, 1, 2):
+        got, _ = lib.debug_gemm(src, w, offsets, stride, bias, True, path=path)
+        err = np.abs(got - want)[valid].max()
+        assert err <= 2e-5, (path, err)
