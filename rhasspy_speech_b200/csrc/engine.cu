@@ -929,7 +929,8 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     iv.post_w = (float *)d->d_post_w.ensure(tf * iv.num_gselect * sizeof(float));
     iv.wf = (double *)d->d_wf.ensure((size_t)n * G * LD * sizeof(double));
     iv.gw = (float *)d->d_gw.ensure((size_t)n * G * sizeof(float));
-    iv.linear = (double *)d->d_linear.ensure((size_t)n * Rv * sizeof(double));
+    iv.linear_chunks = (G * LD + 511) / 512;
+    iv.linear_part = (double *)d->d_linear.ensure((size_t)iv.linear_chunks * n * Rv * sizeof(double));
     iv.quad = (double *)d->d_quad.ensure((size_t)n * P * sizeof(double));
     d_ivector = slot_ptr(pl.ivector_buffer);
     ivector_ld = buf_ld(pl.ivector_buffer);

@@ -74,7 +74,8 @@ struct IvecParams {
   int online_cmvn_iextractor;
   double *wf;                         // [n_utts][G][ldim] weighted feature sums
   float *gw;                          // [n_utts][G] per-Gaussian total weights (float, as the reference)
-  double *linear;                     // [n_utts][R]
+  double *linear_part;                // [linear_chunks][n_utts][R] split-K partial sums of the linear term
+  int linear_chunks;                  // ceil(G * ldim / 512)
   double *quad;                       // [n_utts][R(R+1)/2] packed lower triangle
   float *ivector;                     // [n_utts][ivector_ld] nnet input (prior offset removed)
   int ivector_ld;

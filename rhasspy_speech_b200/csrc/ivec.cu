@@ -280,36 +280,37 @@ __global__ void __launch_bounds__(256) ivec_gw_kernel(IvecParams p) {
 
 // linear[u][r] = prior + sum_g sum_d sigma_inv_m[g][d][r] * wf[u][g][d]
 // quad[u][k]   = prior + sum_g gw[u][g] * U[g][k]
-// One CTA per (column tile, group of UT utterances); the extractor tables are read once per group.
+// The (g, d) sum is split over CTAs: CTA (c, group) adds kLinChunk terms for kUT utterances, reading
+// its slice of the extractor table once, and writes the partial to linear_part[c][u][r]; the solve
+// kernel folds the partials in a fixed order (deterministic, unlike atomics).
 constexpr int kUT = 8;
+constexpr int kLinChunk = 512;
 __global__ void __launch_bounds__(128) ivec_linear_kernel(IvecParams p) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = threadIdx.x;
   const int u0 = blockIdx.y * kUT;
   const int R = p.ivector_dim, GD = p.num_gauss * p.ldim;
-  extern __shared__ double swf[];  // [kUT][chunk]
-  const int chunk = 256;
-  double acc[kUT];
-#pragma unroll
-  for (int j = 0; j < kUT; j++) acc[j] = 0.0;
-  for (int k0 = 0; k0 < GD; k0 += chunk) {
-    int n = min(chunk, GD - k0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < kUT * n; i += blockDim.x) {
-      int j = i / n, k = i - j * n;
-      swf[j * chunk + k] = (u0 + j < p.n_utts) ? p.wf[(size_t)(u0 + j) * GD + k0 + k] : 0.0;
-    }
-    __syncthreads();
-    if (r < R) {
-      for (int k = 0; k < n; k++) {
-        double m = p.sigma_inv_m[(size_t)(k0 + k) * R + r];
-#pragma unroll
-        for (int j = 0; j < kUT; j++) acc[j] = fma(m, swf[j * chunk + k], acc[j]);
-      }
-    }
+  __shared__ double swf[kUT][kLinChunk];
+  const int k0 = blockIdx.x * kLinChunk;
+  const int n = min(kLinChunk, GD - k0);
+  for (int i = threadIdx.x; i < kUT * n; i += blockDim.x) {
+    int j = i / n, k = i - j * n;
+    swf[j][k] = (u0 + j < p.n_utts) ? p.wf[(size_t)(u0 + j) * GD + k0 + k] : 0.0;
   }
-  if (r < R)
+  __syncthreads();
+  for (int rr = r; rr < R; rr += blockDim.x) {
+    double acc[kUT];
+#pragma unroll
+    for (int j = 0; j < kUT; j++) acc[j] = 0.0;
+    const double *m = p.sigma_inv_m + (size_t)k0 * R + rr;
+#pragma unroll 4
+    for (int k = 0; k < n; k++) {
+      const double mv = m[(size_t)k * R];
+#pragma unroll
+      for (int j = 0; j < kUT; j++) acc[j] = fma(mv, swf[j][k], acc[j]);
+    }
     for (int j = 0; j < kUT; j++)
-      if (u0 + j < p.n_utts) p.linear[(size_t)(u0 + j) * R + r] = acc[j];
+      if (u0 + j < p.n_utts) p.linear_part[((size_t)blockIdx.x * p.n_utts + u0 + j) * R + rr] = acc[j];
+  }
 }
 
 __global__ void __launch_bounds__(128) ivec_quad_kernel(IvecParams p) {
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(128) ivec_cg_kernel(IvecParams p) {
     A[i] = v;
   }
   for (int i = tid; i < R; i += blockDim.x) {
-    double v = p.linear[(size_t)u * R + i];
+    double v = 0.0;  // fold the split-K partials of ivec_linear_kernel in chunk order
+    for (int c = 0; c < p.linear_chunks; c++) v += p.linear_part[((size_t)c * p.n_utts + u) * R + i];
     if (i == 0) v += p.prior_offset + p.prior_offset * prior_scale_change;
     b[i] = v;
     x[i] = i == 0 ? p.prior_offset : 0.0;
@@ -457,7 +459,7 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
   }
   ivec_gw_kernel<<<dim3((G + 255) / 256, p.n_utts), 256, 2 * 256 * sizeof(int), stream>>>(p);
   int groups = (p.n_utts + kUT - 1) / kUT;
-  ivec_linear_kernel<<<dim3((R + 127) / 128, groups), 128, (size_t)kUT * 256 * sizeof(double), stream>>>(p);
+  ivec_linear_kernel<<<dim3(p.linear_chunks, groups), 128, 0, stream>>>(p);
   ivec_quad_kernel<<<dim3((P + 127) / 128, groups), 128, (size_t)kUT * G * sizeof(double), stream>>>(p);
   size_t sm3 = ((size_t)R * R + 5 * R + 8) * sizeof(double);
   static bool attr_set = false;

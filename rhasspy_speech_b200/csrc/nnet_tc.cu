@@ -133,12 +133,15 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
 // BatchNorm / bypass / split-store tail of tile i overlaps the main loop of tile i+1.
 constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
 
+// 10 warps = up to 3 per SM sub-partition (16 K registers each): at most 168 registers per thread
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = 2u * kStageABytes + 2u * b_bytes;
-  const uint32_t bar0 = smem0 + (uint32_t)p.stages * stage_bytes;
+  // [stages][8 x 4 KB epilogue staging tiles][barriers]
+  const uint32_t epi0 = smem0 + (uint32_t)p.stages * stage_bytes;
+  const uint32_t bar0 = epi0 + 8u * 4096u;
   // barriers: full[stages] | empty[stages] | set_full[4] | set_empty[4] | tmem slot
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
     for (int a = 0; a < 4; a++) {
       mbar_init(setf_bar(a), 1);
-      mbar_init(sete_bar(a), 4);
+      mbar_init(sete_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -178,22 +181,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       // ------------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      bool uniform = true;
+      for (int s = 1; s < p.n_slabs; s++) uniform = uniform && p.slabs[s].kblocks == p.slabs[0].kblocks;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
-        for (int s = 0; s < p.n_slabs; s++) {
+        // K blocks are visited block-major across the slabs when the slabs are equally long: the
+        // time-offset slabs of a TDNN layer read the same source rows shifted by a few rows, so
+        // back-to-back loads hit in L2 (slab-major order re-read the whole source from HBM)
+        for (int it = 0; it < total_kb; it++) {
+          int s, kb;
+          if (uniform) {
+            s = it % p.n_slabs;
+            kb = it / p.n_slabs;
+          } else {
+            s = 0;
+            kb = it;
+            while (kb >= p.slabs[s].kblocks) kb -= p.slabs[s++].kblocks;
+          }
           const TcSlab sl = p.slabs[s];
-          for (int kb = 0; kb < sl.kblocks; kb++) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, fb = full_bar(stage);
-            mbar_expect_tx(fb, stage_bytes);
-            tma_load_2d(sa, &p.a_hi[s], kb * kTcBK, m0 + sl.yshift, fb);
-            tma_load_2d(sa + kStageABytes, &p.a_lo[s], kb * kTcBK, m0 + sl.yshift, fb);
-            tma_load_2d(sa + 2 * kStageABytes, &p.w_hi, sl.wk0 + kb * kTcBK, n0, fb);
-            tma_load_2d(sa + 2 * kStageABytes + b_bytes, &p.w_lo, sl.wk0 + kb * kTcBK, n0, fb);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, fb = full_bar(stage);
+          mbar_expect_tx(fb, stage_bytes);
+          tma_load_2d(sa, &p.a_hi[s], kb * kTcBK, m0 + sl.yshift, fb);
+          tma_load_2d(sa + kStageABytes, &p.a_lo[s], kb * kTcBK, m0 + sl.yshift, fb);
+          tma_load_2d(sa + 2 * kStageABytes, &p.w_hi, sl.wk0 + kb * kTcBK, n0, fb);
+          tma_load_2d(sa + 2 * kStageABytes + b_bytes, &p.w_lo, sl.wk0 + kb * kTcBK, n0, fb);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -205,12 +220,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
       int stage = 0;
-      uint32_t phase = 0, set_phase = 0;  // bit s of set_phase: parity of TMEM set s
-      int group = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, group ^= 1) {
-        for (int kb = 0; kb < total_kb; kb++) {
-          const int set = 2 * group + (kb & 1);
-          mbar_wait(sete_bar(set), ((set_phase >> set) & 1u) ^ 1u);
+      uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; TMEM set = kbc & 3
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < total_kb; kb++, kbc++) {
+          const int set = kbc & 3;
+          mbar_wait(sete_bar(set), ((kbc >> 2) & 1u) ^ 1u);
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(set * p.bn);
@@ -230,7 +244,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           }
           tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
           tc_commit(setf_bar(set));     // partial sum of this K block complete
-          set_phase ^= 1u << set;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -240,23 +253,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------- epilogue groups (warps 2..5 and 6..9)
-    const int group = (warp - 2) >> 2;
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    uint32_t set_phase = 0;  // bit 0 / 1: parity of this group's two TMEM sets
-    for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
+    // ------------------------------------------------- epilogue warps 2..9
+    // warp -> (TMEM lane quadrant q, column half h): each thread owns one output row and up to 64
+    // columns of the tile, i.e. 64 fp32 running sums in registers
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    // this warp's 32 x 32 fp32 staging tile (float4 columns XOR-swizzled by row: conflict-free both ways)
+    float4 *stg = reinterpret_cast<float4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 2) * 4096u);
+    uint32_t kbc = 0;  // K blocks consumed so far: TMEM set = kbc & 3, parity = (kbc >> 2) & 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
-      float acc[kTcMaxBN];
+      float acc[kTcMaxBN / 2];
 #pragma unroll
-      for (int j = 0; j < kTcMaxBN; j++) acc[j] = 0.f;
-      for (int kb = 0; kb < total_kb; kb++) {
-        const int sl = kb & 1, set = 2 * group + sl;
-        mbar_wait(setf_bar(set), (set_phase >> sl) & 1u);
+      for (int j = 0; j < kTcMaxBN / 2; j++) acc[j] = 0.f;
+      for (int kb = 0; kb < total_kb; kb++, kbc++) {
+        const int set = kbc & 3;
+        mbar_wait(setf_bar(set), (kbc >> 2) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn + h * 64);
 #pragma unroll
-        for (int jc = 0; jc < kTcMaxBN / 32; jc++)
-          if (jc * 32 < p.bn) {
+        for (int jc = 0; jc < 2; jc++)
+          if (h * 64 + jc * 32 < p.bn) {
             uint32_t raw[32];
             tmem_ld32(taddr + jc * 32, raw);
 #pragma unroll
@@ -265,15 +281,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sete_bar(set));
-        set_phase ^= 1u << sl;
       }
       const int r = m0 + q * 32 + lane;
-      const bool row_ok = r < p.m;
-      const int rr = row_ok ? r : p.m - 1;
+      const int rr = r < p.m ? r : p.m - 1;
 #pragma unroll
-      for (int jc = 0; jc < kTcMaxBN / 32; jc++) {
-        const int c0 = n0 + jc * 32;
-        if (jc * 32 >= p.bn || c0 >= p.n) continue;
+      for (int jc = 0; jc < 2; jc++) {
+        const int c0 = n0 + h * 64 + jc * 32;
+        if (h * 64 + jc * 32 >= p.bn || c0 >= p.n) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = acc[jc * 32 + j];
@@ -312,32 +326,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               for (int j = 0; j < 32; j++) v[j] = __fmul_rn(v[j], op.alpha);
               break;
             case EpiOp::kAddScaled: {
-              long long orow = ((long long)rr * op.num) / op.den;
-              if (orow >= op.buf_rows) orow = op.buf_rows - 1;
-              const float *bh = op.buf + (size_t)orow * op.buf_ld + c0;
-              const float *bl = op.buf_lo ? op.buf_lo + (size_t)orow * op.buf_ld + c0 : nullptr;
+              // bypass input: read with full-row coalescing (8 lanes x 16 B cover a 128-byte row
+              // segment, 4 rows per instruction), summed hi + lo, transposed through the warp's
+              // staging tile so that each thread gets the 32 values of its own row
+              __syncwarp();
+              {
+                float4 bh[8], bl[8];  // all 16 loads in flight before the first use
+                const int c4 = lane & 7;
+                const bool col_ok = c0 + c4 * 4 < p.n;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (c0 + j < p.n) {
-                  float4 o = *reinterpret_cast<const float4 *>(bh + j);
-                  if (bl) {
-                    const float4 l = *reinterpret_cast<const float4 *>(bl + j);
-                    o.x = __fadd_rn(o.x, l.x);
-                    o.y = __fadd_rn(o.y, l.y);
-                    o.z = __fadd_rn(o.z, l.z);
-                    o.w = __fadd_rn(o.w, l.w);
+                for (int it = 0; it < 8; it++) {
+                  int ri = m0 + q * 32 + it * 4 + (lane >> 3);
+                  if (ri >= p.m) ri = p.m - 1;
+                  long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
+                  if (orow >= op.buf_rows) orow = op.buf_rows - 1;
+                  const size_t off = (size_t)orow * op.buf_ld + c0 + c4 * 4;
+                  bh[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  bl[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (col_ok) {
+                    bh[it] = __ldcs(reinterpret_cast<const float4 *>(op.buf + off));
+                    if (op.buf_lo) bl[it] = __ldcs(reinterpret_cast<const float4 *>(op.buf_lo + off));
                   }
-                  if (op.alpha != 1.f) {
-                    o.x = __fmul_rn(op.alpha, o.x);
-                    o.y = __fmul_rn(op.alpha, o.y);
-                    o.z = __fmul_rn(op.alpha, o.z);
-                    o.w = __fmul_rn(op.alpha, o.w);
-                  }
-                  v[j] = __fadd_rn(o.x, v[j]);
-                  v[j + 1] = __fadd_rn(o.y, v[j + 1]);
-                  v[j + 2] = __fadd_rn(o.z, v[j + 2]);
-                  v[j + 3] = __fadd_rn(o.w, v[j + 3]);
                 }
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                  const int i = it * 4 + (lane >> 3);
+                  float4 o = bh[it];
+                  o.x = __fadd_rn(o.x, bl[it].x);
+                  o.y = __fadd_rn(o.y, bl[it].y);
+                  o.z = __fadd_rn(o.z, bl[it].z);
+                  o.w = __fadd_rn(o.w, bl[it].w);
+                  stg[i * 8 + (c4 ^ (i & 7))] = o;
+                }
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = stg[lane * 8 + ((j >> 2) ^ (lane & 7))];
+                if (op.alpha != 1.f) {
+                  o.x = __fmul_rn(op.alpha, o.x);
+                  o.y = __fmul_rn(op.alpha, o.y);
+                  o.z = __fmul_rn(op.alpha, o.z);
+                  o.w = __fmul_rn(op.alpha, o.w);
+                }
+                v[j] = __fadd_rn(o.x, v[j]);
+                v[j + 1] = __fadd_rn(o.y, v[j + 1]);
+                v[j + 2] = __fadd_rn(o.z, v[j + 2]);
+                v[j + 3] = __fadd_rn(o.w, v[j + 3]);
+              }
               break;
             }
             case EpiOp::kUttBias: {
@@ -356,25 +392,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
           }
         }
-        if (row_ok) {
-          float *oh = p.out_hi + (size_t)r * p.out_ld + c0;
-          if (p.out_lo) {
-            float *ol = p.out_lo + (size_t)r * p.out_ld + c0;
+        // store through the staging tile: every instruction writes 4 rows x 128 contiguous bytes
+        for (int pl = 0; pl < (p.out_lo ? 2 : 1); pl++) {
+          float *dst = pl == 0 ? p.out_hi : p.out_lo;
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (c0 + j < p.n) {
-                float4 h, l;
-                split_tf32(v[j], h.x, l.x);
-                split_tf32(v[j + 1], h.y, l.y);
-                split_tf32(v[j + 2], h.z, l.z);
-                split_tf32(v[j + 3], h.w, l.w);
-                *reinterpret_cast<float4 *>(oh + j) = h;
-                *reinterpret_cast<float4 *>(ol + j) = l;
-              }
-          } else {
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.out_lo) {  // plane 0: hi = rna_tf32(x); plane 1: lo = x - hi
+              float4 h, l;
+              split_tf32(o.x, h.x, l.x);
+              split_tf32(o.y, h.y, l.y);
+              split_tf32(o.z, h.z, l.z);
+              split_tf32(o.w, h.w, l.w);
+              o = pl == 0 ? h : l;
+            }
+            stg[lane * 8 + ((j >> 2) ^ (lane & 7))] = o;
+          }
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (c0 + j < p.n) *reinterpret_cast<float4 *>(oh + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int it = 0; it < 8; it++) {
+            const int i = it * 4 + (lane >> 3), c4 = lane & 7;
+            const int ri = m0 + q * 32 + i;
+            if (ri < p.m && c0 + c4 * 4 < p.n)
+              *reinterpret_cast<float4 *>(dst + (size_t)ri * p.out_ld + c0 + c4 * 4) = stg[i * 8 + (c4 ^ (i & 7))];
           }
         }
       }
@@ -472,7 +513,7 @@ void TcConfigure(TcParams *p) {
     g_tc_smem_limit = v;
   }
   const int stage_bytes = 2 * kStageABytes + 2 * p->bn * 128;
-  int stages = (g_tc_smem_limit - 1024 - 256) / stage_bytes;
+  int stages = (g_tc_smem_limit - 1024 - 8 * 4096 - 256) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) RS_FAIL("not enough shared memory for the tensor-core GEMM pipeline");
   p->stages = stages;
@@ -486,7 +527,7 @@ void TcConfigure(TcParams *p) {
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream) {
   if (p.m <= 0 || p.n <= 0) return;
   const int stage_bytes = 2 * kStageABytes + 2 * p.bn * 128;
-  const int smem = 1024 + p.stages * stage_bytes + 8 * (2 * p.stages + 8) + 16;
+  const int smem = 1024 + p.stages * stage_bytes + 8 * 4096 + 8 * (2 * p.stages + 8) + 16;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tc_smem_limit);
