@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "../../include/rs_b200.h"
 #include "engine.h"
@@ -246,7 +247,7 @@ struct ModelImpl {
   // tensor-core path (nnet_tc.cu): per plan step, the packed + split weights and their tensor maps
   struct TcStep {
     bool ok = false;
-    const float *w_hi = nullptr, *w_lo = nullptr;
+    const __half *w_hi = nullptr, *w_lo = nullptr;
     int kp = 0, bn = 0;
     std::vector<int> k0;
     CUtensorMap map_hi, map_lo;
@@ -289,6 +290,8 @@ struct DecoderImpl {
   PinBuf h_in, h_out;
   LaneWorkspace *d_lanes = nullptr;
   int *d_next_utt = nullptr;
+  int *d_range_flag = nullptr;  // set by a split store that had to saturate (fp16 planes)
+  int *h_range_flag = nullptr;  // pinned
   std::vector<int4> earc_with_pdf;  // graph arcs with ilabel mapped to pdf for this model
   const int4 *d_earc = nullptr;
   rs_timings last{};
@@ -305,6 +308,7 @@ struct DecoderImpl {
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+    if (h_range_flag) cudaFreeHost(h_range_flag);
   }
 };
 
@@ -442,7 +446,7 @@ static void UploadModel(ModelImpl *mi) {
       ModelImpl::TcStep &ts = mi->tc_steps[si];
       std::vector<std::pair<int, int>> cols;
       for (const Slab &sl : st.slabs) cols.push_back({sl.wcol, sl.k});
-      std::vector<float> hi, lo;
+      std::vector<__half> hi, lo;
       TcPackWeights(pl.matrices[st.weight].d.data(), st.n, st.ktot, cols, &hi, &lo, &ts.k0, &ts.kp);
       ts.w_hi = Upload(hi, &own);
       ts.w_lo = Upload(lo, &own);
@@ -667,6 +671,9 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
   }
   d->d_lanes = Upload(lanes, &d->owned);
   d->d_next_utt = (int *)dalloc(sizeof(int), 0);
+  d->d_range_flag = (int *)dalloc(sizeof(int), 0);
+  CUDA_OK(cudaMallocHost(&d->h_range_flag, sizeof(int)));
+  *d->h_range_flag = 0;
   d->slots.resize(mi->m.plan.num_slots);
   CUDA_OK(cudaDeviceSynchronize());
   return reinterpret_cast<rs_decoder *>(d.release());
@@ -834,8 +841,34 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   const size_t desc_ints = (size_t)2 * n + 5 * (size_t)n + axis_len;
   char *hin = (char *)d->h_in.ensure(pcm_bytes + 16 + desc_ints * sizeof(int));
   int16_t *hpcm = (int16_t *)hin;
-  for (int u = 0; u < n; u++)
-    if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
+  // Staging is split over a few host threads, and each thread's byte range goes to the device as
+  // soon as it is complete, so the H2D copy of the first ranges overlaps the packing of the rest.
+  int n_workers = 1;
+  if (pcm_bytes > (1u << 20)) n_workers = (int)std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u), (size_t)n);
+  std::vector<int> range_begin(n_workers + 1, n);
+  {
+    int u = 0;
+    for (int w = 0; w < n_workers; w++) {
+      range_begin[w] = u;
+      const int64_t target = total_samples * (w + 1) / n_workers;
+      while (u < n && pcm_offset[u] + nsamp[u] <= target) u++;
+      if (w == n_workers - 1) u = n;
+    }
+    range_begin[n_workers] = n;
+  }
+  auto pack = [&](int w) {
+    for (int u = range_begin[w]; u < range_begin[w + 1]; u++)
+      if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
+  };
+  std::vector<std::thread> workers;
+  struct JoinAll {  // an error path must not leave joinable threads behind
+    std::vector<std::thread> *v;
+    ~JoinAll() {
+      for (auto &t : *v)
+        if (t.joinable()) t.join();
+    }
+  } join_all{&workers};
+  for (int w = 1; w < n_workers; w++) workers.emplace_back(pack, w);
   size_t desc_off = (pcm_bytes + 15) & ~(size_t)15;
   int *hdesc = (int *)(hin + desc_off);
   memcpy(hdesc, pcm_offset.data(), sizeof(int64_t) * n);
@@ -857,8 +890,15 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   int16_t *dpcm = (int16_t *)d->d_pcm.ensure(pcm_bytes);
   int *ddesc = (int *)d->d_desc.ensure(desc_ints * sizeof(int));
   CUDA_OK(cudaEventRecord(d->ev[0], d->stream));
-  CUDA_OK(cudaMemcpyAsync(dpcm, hpcm, pcm_bytes, cudaMemcpyHostToDevice, d->stream));
   CUDA_OK(cudaMemcpyAsync(ddesc, hdesc, desc_ints * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  pack(0);
+  for (int w = 0; w < n_workers; w++) {
+    if (w > 0) workers[w - 1].join();
+    const int64_t s0 = range_begin[w] < n ? pcm_offset[range_begin[w]] : total_samples;
+    const int64_t s1 = range_begin[w + 1] < n ? pcm_offset[range_begin[w + 1]] : total_samples;
+    if (s1 > s0)
+      CUDA_OK(cudaMemcpyAsync(dpcm + s0, hpcm + s0, sizeof(int16_t) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, d->stream));
+  }
   CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
   d->last.h2d_bytes = pcm_bytes + desc_ints * sizeof(int);
   const int64_t *d_pcm_off = (const int64_t *)ddesc;
@@ -885,16 +925,17 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   int ivector_ld = 0;
   // slot storage for the plan
   auto slot_ptr = [&](int buffer) -> float * { return d->slots[pl.buffers[buffer].slot].as<float>(); };
-  auto buf_ld = [&](int buffer) { return RoundUp(pl.buffers[buffer].dim, 4); };
+  // row pitch in elements: fp32 buffers are padded to 16 bytes, split (2 x fp16 plane) buffers too
+  auto buf_ld = [&](int buffer) { return RoundUp(pl.buffers[buffer].dim, mi->split[buffer] ? 8 : 4); };
   auto buf_rows = [&](int buffer) { return pl.buffers[buffer].per_utt ? n : axis_len / pl.buffers[buffer].step; };
   // split buffers hold two planes back to back: hi at slot_ptr, lo right behind it
-  auto slot_lo = [&](int buffer) -> float * {
-    return mi->split[buffer] ? slot_ptr(buffer) + (size_t)buf_rows(buffer) * buf_ld(buffer) : nullptr;
+  auto slot_lo = [&](int buffer) -> __half * {
+    return mi->split[buffer] ? reinterpret_cast<__half *>(slot_ptr(buffer)) + (size_t)buf_rows(buffer) * buf_ld(buffer) : nullptr;
   };
   {
     std::vector<size_t> need(pl.num_slots, 0);
     for (size_t b = 0; b < pl.buffers.size(); b++) {
-      size_t bytes = (size_t)buf_rows((int)b) * buf_ld((int)b) * sizeof(float) * (mi->split[b] ? 2 : 1);
+      size_t bytes = (size_t)buf_rows((int)b) * buf_ld((int)b) * 4;  // one fp32 plane or two fp16 planes
       need[pl.buffers[b].slot] = std::max(need[pl.buffers[b].slot], bytes);
     }
     for (int s = 0; s < pl.num_slots; s++) d->slots[s].ensure(std::max<size_t>(need[s], 16));
@@ -963,9 +1004,11 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   {
     float *in = slot_ptr(pl.input_buffer);
     const int ild = buf_ld(pl.input_buffer);
-    CUDA_OK(cudaMemsetAsync(in, 0, (size_t)axis_len * ild * sizeof(float) * (mi->split[pl.input_buffer] ? 2 : 1), d->stream));
+    CUDA_OK(cudaMemsetAsync(in, 0, (size_t)axis_len * ild * 4, d->stream));
+    CUDA_OK(cudaMemsetAsync(d->d_range_flag, 0, sizeof(int), d->stream));
     AssembleParams a{};
     a.dst_lo = slot_lo(pl.input_buffer);
+    a.range_flag = d->d_range_flag;
     a.feats = nnet_feats;
     a.num_frames = d_nf;
     a.frame_offset = d_fo;
@@ -985,6 +1028,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     const PlanBuffer &ob = pl.buffers[st.out];
     g.out = slot_ptr(st.out);
     g.out_lo = slot_lo(st.out);
+    g.range_flag = d->d_range_flag;
     g.out_ld = buf_ld(st.out);
     g.m = buf_rows(st.out);
     g.n = st.n;
@@ -1052,7 +1096,8 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
             const int rem = ((sh % stride) + stride) % stride;
             const int ld = buf_ld(sl.src), rows = buf_rows(sl.src);
             const long long view_rows = rows > rem ? (rows - 1 - rem) / stride + 1 : 0;
-            TcEncodeMap(&t.a_hi[s], slot_ptr(sl.src) + (size_t)rem * ld, view_rows, sl.k, (long long)stride * ld, kTcBM);
+            TcEncodeMap(&t.a_hi[s], reinterpret_cast<const __half *>(slot_ptr(sl.src)) + (size_t)rem * ld, view_rows, sl.k,
+                        (long long)stride * ld, kTcBM);
             TcEncodeMap(&t.a_lo[s], slot_lo(sl.src) + (size_t)rem * ld, view_rows, sl.k, (long long)stride * ld, kTcBM);
             t.slabs[s].kblocks = (sl.k + kTcBK - 1) / kTcBK;
             t.slabs[s].wk0 = ts.k0[s];
@@ -1066,6 +1111,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
           t.n_ops = g.n_ops;
           for (int i = 0; i < g.n_ops; i++) t.ops[i] = g.ops[i];
           t.row_utt = g.row_utt;
+          t.range_flag = d->d_range_flag;
           TcConfigure(&t);
           LaunchGemmTc(t, mi->num_sms, d->stream);
           break;
@@ -1079,12 +1125,15 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
         LaunchElementwise(g, st.term_scale.data(), st.col_offset, d->stream);
         break;
       case Step::kLogSoftmax:
-        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].src_lo, g.slabs[0].ld, g.out, g.out_ld, g.m, g.n, d->stream);
+        if (g.out_lo) RS_FAIL("internal: a log-softmax output feeding a tensor-core layer is not supported");
+        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].src_lo, g.slabs[0].ld, reinterpret_cast<float *>(g.out), g.out_ld, g.m, g.n,
+                         d->stream);
         break;
     }
     launches++;
   }
   CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(d->h_range_flag, d->d_range_flag, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
   CUDA_OK(cudaEventRecord(d->ev[3], d->stream));
   d->last.nnet_flops = (uint64_t)((double)mi->flops_per_axis_unit / 1000.0 * axis_len);
   // ---- stage (iii)
@@ -1092,6 +1141,10 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   B.ll_ld = buf_ld(pl.output_buffer);
   rs_result *r = RunDecodeStage(d, B.loglikes, B.ll_ld, d_r0, d_no, launches);
   FinishTimings(d, launches);
+  if (*d->h_range_flag) {
+    rs_result_free(r);
+    RS_FAIL("an activation exceeded the fp16 range (+-65504) of the tensor-core path; set RS_B200_GEMM=simt for this model");
+  }
   return r;
 }
 
@@ -1340,30 +1393,42 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
       for (void *p : *v) cudaFree(p);
     }
   } free_all{&owned};
-  const int ld = RoundUp(k, 4), m = std::max(rows / stride, 1), ktot = k * n_offsets, out_ld = RoundUp(n, 4);
   const bool tc = path != 0, split_out = path == 2;
-  std::vector<float> hi((size_t)rows * ld, 0.f), lo((size_t)rows * ld, 0.f);
-  for (int r = 0; r < rows; r++)
-    for (int c = 0; c < k; c++) {
-      if (tc) TcSplitHost(src[(size_t)r * k + c], &hi[(size_t)r * ld + c], &lo[(size_t)r * ld + c]);
-      else hi[(size_t)r * ld + c] = src[(size_t)r * k + c];
-    }
-  float *d_hi = Upload(hi, &owned), *d_lo = tc ? Upload(lo, &owned) : nullptr;
+  const int ld = RoundUp(k, tc ? 8 : 4), m = std::max(rows / stride, 1), ktot = k * n_offsets;
+  const int out_ld = RoundUp(n, split_out ? 8 : 4);
+  // source: plain fp32 for the CUDA-core path, two fp16 planes for the tensor-core path
+  const void *d_src = nullptr, *d_src_lo = nullptr;
+  if (tc) {
+    std::vector<__half> hi((size_t)rows * ld, __float2half_rn(0.f)), lo((size_t)rows * ld, __float2half_rn(0.f));
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < k; c++)
+        if (!TcSplitHost(src[(size_t)r * k + c], &hi[(size_t)r * ld + c], &lo[(size_t)r * ld + c]))
+          RS_FAIL("rs_debug_gemm: source value out of fp16 range");
+    d_src = Upload(hi, &owned);
+    d_src_lo = Upload(lo, &owned);
+  } else {
+    std::vector<float> plain((size_t)rows * ld, 0.f);
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < k; c++) plain[(size_t)r * ld + c] = src[(size_t)r * k + c];
+    d_src = Upload(plain, &owned);
+  }
   std::vector<float> zeros((size_t)m * out_ld, 0.f);
-  float *d_out = Upload(zeros, &owned), *d_out_lo = split_out ? Upload(zeros, &owned) : nullptr;
+  float *d_out = Upload(zeros, &owned);  // fp32 matrix, or hi | lo fp16 planes (same bytes)
+  __half *d_out_lo = split_out ? reinterpret_cast<__half *>(d_out) + (size_t)m * out_ld : nullptr;
+  int *d_flag = Upload(std::vector<int>(4, 0), &owned);
   std::vector<float> bias_pad;
   const float *d_bias = nullptr;
   if (bias) {
     bias_pad.assign(bias, bias + n);
-    bias_pad.resize(out_ld, 0.f);
+    bias_pad.resize(RoundUp(n, 8), 0.f);
     d_bias = Upload(bias_pad, &owned);
   }
   GemmParams g{};
   g.n_slabs = n_offsets;
   for (int s = 0; s < n_offsets; s++) {
     GemmSlab &gs = g.slabs[s];
-    gs.src = d_hi;
-    gs.src_lo = d_lo;
+    gs.src = d_src;
+    gs.src_lo = d_src_lo;
     gs.ld = ld;
     gs.rows = rows;
     gs.k = k;
@@ -1374,6 +1439,7 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
   }
   g.out = d_out;
   g.out_lo = d_out_lo;
+  g.range_flag = d_flag;
   g.out_ld = out_ld;
   g.m = m;
   g.n = n;
@@ -1389,11 +1455,11 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
     if (prop.major != 10) RS_FAIL("the tensor-core path needs sm_100a");
     std::vector<std::pair<int, int>> cols;
     for (int s = 0; s < n_offsets; s++) cols.push_back({s * k, k});
-    std::vector<float> whi, wlo;
+    std::vector<__half> whi, wlo;
     std::vector<int> k0;
     int kp = 0;
     TcPackWeights(w, n, ktot, cols, &whi, &wlo, &k0, &kp);
-    const float *d_whi = Upload(whi, &owned), *d_wlo = Upload(wlo, &owned);
+    const __half *d_whi = Upload(whi, &owned), *d_wlo = Upload(wlo, &owned);
     t.bn = TcTileN(n);
     TcEncodeMap(&t.w_hi, d_whi, n, kp, kp, t.bn);
     TcEncodeMap(&t.w_lo, d_wlo, n, kp, kp, t.bn);
@@ -1401,8 +1467,8 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
     for (int s = 0; s < n_offsets; s++) {
       const int sh = offsets[s], rem = ((sh % stride) + stride) % stride;
       const long long view_rows = rows > rem ? (rows - 1 - rem) / stride + 1 : 0;
-      TcEncodeMap(&t.a_hi[s], d_hi + (size_t)rem * ld, view_rows, k, (long long)stride * ld, kTcBM);
-      TcEncodeMap(&t.a_lo[s], d_lo + (size_t)rem * ld, view_rows, k, (long long)stride * ld, kTcBM);
+      TcEncodeMap(&t.a_hi[s], reinterpret_cast<const __half *>(d_src) + (size_t)rem * ld, view_rows, k, (long long)stride * ld, kTcBM);
+      TcEncodeMap(&t.a_lo[s], reinterpret_cast<const __half *>(d_src_lo) + (size_t)rem * ld, view_rows, k, (long long)stride * ld, kTcBM);
       t.slabs[s].kblocks = (k + kTcBK - 1) / kTcBK;
       t.slabs[s].wk0 = k0[s];
       t.slabs[s].yshift = (sh - rem) / stride;
@@ -1414,6 +1480,7 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
     t.n = n;
     t.n_ops = g.n_ops;
     for (int i = 0; i < g.n_ops; i++) t.ops[i] = g.ops[i];
+    t.range_flag = d_flag;
     TcConfigure(&t);
   } else {
     std::vector<float> wv(w, w + (size_t)n * ktot);
@@ -1443,15 +1510,17 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  std::vector<float> h((size_t)m * out_ld), hl;
+  std::vector<float> h((size_t)m * out_ld);
   CUDA_OK(cudaMemcpy(h.data(), d_out, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
   if (split_out) {
-    hl.resize(h.size());
-    CUDA_OK(cudaMemcpy(hl.data(), d_out_lo, hl.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const __half *hh = reinterpret_cast<const __half *>(h.data()), *hl = hh + (size_t)m * out_ld;
+    for (int r = 0; r < m; r++)
+      for (int c = 0; c < n; c++)
+        out[(size_t)r * n + c] = __half2float(hh[(size_t)r * out_ld + c]) + __half2float(hl[(size_t)r * out_ld + c]) / kSplitScale;
+  } else {
+    for (int r = 0; r < m; r++)
+      for (int c = 0; c < n; c++) out[(size_t)r * n + c] = h[(size_t)r * out_ld + c];
   }
-  for (int r = 0; r < m; r++)
-    for (int c = 0; c < n; c++)
-      out[(size_t)r * n + c] = h[(size_t)r * out_ld + c] + (split_out ? hl[(size_t)r * out_ld + c] : 0.f);
   return 0;
   API_GUARD_END(1)
 }

@@ -86,9 +86,9 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream);
 constexpr int kMaxSlabs = 8;
 constexpr int kMaxOps = 8;
 struct GemmSlab {
-  const float *src;
-  const float *src_lo;  // second plane of a split buffer (value = src + src_lo), or null
-  int ld;        // row stride of src in floats
+  const void *src;      // fp32 matrix, or the hi plane of a split buffer (split.cuh)
+  const void *src_lo;   // lo plane of a split buffer, or null
+  int ld;        // row stride of src in elements
   int rows;      // valid rows of src (indices are clamped into [0, rows))
   int k;         // columns used
   int wcol;      // first weight column
@@ -99,8 +99,8 @@ struct DevOp {
   int type;            // EpiOp::Type
   const float *v0, *v1;
   float alpha;
-  const float *buf;    // kAddScaled: other activation buffer ; kUttBias: [n_utts, ld]
-  const float *buf_lo; // kAddScaled: second plane of a split buffer, or null
+  const void *buf;     // kAddScaled: other activation buffer (fp32 or hi plane) ; kUttBias: fp32 [n_utts, ld]
+  const void *buf_lo;  // kAddScaled: lo plane of a split buffer, or null
   int buf_ld, buf_rows;
   int num, den;        // kAddScaled: other_row = out_row * num / den ; kUttBias: axis time = out_row * num
 };
@@ -109,8 +109,9 @@ struct GemmParams {
   int n_slabs;
   const float *w;  // [n, ktot] row-major
   int ktot;
-  float *out;
-  float *out_lo;   // not null: store the result split into two TF32 planes (see nnet_tc.cu)
+  void *out;
+  void *out_lo;    // not null: store the result split into two fp16 planes (split.cuh)
+  int *range_flag; // set if a split store saturated
   int out_ld;
   int m, n;        // output rows / columns
   DevOp ops[kMaxOps];
@@ -120,14 +121,15 @@ struct GemmParams {
 };
 void LaunchGemm(const GemmParams &p, cudaStream_t stream);
 void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int col_offset, cudaStream_t stream);
-void LaunchLogSoftmax(const float *in, const float *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
+void LaunchLogSoftmax(const void *in, const void *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
                       cudaStream_t stream);
 
 struct AssembleParams {
   const float *feats;  // [total_frames, dim]
   const int *num_frames, *frame_offset, *origin;  // per utt
-  float *dst;          // nnet input buffer on the global axis [axis_len, ld]
-  float *dst_lo;       // not null: split store
+  void *dst;           // nnet input buffer on the global axis [axis_len, ld]
+  void *dst_lo;        // not null: split store
+  int *range_flag;
   int dim, ld, left, right, axis_len;
 };
 void LaunchAssembleInput(const AssembleParams &p, int n_utts, int max_rows, cudaStream_t stream);

@@ -115,121 +115,134 @@ __global__ void __launch_bounds__(256) splice_lda_kernel(IvecParams p) {
   }
 }
 
-// -------------------------------------------------------------------- UBM posteriors (warp/frame)
-constexpr int kMaxGaussPerLane = 64;  // up to 2048 Gaussians
+// -------------------------------------------------------------------- UBM posteriors
+// DiagGmm::LogLikelihoods (gmm/diag-gmm.cc:546-562) for a tile of kUbmFrames frames per CTA as a
+// register-tiled product [frames x D] x [D x G] (the UBM tables stream through L2 once per tile,
+// not once per frame), then VectorToPosteriorEntry (hmm/posterior.cc:440-508) with one warp per
+// frame over the log-likelihood row kept in shared memory.
+constexpr int kUbmFrames = 16;
 __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
   extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= p.total_frames) return;
-  float *x = sm + (size_t)warp * p.ldim * 2, *xsq = x + p.ldim;
-  for (int d = lane; d < p.ldim; d += 32) {
-    float v = p.x_norm[(size_t)row * p.ldim + d];
-    x[d] = v;
-    xsq[d] = __fmul_rn(v, v);
+  const int D = p.ldim, G = p.num_gauss;
+  float *sx = sm, *sxsq = sx + kUbmFrames * D, *sll = sxsq + kUbmFrames * D;  // [F][D], [F][D], [F][G]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kUbmFrames;
+  const int nrows = min(kUbmFrames, p.total_frames - row0);
+  for (int i = tid; i < kUbmFrames * D; i += 256) {
+    const int f = i / D;
+    const float v = f < nrows ? p.x_norm[(size_t)row0 * D + i] : 0.f;
+    sx[i] = v;
+    sxsq[i] = __fmul_rn(v, v);
   }
-  __syncwarp();
-  const int G = p.num_gauss;
-  float ll[kMaxGaussPerLane];
-  float mx = -FLT_MAX;
-#pragma unroll 1
-  for (int i = 0; i < kMaxGaussPerLane; i++) {
-    int g = lane + i * 32;
-    if (g >= G) break;
-    float a1 = 0.f, a2 = 0.f;
-    for (int d = 0; d < p.ldim; d++) {
-      a1 = fmaf(x[d], p.means_invvars_t[(size_t)d * G + g], a1);
-      a2 = fmaf(xsq[d], p.inv_vars_t[(size_t)d * G + g], a2);
-    }
-    float v = __fadd_rn(__fadd_rn(p.gconsts[g], a1), __fmul_rn(-0.5f, a2));
-    ll[i] = v;
-    mx = fmaxf(mx, v);
-  }
+  __syncthreads();
+  {
+    const int tg = tid & 63, tf = tid >> 6;  // 64 Gaussian lanes x 4 frame groups of 4 frames
+    for (int g0 = 0; g0 < G; g0 += 512) {
+      float a1[4][8], a2[4][8];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) a1[f][j] = a2[f][j] = 0.f;
+      for (int d = 0; d < D; d++) {
+        float m[8], iv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int g = g0 + tg + 64 * j;
+          m[j] = g < G ? __ldg(p.means_invvars_t + (size_t)d * G + g) : 0.f;
+          iv[j] = g < G ? __ldg(p.inv_vars_t + (size_t)d * G + g) : 0.f;
+        }
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+          const float xf = sx[(tf * 4 + f) * D + d], x2 = sxsq[(tf * 4 + f) * D + d];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            a1[f][j] = fmaf(xf, m[j], a1[f][j]);
+            a2[f][j] = fmaf(x2, iv[j], a2[f][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int g = g0 + tg + 64 * j;
+        if (g < G) {
+          const float gc = p.gconsts[g];
+#pragma unroll
+          for (int f = 0; f < 4; f++)
+            sll[(tf * 4 + f) * G + g] = __fadd_rn(__fadd_rn(gc, a1[f][j]), __fmul_rn(-0.5f, a2[f][j]));
+        }
+      }
+    }
+  }
+  __syncthreads();
   // GetMinPost with weight 1.0 (online-ivector-feature.cc:188-199)
-  float min_post = p.min_post > 0.99f ? 0.99f : p.min_post;
-  const float cut = min_post != 0.f ? __fadd_rn(mx, logf(min_post)) : -FLT_MAX;
-  // posteriors of the candidates; everything else is marked -1
-  int any = 0;
-#pragma unroll 1
-  for (int i = 0; i < kMaxGaussPerLane; i++) {
-    int g = lane + i * 32;
-    if (g >= G) break;
-    float v = ll[i];
-    if (min_post != 0.f && v > cut) {
-      ll[i] = (float)exp((double)__fsub_rn(v, mx));
-      any = 1;
-    } else {
-      ll[i] = -1.f;
-    }
-  }
-  any = __any_sync(0xffffffffu, any);
-  if (!any) {  // min_post == 0 or nothing above the threshold: all Gaussians are candidates
-#pragma unroll 1
-    for (int i = 0; i < kMaxGaussPerLane; i++) {
-      int g = lane + i * 32;
-      if (g >= G) break;
-      float a1 = 0.f, a2 = 0.f;
-      for (int d = 0; d < p.ldim; d++) {
-        a1 = fmaf(x[d], p.means_invvars_t[(size_t)d * G + g], a1);
-        a2 = fmaf(xsq[d], p.inv_vars_t[(size_t)d * G + g], a2);
-      }
-      float v = __fadd_rn(__fadd_rn(p.gconsts[g], a1), __fmul_rn(-0.5f, a2));
-      ll[i] = expf(__fsub_rn(v, mx));
-    }
-  }
-  // top num_gselect by posterior, in decreasing order (ties: lowest Gaussian index)
-  const int ng = p.num_gselect < G ? p.num_gselect : G;
-  float sel_post[8];
-  int sel_idx[8];
-  int nsel = 0;
-  for (int s = 0; s < ng && s < 8; s++) {
-    float best = -1.f;
-    int bi = 0x7fffffff;
-#pragma unroll 1
-    for (int i = 0; i < kMaxGaussPerLane; i++) {
-      int g = lane + i * 32;
-      if (g >= G) break;
-      if (ll[i] > best) {
-        best = ll[i];
-        bi = g;
-      }
-    }
+  const float min_post = p.min_post > 0.99f ? 0.99f : p.min_post;
+  for (int f = warp; f < nrows; f += 8) {
+    const int row = row0 + f;
+    float *ll = sll + (size_t)f * G;  // lane owns elements lane, lane + 32, ...
+    float mx = -FLT_MAX;
+    for (int g = lane; g < G; g += 32) mx = fmaxf(mx, ll[g]);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) {
-        best = ob;
-        bi = oi;
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float cut = min_post != 0.f ? __fadd_rn(mx, logf(min_post)) : -FLT_MAX;
+    // posteriors of the candidates; everything else is marked -1
+    int any = 0;
+    for (int g = lane; g < G; g += 32) any |= (min_post != 0.f && ll[g] > cut) ? 1 : 0;
+    any = __any_sync(0xffffffffu, any);
+    for (int g = lane; g < G; g += 32) {
+      const float v = ll[g];
+      if (any)
+        ll[g] = v > cut ? (float)exp((double)__fsub_rn(v, mx)) : -1.f;
+      else  // min_post == 0 or nothing above the threshold: all Gaussians are candidates
+        ll[g] = expf(__fsub_rn(v, mx));
+    }
+    // top num_gselect by posterior, in decreasing order (ties: lowest Gaussian index)
+    const int ng = p.num_gselect < G ? p.num_gselect : G;
+    float sel_post[8];
+    int sel_idx[8];
+    int nsel = 0;
+    for (int s = 0; s < ng && s < 8; s++) {
+      float best = -1.f;
+      int bi = 0x7fffffff;
+      for (int g = lane; g < G; g += 32)
+        if (ll[g] > best) {
+          best = ll[g];
+          bi = g;
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
       }
+      if (best < 0.f) break;
+      sel_post[nsel] = best;
+      sel_idx[nsel] = bi;
+      nsel++;
+      if ((bi & 31) == lane) ll[bi] = -1.f;
     }
-    if (best < 0.f) break;
-    sel_post[nsel] = best;
-    sel_idx[nsel] = bi;
-    nsel++;
-    if ((bi & 31) == lane) ll[bi >> 5] = -1.f;
-  }
-  // prune + renormalise (posterior.cc:490-505), all lanes redundantly
-  float tot = 0.f;
-  for (int s = 0; s < nsel; s++) tot = __fadd_rn(tot, sel_post[s]);
-  const float cutoff = __fmul_rn(min_post, tot);
-  while (nsel > 1 && sel_post[nsel - 1] < cutoff) {
-    tot = __fsub_rn(tot, sel_post[nsel - 1]);
-    nsel--;
-  }
-  const float inv_tot = (float)(1.0 / (double)tot);
-  const float sc = p.posterior_scale;  // * weight (1.0)
-  if (lane < p.num_gselect) {
-    int idx = -1;
-    float w = 0.f;
-    if (lane < nsel) {
-      idx = sel_idx[lane];
-      w = __fmul_rn(__fmul_rn(sel_post[lane], inv_tot), sc);
+    // prune + renormalise (posterior.cc:490-505), all lanes redundantly
+    float tot = 0.f;
+    for (int s = 0; s < nsel; s++) tot = __fadd_rn(tot, sel_post[s]);
+    const float cutoff = __fmul_rn(min_post, tot);
+    while (nsel > 1 && sel_post[nsel - 1] < cutoff) {
+      tot = __fsub_rn(tot, sel_post[nsel - 1]);
+      nsel--;
     }
-    p.post_idx[(size_t)row * p.num_gselect + lane] = idx;
-    p.post_w[(size_t)row * p.num_gselect + lane] = w;
+    const float inv_tot = (float)(1.0 / (double)tot);
+    const float sc = p.posterior_scale;  // * weight (1.0)
+    if (lane < p.num_gselect) {
+      int idx = -1;
+      float w = 0.f;
+      if (lane < nsel) {
+        idx = sel_idx[lane];
+        w = __fmul_rn(__fmul_rn(sel_post[lane], inv_tot), sc);
+      }
+      p.post_idx[(size_t)row * p.num_gselect + lane] = idx;
+      p.post_w[(size_t)row * p.num_gselect + lane] = w;
+    }
   }
 }
 
@@ -447,8 +460,13 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
     dim3 g1((p.max_frames + kLdaFrames - 1) / kLdaFrames, p.n_utts);
     size_t sm1 = (size_t)2 * (kLdaFrames + p.left + p.right) * p.dim * sizeof(float);
     splice_lda_kernel<<<g1, 256, sm1, stream>>>(p);
-    size_t sm2 = (size_t)8 * 2 * D * sizeof(float);
-    ubm_post_kernel<<<(p.total_frames + 7) / 8, 256, sm2, stream>>>(p);
+    size_t sm2 = (size_t)kUbmFrames * (2 * D + G) * sizeof(float);
+    static size_t ubm_attr = 48 * 1024;
+    if (sm2 > ubm_attr) {
+      cudaFuncSetAttribute(ubm_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      ubm_attr = sm2;
+    }
+    ubm_post_kernel<<<(p.total_frames + kUbmFrames - 1) / kUbmFrames, 256, sm2, stream>>>(p);
   }
   cudaMemsetAsync(p.wf, 0, (size_t)p.n_utts * G * D * sizeof(double), stream);
   if (p.total_frames > 0) {

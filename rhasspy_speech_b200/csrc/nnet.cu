@@ -16,6 +16,7 @@
 // This file holds the fp32 CUDA-core path (exact fp32 products, fp32 FMA accumulation).
 #include "engine.h"
 #include "model.h"
+#include "split.cuh"
 
 namespace rs {
 
@@ -43,14 +44,13 @@ __device__ __forceinline__ float apply_ops(float v, int r, int c, const GemmPara
       case EpiOp::kAddScaled: {
         long long orow = ((long long)r * op.num) / op.den;
         if (orow >= op.buf_rows) orow = op.buf_rows - 1;
-        float o = op.buf[(size_t)orow * op.buf_ld + c];
-        if (op.buf_lo) o = __fadd_rn(o, op.buf_lo[(size_t)orow * op.buf_ld + c]);
+        const float o = ld_act(op.buf, op.buf_lo, (size_t)orow * op.buf_ld + c);
         v = __fadd_rn(op.alpha == 1.f ? o : __fmul_rn(op.alpha, o), v);
         break;
       }
       case EpiOp::kUttBias: {
         int u = p.row_utt[(size_t)r * op.num];
-        v = __fadd_rn(v, op.buf[(size_t)u * op.buf_ld + c]);
+        v = __fadd_rn(v, reinterpret_cast<const float *>(op.buf)[(size_t)u * op.buf_ld + c]);
         break;
       }
     }
@@ -64,15 +64,6 @@ __device__ __forceinline__ long long slab_row(const GemmSlab &s, int r) {
   if (q < 0) q = 0;
   if (q >= s.rows) q = s.rows - 1;
   return q;
-}
-
-// x = hi + lo with hi on the TF32 grid (the layout the tensor-core layers read, nnet_tc.cu)
-__device__ __forceinline__ void split_store(float *hi_p, float *lo_p, float x) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  const float hi = __uint_as_float(h);
-  *hi_p = hi;
-  *lo_p = __fsub_rn(x, hi);
 }
 
 template <bool kVec>
@@ -89,16 +80,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
 
   float4 ra[2], rb[2];
   int cur_slab = 0, cur_k0 = 0;
-  const float *arow[2] = {nullptr, nullptr};
-  const float *arow_lo[2] = {nullptr, nullptr};
+  const float *arow[2] = {nullptr, nullptr};  // plain fp32 source rows
+  size_t aoff[2] = {0, 0};                    // element offset of the row (split sources)
   auto set_slab = [&](int s) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       int r = row0 + lrow + h * 64;
       if (r >= p.m) r = p.m - 1;
-      const size_t off = (size_t)slab_row(p.slabs[s], r) * p.slabs[s].ld;
-      arow[h] = p.slabs[s].src + off;
-      arow_lo[h] = p.slabs[s].src_lo ? p.slabs[s].src_lo + off : nullptr;
+      aoff[h] = (size_t)slab_row(p.slabs[s], r) * p.slabs[s].ld;
+      arow[h] = reinterpret_cast<const float *>(p.slabs[s].src) + aoff[h];
     }
   };
   auto load_tile = [&]() {
@@ -107,19 +97,18 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kVec) {
+      if (sl.src_lo) {  // split source (two fp16 planes)
+        if (k + 0 < sl.k) v.x = ld_act(sl.src, sl.src_lo, aoff[h] + k + 0);
+        if (k + 1 < sl.k) v.y = ld_act(sl.src, sl.src_lo, aoff[h] + k + 1);
+        if (k + 2 < sl.k) v.z = ld_act(sl.src, sl.src_lo, aoff[h] + k + 2);
+        if (k + 3 < sl.k) v.w = ld_act(sl.src, sl.src_lo, aoff[h] + k + 3);
+      } else if (kVec) {
         if (k < sl.k) v = *reinterpret_cast<const float4 *>(arow[h] + k);
       } else {
         if (k + 0 < sl.k) v.x = arow[h][k + 0];
         if (k + 1 < sl.k) v.y = arow[h][k + 1];
         if (k + 2 < sl.k) v.z = arow[h][k + 2];
         if (k + 3 < sl.k) v.w = arow[h][k + 3];
-      }
-      if (arow_lo[h]) {  // split buffer: value = hi + lo (exact)
-        if (k + 0 < sl.k) v.x = __fadd_rn(v.x, arow_lo[h][k + 0]);
-        if (k + 1 < sl.k) v.y = __fadd_rn(v.y, arow_lo[h][k + 1]);
-        if (k + 2 < sl.k) v.z = __fadd_rn(v.z, arow_lo[h][k + 2]);
-        if (k + 3 < sl.k) v.w = __fadd_rn(v.w, arow_lo[h][k + 3]);
       }
       ra[h] = v;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -214,12 +203,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const __grid_constan
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = (c + j < p.n) ? apply_ops(acc[i][jh * 4 + j], r, c + j, p) : 0.f;
-      float *o = p.out + (size_t)r * p.out_ld + c;
+      float *o = reinterpret_cast<float *>(p.out) + (size_t)r * p.out_ld + c;
       if (p.out_lo) {
-        float *ol = p.out_lo + (size_t)r * p.out_ld + c;
 #pragma unroll
         for (int j = 0; j < 4; j++)
-          if (c + j < p.n) split_store(o + j, ol + j, v[j]);
+          if (c + j < p.n) st_act(p.out, p.out_lo, (size_t)r * p.out_ld + c + j, v[j], p.range_flag);
       } else if (c + 3 < p.n && (p.out_ld & 3) == 0) {
         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
@@ -236,7 +224,8 @@ void LaunchGemm(const GemmParams &p, cudaStream_t stream) {
   bool vec = (p.ktot % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
   for (int s = 0; s < p.n_slabs; s++) {
     const GemmSlab &sl = p.slabs[s];
-    if (sl.k % 4 || sl.ld % 4 || sl.wcol % 4 || (reinterpret_cast<uintptr_t>(sl.src) & 15)) vec = false;
+    if (!sl.src_lo && (sl.k % 4 || sl.ld % 4 || sl.wcol % 4 || (reinterpret_cast<uintptr_t>(sl.src) & 15))) vec = false;
+    if (sl.src_lo && (sl.wcol % 4)) vec = false;
   }
   dim3 grid((p.n + BN - 1) / BN, (p.m + BM - 1) / BM);
   if (vec)
@@ -259,15 +248,13 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const __grid_constant_
   for (int s = 0; s < p.n_slabs; s++) {
     const GemmSlab &sl = p.slabs[s];
     const size_t idx = (size_t)slab_row(sl, r) * sl.ld + sl.wcol + c;
-    float x = sl.src[idx];
-    if (sl.src_lo) x = __fadd_rn(x, sl.src_lo[idx]);
+    const float x = ld_act(sl.src, sl.src_lo, idx);
     float t = sc.s[s] == 1.f ? x : __fmul_rn(sc.s[s], x);
     v = s == 0 ? t : __fadd_rn(v, t);
   }
   v = apply_ops(v, r, c, p);
   const size_t oidx = (size_t)r * p.out_ld + col_offset + c;
-  if (p.out_lo) split_store(p.out + oidx, p.out_lo + oidx, v);
-  else p.out[oidx] = v;
+  st_act(p.out, p.out_lo, oidx, v, p.range_flag);
 }
 
 void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int col_offset, cudaStream_t stream) {
@@ -279,13 +266,11 @@ void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int co
 }
 
 // --------------------------------------------------------------------------- log-softmax (warp/row)
-__global__ void __launch_bounds__(256) logsoftmax_kernel(const float *in, const float *in_lo, int in_ld, float *out, int out_ld,
+__global__ void __launch_bounds__(256) logsoftmax_kernel(const void *in, const void *in_lo, int in_ld, float *out, int out_ld,
                                                          int rows, int n) {
   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float *x = in + (size_t)row * in_ld;
-  const float *xl = in_lo ? in_lo + (size_t)row * in_ld : nullptr;
-  auto at = [&](int c) { return xl ? __fadd_rn(x[c], xl[c]) : x[c]; };
+  auto at = [&](int c) { return ld_act(in, in_lo, (size_t)row * in_ld + c); };
   float mx = -3.4e38f;
   for (int c = lane; c < n; c += 32) mx = fmaxf(mx, at(c));
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -296,7 +281,7 @@ __global__ void __launch_bounds__(256) logsoftmax_kernel(const float *in, const 
   for (int c = lane; c < n; c += 32) out[(size_t)row * out_ld + c] = at(c) - lse;
 }
 
-void LaunchLogSoftmax(const float *in, const float *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
+void LaunchLogSoftmax(const void *in, const void *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
                       cudaStream_t stream) {
   if (rows <= 0) return;
   logsoftmax_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(in, in_lo, in_ld, out, out_ld, rows, n);
@@ -318,8 +303,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
     if (row < 0 || row >= p.axis_len) continue;
     int tc = t < 0 ? 0 : (t >= T ? T - 1 : t);
     const float x = p.feats[((size_t)p.frame_offset[u] + tc) * p.dim + d];
-    if (p.dst_lo) split_store(p.dst + (size_t)row * p.ld + d, p.dst_lo + (size_t)row * p.ld + d, x);
-    else p.dst[(size_t)row * p.ld + d] = x;
+    st_act(p.dst, p.dst_lo, (size_t)row * p.ld + d, x, p.range_flag);
   }
 }
 

@@ -6,20 +6,27 @@
 //   warp 0      TMA producer : cp.async.bulk.tensor tiles of the activations (one tensor map per
 //                              time-offset slab: the TDNN splice is a row-shifted / row-strided view
 //                              of the producing layer's buffer, never materialised) and of the weights
-//   warp 1      MMA issuer   : tcgen05.mma.kind::tf32, accumulators in TMEM (two buffers, so the
-//                              epilogue of tile i overlaps the main loop of tile i+1)
-//   warps 2..5  epilogue     : tcgen05.ld -> bias / ReLU / BatchNorm scale+offset / bypass add in
-//                              the reference's order -> split store
+//   warp 1      MMA issuer   : tcgen05.mma.kind::f16, per-K-block partial sums in TMEM
+//   warps 2..9  epilogue     : tcgen05.ld of every K-block partial sum -> fp32 running sums in
+//                              registers -> bias / ReLU / BatchNorm scale+offset / bypass add in the
+//                              reference's order -> split store
 //
-// Numerics.  The reference computes in fp32; the tolerance on the log-likelihoods is 1e-4.  A plain
-// TF32 product (10-bit mantissa) is ~1e-3, so every operand is carried as two TF32 planes
-//   x = hi + lo,  hi = rna_tf32(x),  lo = x - hi   (exact in fp32; the tensor core drops lo's low bits)
-// and a product is three MMAs into the same fp32 TMEM accumulator: hi*hi + hi*lo + lo*hi.  The
-// dropped terms are O(2^-21) relative per product and unbiased.  Activations are stored by the
-// producing epilogue already split (the two planes ARE the buffer: hi + lo reproduces the fp32
-// value bit for bit), weights are split once at model load.
+// Numerics.  The reference computes in fp32; the tolerance on the log-likelihoods is 1e-4.  One
+// fp16 (or TF32) product carries an 11-bit significand, ~1e-3.  So every operand is carried as two
+// fp16 planes (split.cuh)
+//   x ~ hi + lo / 2048,   hi = fp16(x),   lo = fp16((x - hi) * 2048)          (22+ significant bits)
+// and a product is three MMAs:  hi*hi  into a "main" accumulator and  hi*lo + lo*hi  into a "cross"
+// accumulator that is folded with the exact factor 2^-11.  The dropped lo*lo term and the rounding
+// of lo are O(2^-22) relative per product and unbiased.  The scaling keeps lo in fp16's normal range
+// whatever the magnitude of x (an unscaled remainder of a weight of 0.03 would be subnormal).
+// fp16 rather than TF32 planes: the kernel is bound by the bytes each SM can pull from L2 per MMA
+// (measured with the TF32 variant: 35 B/clk/SM, tensor pipe 30 % busy), and fp16 halves the bytes
+// per product and doubles the MMA rate.  Activations are stored by the producing epilogue already
+// split, weights are split once at model load; values beyond +-65504 saturate and raise a flag
+// that fails the call (the fp32 CUDA-core path, RS_B200_GEMM=simt, has no such limit).
 #include <cuda.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -27,6 +34,7 @@
 #include "engine.h"
 #include "model.h"
 #include "nnet_tc.h"
+#include "split.cuh"
 
 namespace rs {
 
@@ -78,16 +86,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -98,10 +106,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor of a K-major operand tile [rows x 32 floats] written by TMA with
+// Shared-memory matrix descriptor of a K-major operand tile [rows x 64 halves] written by TMA with
 // the 128-byte swizzle: 8-row groups are 1024 B apart (SBO), one swizzle atom along K (LBO unused).
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   uint64_t d = 0;
@@ -112,25 +119,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return d;
 }
 
-// x = hi + lo with hi on the TF32 grid (round to nearest, ties away) and lo the exact remainder
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  lo = __fsub_rn(x, hi);
-}
-
 // ------------------------------------------------------------------------------------ the kernel
-// Accumulation.  The tensor core adds each MMA (8 products per output) into the fp32 TMEM
-// accumulator with truncation, not round-to-nearest (measured: the error of a K = 2048 dot product
-// accumulated entirely in TMEM grows linearly with K and is biased towards zero, ~1e-5 relative).
-// So TMEM only ever holds the partial sum of ONE 32-wide K block: per block the issuer starts a
-// fresh accumulator, adds the eight small cross terms first (while the accumulator is ~2^-11 of its
-// final size their truncation is negligible) and the four hi*hi terms last, and hands the block to
-// the epilogue warps, which add it into fp32 registers with round-to-nearest -- the same blocked
-// summation a CPU sgemm micro-kernel performs.  Four TMEM sets of bn columns form the ring between
-// the MMA warp and the two epilogue groups; the groups alternate tiles, so the bias / ReLU /
-// BatchNorm / bypass / split-store tail of tile i overlaps the main loop of tile i+1.
+// Accumulation.  The tensor core adds each MMA into the fp32 TMEM accumulator with truncation, not
+// round-to-nearest (measured with whole-K accumulation in TMEM: the error of a K = 2048 dot product
+// grows linearly with K and is biased towards zero, ~1e-5 relative, which breaks the 1e-4 gate after
+// 30 layers).  So TMEM only ever holds the partial sums of ONE 64-wide K block: per block the issuer
+// starts a fresh main and a fresh cross accumulator (4 + 8 MMAs) and hands the pair to the epilogue
+// warps, which fold  main + cross * 2^-11  into fp32 registers with round-to-nearest -- the blocked
+// summation a CPU sgemm micro-kernel performs.  Two accumulator pairs (4 x bn TMEM columns) form the
+// ring between the MMA warp and the epilogue warps, so the issuer runs up to two K blocks ahead,
+// also across the tile boundary while the epilogue warps run the bias / ReLU / BatchNorm / bypass /
+// split-store tail of the previous tile.
 constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
 
 // 10 warps = up to 3 per SM sub-partition (16 K registers each): at most 168 registers per thread
@@ -217,33 +216,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      // instruction descriptor: D fp32, A/B fp16, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
       int stage = 0;
-      uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; TMEM set = kbc & 3
+      uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; accumulator pair = kbc & 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < total_kb; kb++, kbc++) {
-          const int set = kbc & 3;
-          mbar_wait(sete_bar(set), ((kbc >> 2) & 1u) ^ 1u);
+          const int set = kbc & 1;
+          mbar_wait(sete_bar(set), ((kbc >> 1) & 1u) ^ 1u);
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(set * p.bn);
+          const uint32_t d_main = tmem_base + (uint32_t)(set * 2 * p.bn), d_cross = d_main + (uint32_t)p.bn;
           const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
           const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kStageABytes);
           const uint64_t b_hi = smem_desc_sw128(sa + 2 * kStageABytes), b_lo = smem_desc_sw128(sa + 2 * kStageABytes + b_bytes);
 #pragma unroll
-          for (int k = 0; k < kTcBK / 8; k++) {  // cross terms first: 8 tf32 = 32 bytes per step inside the swizzle atom
+          for (int k = 0; k < kTcBK / 16; k++) {  // 16 fp16 = 32 bytes per step inside the swizzle atom
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-          }
-#pragma unroll
-          for (int k = 0; k < kTcBK / 8; k++) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
+            tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
+            tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
-          tc_commit(setf_bar(set));     // partial sum of this K block complete
+          tc_commit(setf_bar(set));     // partial sums of this K block complete
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -259,24 +254,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int q = warp & 3, h = (warp - 2) >> 2;
     // this warp's 32 x 32 fp32 staging tile (float4 columns XOR-swizzled by row: conflict-free both ways)
     float4 *stg = reinterpret_cast<float4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 2) * 4096u);
-    uint32_t kbc = 0;  // K blocks consumed so far: TMEM set = kbc & 3, parity = (kbc >> 2) & 1
+    uint32_t kbc = 0;  // K blocks consumed so far: accumulator pair = kbc & 1, parity = (kbc >> 1) & 1
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
       float acc[kTcMaxBN / 2];
 #pragma unroll
       for (int j = 0; j < kTcMaxBN / 2; j++) acc[j] = 0.f;
       for (int kb = 0; kb < total_kb; kb++, kbc++) {
-        const int set = kbc & 3;
-        mbar_wait(setf_bar(set), (kbc >> 2) & 1u);
+        const int set = kbc & 1;
+        mbar_wait(setf_bar(set), (kbc >> 1) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn + h * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 2 * p.bn + h * 64);
 #pragma unroll
         for (int jc = 0; jc < 2; jc++)
           if (h * 64 + jc * 32 < p.bn) {
-            uint32_t raw[32];
-            tmem_ld32(taddr + jc * 32, raw);
+            uint32_t mraw[32], craw[32];
+            tmem_ld32_nowait(taddr + jc * 32, mraw);
+            tmem_ld32_nowait(taddr + p.bn + jc * 32, craw);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 32; j++) acc[jc * 32 + j] = __fadd_rn(acc[jc * 32 + j], __uint_as_float(raw[j]));
+            for (int j = 0; j < 32; j++)
+              acc[jc * 32 + j] = __fadd_rn(acc[jc * 32 + j], fmaf(__uint_as_float(craw[j]), 1.f / kSplitScale, __uint_as_float(mraw[j])));
           }
         tc_fence_before();
         __syncwarp();
@@ -330,8 +328,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               // segment, 4 rows per instruction), summed hi + lo, transposed through the warp's
               // staging tile so that each thread gets the 32 values of its own row
               __syncwarp();
-              {
-                float4 bh[8], bl[8];  // all 16 loads in flight before the first use
+              if (op.buf_lo) {
+                // split source: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B cover a row
+                // segment, 8 rows per instruction, all 8 loads in flight before the first use
+                uint4 bh[4], bl[4];
+                const int c8 = lane & 3;
+                const bool col_ok = c0 + c8 * 8 < p.n;
+#pragma unroll
+                for (int it = 0; it < 4; it++) {
+                  int ri = m0 + q * 32 + it * 8 + (lane >> 2);
+                  if (ri >= p.m) ri = p.m - 1;
+                  long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
+                  if (orow >= op.buf_rows) orow = op.buf_rows - 1;
+                  const size_t off = (size_t)orow * op.buf_ld + c0 + c8 * 8;
+                  bh[it] = make_uint4(0u, 0u, 0u, 0u);
+                  bl[it] = make_uint4(0u, 0u, 0u, 0u);
+                  if (col_ok) {
+                    bh[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf) + off));
+                    bl[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf_lo) + off));
+                  }
+                }
+#pragma unroll
+                for (int it = 0; it < 4; it++) {
+                  const int i = it * 8 + (lane >> 2);
+                  const __half2 *hh = reinterpret_cast<const __half2 *>(&bh[it]), *ll = reinterpret_cast<const __half2 *>(&bl[it]);
+                  float x[8];
+#pragma unroll
+                  for (int e = 0; e < 4; e++) {
+                    const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+                    x[2 * e] = fmaf(fl.x, 1.f / kSplitScale, fh.x);  // exact: hi + lo / 2048
+                    x[2 * e + 1] = fmaf(fl.y, 1.f / kSplitScale, fh.y);
+                  }
+                  stg[i * 8 + ((2 * c8) ^ (i & 7))] = make_float4(x[0], x[1], x[2], x[3]);
+                  stg[i * 8 + ((2 * c8 + 1) ^ (i & 7))] = make_float4(x[4], x[5], x[6], x[7]);
+                }
+              } else {
+                // plain fp32 source: 8 lanes x 16 B cover a 128-byte row segment, 4 rows per instruction
+                float4 bf[8];
                 const int c4 = lane & 7;
                 const bool col_ok = c0 + c4 * 4 < p.n;
 #pragma unroll
@@ -340,23 +373,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                   if (ri >= p.m) ri = p.m - 1;
                   long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
                   if (orow >= op.buf_rows) orow = op.buf_rows - 1;
-                  const size_t off = (size_t)orow * op.buf_ld + c0 + c4 * 4;
-                  bh[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  bl[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (col_ok) {
-                    bh[it] = __ldcs(reinterpret_cast<const float4 *>(op.buf + off));
-                    if (op.buf_lo) bl[it] = __ldcs(reinterpret_cast<const float4 *>(op.buf_lo + off));
-                  }
+                  bf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (col_ok)
+                    bf[it] = __ldcs(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(op.buf) + (size_t)orow * op.buf_ld + c0 + c4 * 4));
                 }
 #pragma unroll
                 for (int it = 0; it < 8; it++) {
                   const int i = it * 4 + (lane >> 3);
-                  float4 o = bh[it];
-                  o.x = __fadd_rn(o.x, bl[it].x);
-                  o.y = __fadd_rn(o.y, bl[it].y);
-                  o.z = __fadd_rn(o.z, bl[it].z);
-                  o.w = __fadd_rn(o.w, bl[it].w);
-                  stg[i * 8 + (c4 ^ (i & 7))] = o;
+                  stg[i * 8 + (c4 ^ (i & 7))] = bf[it];
                 }
               }
               __syncwarp();
@@ -378,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
             case EpiOp::kUttBias: {
               const int u = p.row_utt[(size_t)rr * op.num];
-              const float *b = op.buf + (size_t)u * op.buf_ld + c0;
+              const float *b = reinterpret_cast<const float *>(op.buf) + (size_t)u * op.buf_ld + c0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 if (c0 + j < p.n) {
@@ -392,32 +416,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
           }
         }
-        // store through the staging tile: every instruction writes 4 rows x 128 contiguous bytes
-        for (int pl = 0; pl < (p.out_lo ? 2 : 1); pl++) {
-          float *dst = pl == 0 ? p.out_hi : p.out_lo;
-          __syncwarp();
+        // store through the staging tile so that every instruction writes whole row segments
+        __syncwarp();
+        if (p.out_lo) {
+          // two fp16 planes: hi tile in the first 2 KB of the staging tile, lo tile in the second;
+          // 16-byte chunks XOR-swizzled by row pair (conflict-free for both access patterns)
+          uint4 *st16 = reinterpret_cast<uint4 *>(stg);
+          bool sat = false;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.out_lo) {  // plane 0: hi = rna_tf32(x); plane 1: lo = x - hi
-              float4 h, l;
-              split_tf32(o.x, h.x, l.x);
-              split_tf32(o.y, h.y, l.y);
-              split_tf32(o.z, h.z, l.z);
-              split_tf32(o.w, h.w, l.w);
-              o = pl == 0 ? h : l;
+          for (int c = 0; c < 4; c++) {
+            __half2 hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              __half h0, l0, h1, l1;
+              sat |= split_f16(v[8 * c + 2 * e], h0, l0);
+              sat |= split_f16(v[8 * c + 2 * e + 1], h1, l1);
+              hh[e] = __halves2half2(h0, h1);
+              ll[e] = __halves2half2(l0, l1);
             }
-            stg[lane * 8 + ((j >> 2) ^ (lane & 7))] = o;
+            const int slot = lane * 4 + (c ^ ((lane >> 1) & 3));
+            st16[slot] = *reinterpret_cast<const uint4 *>(hh);
+            st16[128 + slot] = *reinterpret_cast<const uint4 *>(ll);
           }
+          if (sat && r < p.m) *p.range_flag = 1;
+          __syncwarp();
+          const int c8 = lane & 3;
+#pragma unroll
+          for (int it = 0; it < 4; it++) {
+            const int i = it * 8 + (lane >> 2);
+            const int ri = m0 + q * 32 + i;
+            if (ri < p.m && c0 + c8 * 8 < p.n) {
+              const int slot = i * 4 + (c8 ^ ((i >> 1) & 3));
+              const size_t off = (size_t)ri * p.out_ld + c0 + c8 * 8;
+              *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out_hi) + off) = st16[slot];
+              *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.out_lo) + off) = st16[128 + slot];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) stg[lane * 8 + ((j >> 2) ^ (lane & 7))] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 8; it++) {
             const int i = it * 4 + (lane >> 3), c4 = lane & 7;
             const int ri = m0 + q * 32 + i;
             if (ri < p.m && c0 + c4 * 4 < p.n)
-              *reinterpret_cast<float4 *>(dst + (size_t)ri * p.out_ld + c0 + c4 * 4) = stg[i * 8 + (c4 ^ (i & 7))];
+              *reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out_hi) + (size_t)ri * p.out_ld + c0 + c4 * 4) = stg[i * 8 + (c4 ^ (i & 7))];
           }
         }
+        __syncwarp();
       }
     }
   }
@@ -452,29 +499,31 @@ EncodeTiledFn GetEncodeTiled() {
 
 }  // namespace
 
-// 2-D fp32 tensor [rows x cols], row pitch `pitch_floats`, box = 32 columns x box_rows, 128-byte
+// 2-D fp16 tensor [rows x cols], row pitch `pitch_elems`, box = 64 columns x box_rows, 128-byte
 // swizzle, out-of-bounds elements read as zero.
-void TcEncodeMap(CUtensorMap *map, const float *base, long long rows, int cols, long long pitch_floats, int box_rows) {
+void TcEncodeMap(CUtensorMap *map, const __half *base, long long rows, int cols, long long pitch_elems, int box_rows) {
   if (rows < 1) rows = 1;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_floats * 4) % 16) RS_FAIL("tensor map operand is not 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_elems * 2) % 16) RS_FAIL("tensor map operand is not 16-byte aligned");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch_floats * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
   cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult rc = GetEncodeTiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+  CUresult rc = GetEncodeTiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(base), dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS)
-    RS_FAIL("cuTensorMapEncodeTiled failed (" << (int)rc << ") rows " << rows << " cols " << cols << " pitch " << pitch_floats);
+    RS_FAIL("cuTensorMapEncodeTiled failed (" << (int)rc << ") rows " << rows << " cols " << cols << " pitch " << pitch_elems);
 }
 
-void TcSplitHost(float x, float *hi, float *lo) {
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  uint32_t h = (u + 0x1000u) & 0xffffe000u;  // round to nearest, ties away (cvt.rna.tf32.f32)
-  if ((u & 0x7f800000u) == 0x7f800000u) h = u;  // inf / nan unchanged
-  memcpy(hi, &h, 4);
-  *lo = x - *hi;
+bool TcSplitHost(float x, __half *hi, __half *lo) {
+  bool ok = true;
+  if (std::fabs(x) > 65504.f) {
+    x = std::copysign(65504.f, x);
+    ok = false;
+  }
+  *hi = __float2half_rn(x);
+  *lo = __float2half_rn((x - __half2float(*hi)) * kSplitScale);
+  return ok;
 }
 
 int TcTileN(int n) {
@@ -483,8 +532,8 @@ int TcTileN(int n) {
   return (per + 31) / 32 * 32;
 }
 
-void TcPackWeights(const float *w, int n, int ktot, const std::vector<std::pair<int, int>> &slabs, std::vector<float> *hi,
-                   std::vector<float> *lo, std::vector<int> *k0, int *kp) {
+void TcPackWeights(const float *w, int n, int ktot, const std::vector<std::pair<int, int>> &slabs, std::vector<__half> *hi,
+                   std::vector<__half> *lo, std::vector<int> *k0, int *kp) {
   int total = 0;
   k0->clear();
   for (const auto &s : slabs) {
@@ -492,14 +541,15 @@ void TcPackWeights(const float *w, int n, int ktot, const std::vector<std::pair<
     total += (s.second + kTcBK - 1) / kTcBK * kTcBK;
   }
   *kp = total;
-  hi->assign((size_t)n * total, 0.f);
-  lo->assign((size_t)n * total, 0.f);
+  hi->assign((size_t)n * total, __float2half_rn(0.f));
+  lo->assign((size_t)n * total, __float2half_rn(0.f));
   for (size_t si = 0; si < slabs.size(); si++) {
     const int wcol = slabs[si].first, k = slabs[si].second;
     if (wcol + k > ktot) RS_FAIL("weight slab out of range");
     for (int r = 0; r < n; r++)
       for (int c = 0; c < k; c++)
-        TcSplitHost(w[(size_t)r * ktot + wcol + c], &(*hi)[(size_t)r * total + (*k0)[si] + c], &(*lo)[(size_t)r * total + (*k0)[si] + c]);
+        if (!TcSplitHost(w[(size_t)r * ktot + wcol + c], &(*hi)[(size_t)r * total + (*k0)[si] + c], &(*lo)[(size_t)r * total + (*k0)[si] + c]))
+          RS_FAIL("a weight exceeds the fp16 range of the tensor-core path (set RS_B200_GEMM=simt)");
   }
 }
 

@@ -1,6 +1,7 @@
 // Parameter block and host helpers of the tcgen05 / TMA affine-layer kernel (nnet_tc.cu).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <utility>
@@ -11,14 +12,15 @@
 namespace rs {
 
 constexpr int kTcBM = 128;      // output rows (time steps) per tile = UMMA M
-constexpr int kTcBK = 32;       // fp32 columns per pipeline stage = one 128-byte swizzle atom
-constexpr int kTcThreads = 320; // TMA warp, MMA warp, 2 epilogue groups of 4 warps
+constexpr int kTcBK = 64;       // fp16 columns per pipeline stage = one 128-byte swizzle atom
+constexpr int kTcThreads = 320; // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kTcMaxBN = 128;   // output columns per tile (fp32 running sums live in registers)
 constexpr int kTcMaxSlabs = 4;
+constexpr float kSplitScale = 2048.f;  // lo plane = (x - hi) * 2^11, see nnet_tc.cu
 
 struct TcSlab {
-  int kblocks;  // ceil(k / 32)
-  int wk0;      // first column of this slab in the packed weight matrix (multiple of 32)
+  int kblocks;  // ceil(k / 64)
+  int wk0;      // first column of this slab in the packed weight matrix (multiple of 64)
   int yshift;   // row of the slab's (shifted, strided) source view that output row 0 reads
 };
 
@@ -29,23 +31,25 @@ struct TcParams {
   int n_slabs;
   int bn;         // output columns per tile = UMMA N (multiple of 32, <= kTcMaxBN)
   int stages;     // smem pipeline depth
-  int tmem_cols;  // power of two >= 4 * bn (ring of four K-block accumulators)
+  int tmem_cols;  // power of two >= 4 * bn (two K-block accumulator pairs)
   int tiles_m, tiles_n;
-  float *out_hi, *out_lo;  // out_lo == nullptr: plain fp32 output
+  void *out_hi, *out_lo;  // out_lo == nullptr: plain fp32 output at out_hi, else two fp16 planes
   int out_ld, m, n;
   DevOp ops[kMaxOps];
   int n_ops;
   const int *row_utt;
+  int *range_flag;  // set to 1 if a split store had to saturate (|x| > 65504)
 };
 
-// tensor map over a row-major fp32 matrix (box 32 columns x box_rows, SWIZZLE_128B, zero fill)
-void TcEncodeMap(CUtensorMap *map, const float *base, long long rows, int cols, long long pitch_floats, int box_rows);
-void TcSplitHost(float x, float *hi, float *lo);
+// tensor map over a row-major fp16 matrix (box 64 columns x box_rows, SWIZZLE_128B, zero fill)
+void TcEncodeMap(CUtensorMap *map, const __half *base, long long rows, int cols, long long pitch_elems, int box_rows);
+// x ~ hi + lo / 2048 with hi = fp16(x), lo = fp16((x - hi) * 2048); returns false if |x| is out of fp16 range
+bool TcSplitHost(float x, __half *hi, __half *lo);
 int TcTileN(int n);
-// Re-lays W [n x ktot] as [n x kp] with every slab's columns padded to a multiple of 32 (so a
-// K block never straddles two slabs) and splits it into the two TF32 planes.
+// Re-lays W [n x ktot] as [n x kp] with every slab's columns padded to a multiple of 64 (so a
+// K block never straddles two slabs) and splits it into the two fp16 planes.
 void TcPackWeights(const float *w, int n, int ktot, const std::vector<std::pair<int, int>> &slabs /* (wcol, k) */,
-                   std::vector<float> *hi, std::vector<float> *lo, std::vector<int> *k0, int *kp);
+                   std::vector<__half> *hi, std::vector<__half> *lo, std::vector<int> *k0, int *kp);
 void TcConfigure(TcParams *p);  // fills stages / tmem_cols / tiles_* from bn, m, n
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream);
 
