@@ -21,18 +21,32 @@
 // and therefore the surviving token sets are bit-identical wherever the reference itself is
 // order-independent ("decoder semantics").
 #include <cfloat>
+#include <cstdlib>
 
 #include "engine.h"
 
 namespace rs {
 
-constexpr int NT = 512;
-constexpr int NW = NT / 32;
+// CTA size is a launch-time choice (128 .. 512 threads): the frontier of a grammar graph is a few
+// hundred tokens, where a small CTA pays far less per __syncthreads than a large one
+constexpr int kMaxNT = 512;
+constexpr int kMaxNW = kMaxNT / 32;
+#define NT ((int)blockDim.x)
+#define NW ((int)(blockDim.x >> 5))
 constexpr unsigned long long kEmptyVal = ~0ULL;
 constexpr int kEmptyKey = -1;
 constexpr unsigned kArcNone = 0xffffffffu;
 
-int DecodeCtaThreads() { return NT; }
+static int g_decode_threads = 0;
+int DecodeCtaThreads() {
+  if (g_decode_threads == 0) {
+    const char *e = getenv("RS_B200_DECODE_THREADS");
+    int v = e ? atoi(e) : 512;
+    if (v != 128 && v != 256 && v != 512) v = 512;
+    g_decode_threads = v;
+  }
+  return g_decode_threads;
+}
 
 __device__ __forceinline__ unsigned ord(float f) {
   unsigned b = __float_as_uint(f);
@@ -48,9 +62,9 @@ __device__ __forceinline__ unsigned long long pack(float cost, unsigned arc) {
 __device__ __forceinline__ unsigned hash_state(int s) { return (unsigned)s * 2654435761u; }
 
 struct Shared {
-  unsigned warp_sums[NW + 1];
-  float red_v[NW];
-  int red_i[NW];
+  unsigned warp_sums[kMaxNW + 1];
+  float red_v[kMaxNW];
+  int red_i[kMaxNW];
   unsigned hist[256];
   unsigned sel_prefix, sel_mask;
   int sel_k;
@@ -196,7 +210,7 @@ __device__ __forceinline__ int insert_slot(const Table &t, int state, unsigned m
   }
 }
 
-__global__ void __launch_bounds__(NT, 2) decode_kernel(const __grid_constant__ DecodeParams P) {
+__global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant__ DecodeParams P) {
   __shared__ Shared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const LaneWorkspace ws = P.lanes[blockIdx.x];
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(NT, 2) decode_kernel(const __grid_constant__ D
       unsigned long long v = cnt_arcs;
 #pragma unroll
       for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      __shared__ unsigned long long red[NW];
+      __shared__ unsigned long long red[kMaxNW];
       if (lane == 0) red[warp] = v;
       __syncthreads();
       if (tid == 0) {
@@ -626,7 +640,7 @@ __global__ void __launch_bounds__(NT, 2) decode_kernel(const __grid_constant__ D
 
 void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream) {
   if (p.n_utts == 0) return;
-  decode_kernel<<<n_lanes, NT, 0, stream>>>(p);
+  decode_kernel<<<n_lanes, DecodeCtaThreads(), 0, stream>>>(p);
 }
 
 }  // namespace rs
