@@ -119,17 +119,37 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return d;
 }
 
+// two fp32 additions in one instruction (FADD2, sm_100): {a0 + b0, a1 + b1}, each rounded to nearest
+__device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1) {
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+// split two values into the packed hi / lo fp16 pairs of the plane format (split.cuh); conversions
+// saturate at +-65504, `amax` collects max |x| so that the caller can flag a saturation
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo, float &amax) {
+  amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+  // (x - hi) * 2048, exact: both products are exact and their difference is representable
+  const float r0 = fmaf(f.x, -kSplitScale, __fmul_rn(x0, kSplitScale)), r1 = fmaf(f.y, -kSplitScale, __fmul_rn(x1, kSplitScale));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
 // ------------------------------------------------------------------------------------ the kernel
 // Accumulation.  The tensor core adds each MMA into the fp32 TMEM accumulator with truncation, not
 // round-to-nearest (measured with whole-K accumulation in TMEM: the error of a K = 2048 dot product
 // grows linearly with K and is biased towards zero, ~1e-5 relative, which breaks the 1e-4 gate after
 // 30 layers).  So TMEM only ever holds the partial sums of ONE 64-wide K block: per block the issuer
-// starts a fresh main and a fresh cross accumulator (4 + 8 MMAs) and hands the pair to the epilogue
-// warps, which fold  main + cross * 2^-11  into fp32 registers with round-to-nearest -- the blocked
-// summation a CPU sgemm micro-kernel performs.  Two accumulator pairs (4 x bn TMEM columns) form the
-// ring between the MMA warp and the epilogue warps, so the issuer runs up to two K blocks ahead,
-// also across the tile boundary while the epilogue warps run the bias / ReLU / BatchNorm / bypass /
-// split-store tail of the previous tile.
+// starts a fresh main accumulator (4 MMAs) and hands it to the epilogue warps, which add it into
+// fp32 registers with round-to-nearest -- the blocked summation a CPU sgemm micro-kernel performs.
+// The cross terms (8 MMAs per block) are 2^-11 of the result, so their accumulator stays in TMEM
+// for the whole tile and is folded once (its truncation error is 2^-11 * 1e-5: nothing).  TMEM holds
+// a ring of two main accumulators and two cross accumulators (4 x bn columns), so the issuer runs
+// up to two K blocks ahead, also across the tile boundary while the epilogue warps run the bias /
+// ReLU / BatchNorm / bypass / split-store tail of the previous tile.
 constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
 
 // 10 warps = up to 3 per SM sub-partition (16 K registers each): at most 168 registers per thread
@@ -146,6 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
   auto setf_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + a); };
   auto sete_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 4 + a); };
+  auto crosse_bar = [&](int a) { return sete_bar(2 + a); };  // cross accumulator a (tile parity) drained
   const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,13 +241,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; accumulator pair = kbc & 1
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t tcount = 0;  // tiles issued so far: cross accumulator = tcount & 1
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+        const uint32_t d_cross = tmem_base + (uint32_t)((2 + (tcount & 1)) * p.bn);
+        mbar_wait(crosse_bar(tcount & 1), ((tcount >> 1) & 1u) ^ 1u);
         for (int kb = 0; kb < total_kb; kb++, kbc++) {
           const int set = kbc & 1;
           mbar_wait(sete_bar(set), ((kbc >> 1) & 1u) ^ 1u);
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t d_main = tmem_base + (uint32_t)(set * 2 * p.bn), d_cross = d_main + (uint32_t)p.bn;
+          const uint32_t d_main = tmem_base + (uint32_t)(set * p.bn);
           const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
           const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kStageABytes);
           const uint64_t b_hi = smem_desc_sw128(sa + 2 * kStageABytes), b_lo = smem_desc_sw128(sa + 2 * kStageABytes + b_bytes);
@@ -234,11 +258,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           for (int k = 0; k < kTcBK / 16; k++) {  // 16 fp16 = 32 bytes per step inside the swizzle atom
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
             tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
-            tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
+            tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
             tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
-          tc_commit(setf_bar(set));     // partial sums of this K block complete
+          tc_commit(setf_bar(set));     // this block's main sum (and, on the last block, the cross sum) complete
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -254,31 +278,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int q = warp & 3, h = (warp - 2) >> 2;
     // this warp's 32 x 32 fp32 staging tile (float4 columns XOR-swizzled by row: conflict-free both ways)
     float4 *stg = reinterpret_cast<float4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 2) * 4096u);
-    uint32_t kbc = 0;  // K blocks consumed so far: accumulator pair = kbc & 1, parity = (kbc >> 1) & 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    uint32_t kbc = 0, tcount = 0;  // K blocks / tiles consumed so far (ring positions and parities)
+    int ib = -1;  // the op whose split bypass input is prefetched (first kAddScaled with a split source)
+    for (int i = 0; i < p.n_ops && ib < 0; i++)
+      if (p.ops[i].type == EpiOp::kAddScaled && p.ops[i].buf_lo) ib = i;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
       const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
+      // bypass input of one 32-column chunk: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B
+      // cover a row segment, 8 rows per instruction; issued early so that HBM latency is hidden
+      uint4 pf_h[4], pf_l[4];
+      auto prefetch = [&](int jc) {
+        const DevOp &op = p.ops[ib];
+        const int c0 = n0 + h * 64 + jc * 32, c8 = lane & 3;
+        const bool ok = h * 64 + jc * 32 < p.bn && c0 + c8 * 8 < p.n;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          int ri = m0 + q * 32 + it * 8 + (lane >> 2);
+          if (ri >= p.m) ri = p.m - 1;
+          long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
+          if (orow >= op.buf_rows) orow = op.buf_rows - 1;
+          const size_t off = (size_t)orow * op.buf_ld + c0 + c8 * 8;
+          pf_h[it] = make_uint4(0u, 0u, 0u, 0u);
+          pf_l[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) {
+            pf_h[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf) + off));
+            pf_l[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf_lo) + off));
+          }
+        }
+      };
       float acc[kTcMaxBN / 2];
 #pragma unroll
       for (int j = 0; j < kTcMaxBN / 2; j++) acc[j] = 0.f;
       for (int kb = 0; kb < total_kb; kb++, kbc++) {
+        if (kb == total_kb - 1 && ib >= 0) prefetch(0);
         const int set = kbc & 1;
         mbar_wait(setf_bar(set), (kbc >> 1) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 2 * p.bn + h * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn + h * 64);
 #pragma unroll
         for (int jc = 0; jc < 2; jc++)
           if (h * 64 + jc * 32 < p.bn) {
-            uint32_t mraw[32], craw[32];
-            tmem_ld32_nowait(taddr + jc * 32, mraw);
-            tmem_ld32_nowait(taddr + p.bn + jc * 32, craw);
+            uint32_t raw[32];
+            tmem_ld32_nowait(taddr + jc * 32, raw);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              acc[jc * 32 + j] = __fadd_rn(acc[jc * 32 + j], fmaf(__uint_as_float(craw[j]), 1.f / kSplitScale, __uint_as_float(mraw[j])));
+            for (int j = 0; j < 32; j += 2)
+              add2(acc[jc * 32 + j], acc[jc * 32 + j + 1], __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
           }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sete_bar(set));
+      }
+      {  // the tile's cross sum: acc += cross * 2^-11 (the last block's commit covers it)
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + (tcount & 1)) * p.bn + h * 64);
+#pragma unroll
+        for (int jc = 0; jc < 2; jc++)
+          if (h * 64 + jc * 32 < p.bn) {
+            uint32_t raw[32];
+            tmem_ld32_nowait(taddr + jc * 32, raw);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[jc * 32 + j] = fmaf(__uint_as_float(raw[j]), 1.f / kSplitScale, acc[jc * 32 + j]);
+          }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(crosse_bar(tcount & 1));
       }
       const int r = m0 + q * 32 + lane;
       const int rr = r < p.m ? r : p.m - 1;
@@ -329,29 +393,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               // staging tile so that each thread gets the 32 values of its own row
               __syncwarp();
               if (op.buf_lo) {
-                // split source: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B cover a row
-                // segment, 8 rows per instruction, all 8 loads in flight before the first use
-                uint4 bh[4], bl[4];
+                // split source: registers filled by prefetch() (or loaded now for a second bypass op)
                 const int c8 = lane & 3;
-                const bool col_ok = c0 + c8 * 8 < p.n;
-#pragma unroll
-                for (int it = 0; it < 4; it++) {
-                  int ri = m0 + q * 32 + it * 8 + (lane >> 2);
-                  if (ri >= p.m) ri = p.m - 1;
-                  long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
-                  if (orow >= op.buf_rows) orow = op.buf_rows - 1;
-                  const size_t off = (size_t)orow * op.buf_ld + c0 + c8 * 8;
-                  bh[it] = make_uint4(0u, 0u, 0u, 0u);
-                  bl[it] = make_uint4(0u, 0u, 0u, 0u);
-                  if (col_ok) {
-                    bh[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf) + off));
-                    bl[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf_lo) + off));
-                  }
+                if (i != ib) {
+                  const int keep = ib;
+                  ib = i;
+                  prefetch(jc);
+                  ib = keep;
                 }
 #pragma unroll
                 for (int it = 0; it < 4; it++) {
-                  const int i = it * 8 + (lane >> 2);
-                  const __half2 *hh = reinterpret_cast<const __half2 *>(&bh[it]), *ll = reinterpret_cast<const __half2 *>(&bl[it]);
+                  const int ii = it * 8 + (lane >> 2);
+                  const __half2 *hh = reinterpret_cast<const __half2 *>(&pf_h[it]), *ll = reinterpret_cast<const __half2 *>(&pf_l[it]);
                   float x[8];
 #pragma unroll
                   for (int e = 0; e < 4; e++) {
@@ -359,9 +412,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     x[2 * e] = fmaf(fl.x, 1.f / kSplitScale, fh.x);  // exact: hi + lo / 2048
                     x[2 * e + 1] = fmaf(fl.y, 1.f / kSplitScale, fh.y);
                   }
-                  stg[i * 8 + ((2 * c8) ^ (i & 7))] = make_float4(x[0], x[1], x[2], x[3]);
-                  stg[i * 8 + ((2 * c8 + 1) ^ (i & 7))] = make_float4(x[4], x[5], x[6], x[7]);
+                  stg[ii * 8 + ((2 * c8) ^ (ii & 7))] = make_float4(x[0], x[1], x[2], x[3]);
+                  stg[ii * 8 + ((2 * c8 + 1) ^ (ii & 7))] = make_float4(x[4], x[5], x[6], x[7]);
                 }
+                if (i == ib && jc == 0) prefetch(1);  // next chunk's bypass while this one is finished
               } else {
                 // plain fp32 source: 8 lanes x 16 B cover a 128-byte row segment, 4 rows per instruction
                 float4 bf[8];
@@ -422,22 +476,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           // two fp16 planes: hi tile in the first 2 KB of the staging tile, lo tile in the second;
           // 16-byte chunks XOR-swizzled by row pair (conflict-free for both access patterns)
           uint4 *st16 = reinterpret_cast<uint4 *>(stg);
-          bool sat = false;
+          float amax = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            __half2 hh[4], ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              __half h0, l0, h1, l1;
-              sat |= split_f16(v[8 * c + 2 * e], h0, l0);
-              sat |= split_f16(v[8 * c + 2 * e + 1], h1, l1);
-              hh[e] = __halves2half2(h0, h1);
-              ll[e] = __halves2half2(l0, l1);
-            }
+            uint4 hh, ll;
+            split2(v[8 * c + 0], v[8 * c + 1], hh.x, ll.x, amax);
+            split2(v[8 * c + 2], v[8 * c + 3], hh.y, ll.y, amax);
+            split2(v[8 * c + 4], v[8 * c + 5], hh.z, ll.z, amax);
+            split2(v[8 * c + 6], v[8 * c + 7], hh.w, ll.w, amax);
             const int slot = lane * 4 + (c ^ ((lane >> 1) & 3));
-            st16[slot] = *reinterpret_cast<const uint4 *>(hh);
-            st16[128 + slot] = *reinterpret_cast<const uint4 *>(ll);
+            st16[slot] = hh;
+            st16[128 + slot] = ll;
           }
+          const bool sat = amax > 65504.f;
           if (sat && r < p.m) *p.range_flag = 1;
           __syncwarp();
           const int c8 = lane & 3;
