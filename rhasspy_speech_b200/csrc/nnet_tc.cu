@@ -153,7 +153,13 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
 constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
 
 // 10 warps = up to 3 per SM sub-partition (16 K registers each): at most 168 registers per thread
+// PAT >= 0: the epilogue op sequence is a compile-time constant (4 bits per op: EpiOp::Type + 1,
+// first op in the low bits, see TcPattern); PAT < 0: run-time op list.
+template <int PAT>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool kStatic = PAT >= 0;
+  constexpr int kT0 = kStatic ? ((PAT >> 0) & 15) - 1 : -1, kT1 = kStatic ? ((PAT >> 4) & 15) - 1 : -1;
+  constexpr int kT2 = kStatic ? ((PAT >> 8) & 15) - 1 : -1, kT3 = kStatic ? ((PAT >> 12) & 15) - 1 : -1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
@@ -306,6 +312,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           }
         }
       };
+      // static op list: lane l keeps column l of each per-column vector (bias, BatchNorm scale /
+      // offset) of both chunks in a register, loaded here so that the latency hides behind the main
+      // loop; the tail broadcasts a column with a shuffle (a warp works on one column set for 32 rows)
+      float vr0[4][2], vr1[4][2];
+      if constexpr (kStatic) {
+        constexpr int types[4] = {kT0, kT1, kT2, kT3};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int jc = 0; jc < 2; jc++) {
+            const int c = n0 + h * 64 + jc * 32 + lane;
+            const bool ok = h * 64 + jc * 32 + lane < p.bn && c < p.n;
+            vr0[i][jc] = vr1[i][jc] = 0.f;
+            if (types[i] == EpiOp::kBias || types[i] == EpiOp::kScaleOffset) vr0[i][jc] = ok ? __ldg(p.ops[i].v0 + c) : 0.f;
+            if (types[i] == EpiOp::kScaleOffset) vr1[i][jc] = ok ? __ldg(p.ops[i].v1 + c) : 0.f;
+          }
+      }
       float acc[kTcMaxBN / 2];
 #pragma unroll
       for (int j = 0; j < kTcMaxBN / 2; j++) acc[j] = 0.f;
@@ -353,10 +376,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = acc[jc * 32 + j];
-        for (int i = 0; i < p.n_ops; i++) {
+        auto apply = [&](const int i, const int type, const float vb0, const float vb1) {
           const DevOp &op = p.ops[i];
-          switch (op.type) {
+          switch (type) {
             case EpiOp::kBias:
+              if constexpr (kStatic) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __fadd_rn(v[j], __shfl_sync(0xffffffffu, vb0, j));
+                break;
+              }
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 if (c0 + j < p.n) {
@@ -372,6 +400,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : 0.f;
               break;
             case EpiOp::kScaleOffset:
+              if constexpr (kStatic) {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                  v[j] = __fadd_rn(__fmul_rn(v[j], __shfl_sync(0xffffffffu, vb0, j)), __shfl_sync(0xffffffffu, vb1, j));
+                break;
+              }
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 if (c0 + j < p.n) {
@@ -469,6 +503,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               break;
             }
           }
+        };
+        if constexpr (kStatic) {
+          if constexpr (kT0 >= 0) apply(0, kT0, vr0[0][jc], vr1[0][jc]);
+          if constexpr (kT1 >= 0) apply(1, kT1, vr0[1][jc], vr1[1][jc]);
+          if constexpr (kT2 >= 0) apply(2, kT2, vr0[2][jc], vr1[2][jc]);
+          if constexpr (kT3 >= 0) apply(3, kT3, vr0[3][jc], vr1[3][jc]);
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < p.n_ops; i++) apply(i, p.ops[i].type, 0.f, 0.f);
         }
         // store through the staging tile so that every instruction writes whole row segments
         __syncwarp();
@@ -625,19 +668,49 @@ void TcConfigure(TcParams *p) {
   p->tiles_n = (p->n + p->bn - 1) / p->bn;
 }
 
+// op sequence -> template pattern (4 bits per op, type + 1); -1 if it has no static instantiation
+static int TcPattern(const TcParams &p) {
+  if (p.n_ops > 4) return -1;
+  int pat = 0;
+  for (int i = 0; i < p.n_ops; i++) pat |= (p.ops[i].type + 1) << (4 * i);
+  return pat;
+}
+constexpr int PatOf(int a = -1, int b = -1, int c = -1, int d = -1) { return (a + 1) | ((b + 1) << 4) | ((c + 1) << 8) | ((d + 1) << 12); }
+constexpr int kPatNone = PatOf();
+constexpr int kPatBias = PatOf(EpiOp::kBias);
+constexpr int kPatBRS = PatOf(EpiOp::kBias, EpiOp::kRelu, EpiOp::kScaleOffset);
+constexpr int kPatBRSA = PatOf(EpiOp::kBias, EpiOp::kRelu, EpiOp::kScaleOffset, EpiOp::kAddScaled);
+constexpr int kPatS = PatOf(EpiOp::kScaleOffset);
+constexpr int kPatU = PatOf(EpiOp::kUttBias);
+
+template <int PAT>
+static void LaunchPattern(const TcParams &p, int grid, int smem, cudaStream_t stream) {
+  static int configured_dev = -1;  // opt-in shared memory size is a per-device function attribute
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tc_smem_limit);
+    if (e != cudaSuccess) RS_FAIL("cudaFuncSetAttribute(gemm_tc_kernel): " << cudaGetErrorString(e));
+    configured_dev = dev;
+  }
+  gemm_tc_kernel<PAT><<<grid, kTcThreads, smem, stream>>>(p);
+}
+
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream) {
   if (p.m <= 0 || p.n <= 0) return;
   const int stage_bytes = 2 * kStageABytes + 2 * p.bn * 128;
   const int smem = 1024 + p.stages * stage_bytes + 8 * 4096 + 8 * (2 * p.stages + 8) + 16;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tc_smem_limit);
-    if (e != cudaSuccess) RS_FAIL("cudaFuncSetAttribute(gemm_tc_kernel): " << cudaGetErrorString(e));
-    configured = g_tc_smem_limit;
-  }
   int grid = p.tiles_m * p.tiles_n;
   if (grid > num_sms) grid = num_sms;
-  gemm_tc_kernel<<<grid, kTcThreads, smem, stream>>>(p);
+  switch (TcPattern(p)) {
+    case kPatNone: LaunchPattern<kPatNone>(p, grid, smem, stream); break;
+    case kPatBias: LaunchPattern<kPatBias>(p, grid, smem, stream); break;
+    case kPatBRS: LaunchPattern<kPatBRS>(p, grid, smem, stream); break;
+    case kPatBRSA: LaunchPattern<kPatBRSA>(p, grid, smem, stream); break;
+    case kPatS: LaunchPattern<kPatS>(p, grid, smem, stream); break;
+    case kPatU: LaunchPattern<kPatU>(p, grid, smem, stream); break;
+    default: LaunchPattern<-1>(p, grid, smem, stream); break;
+  }
 }
 
 }  // namespace rs
