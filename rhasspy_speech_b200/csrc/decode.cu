@@ -171,6 +171,13 @@ __device__ float block_select(const float *a, int n, int k, Shared &S) {
   return unord(S.sel_prefix);
 }
 
+// volatile (uncached) loads of table words that other threads update with atomics; the tables live
+// in global memory or -- for small graphs -- in shared memory, so the address is generic
+__device__ __forceinline__ int ldv(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ unsigned long long ldv(const unsigned long long *p) {
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
 struct Table {
   int *hkey;
   unsigned long long *hval;
@@ -182,7 +189,7 @@ struct Table {
 __device__ __forceinline__ int find_slot(const int *hkey, int state, unsigned mask, bool identity) {
   unsigned s = identity ? (unsigned)state : (hash_state(state) & mask);
   while (true) {
-    int k = __ldcg(hkey + s);
+    int k = ldv(hkey + s);
     if (k == state) return (int)s;
     if (k == kEmptyKey) return -1;
     s = (s + 1) & mask;
@@ -192,7 +199,7 @@ __device__ __forceinline__ int find_slot(const int *hkey, int state, unsigned ma
 __device__ __forceinline__ int insert_slot(const Table &t, int state, unsigned mask, bool identity, int cap, int *overflow) {
   unsigned s = identity ? (unsigned)state : (hash_state(state) & mask);
   while (true) {
-    int k = __ldcg(t.hkey + s);
+    int k = ldv(t.hkey + s);
     if (k == state) return (int)s;
     if (k == kEmptyKey) {
       int prev = atomicCAS(t.hkey + s, kEmptyKey, state);
@@ -213,11 +220,50 @@ __device__ __forceinline__ int insert_slot(const Table &t, int state, unsigned m
 __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant__ DecodeParams P) {
   __shared__ Shared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const LaneWorkspace ws = P.lanes[blockIdx.x];
+  LaneWorkspace ws = P.lanes[blockIdx.x];
   const DevGraph &g = P.g;
   const DecodeConfig &cfg = P.cfg;
-  const unsigned mask = (unsigned)cfg.hash_size - 1u;
-  const bool identity = g.num_states <= cfg.hash_size;
+  // Small graphs (a grammar HCLG has a few hundred states): the per-frame state tables -- keys,
+  // packed (cost, arc) values, token lists, epsilon frontier, prefix sums -- are carved out of shared
+  // memory and addressed by state id, so token deduplication is a shared-memory atomicMin instead of
+  // an L2 round trip.  Only the traceback arena stays in HBM.
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int smem_slots = cfg.smem_slots;
+  const int tok_cap = smem_slots ? smem_slots : P.cfg.tok_cap;
+  const int hash_size = smem_slots ? smem_slots : P.cfg.hash_size;
+  if (smem_slots) {
+    unsigned char *q = dsm;
+    const size_t H = (size_t)smem_slots;
+    for (int k = 0; k < 2; k++) {
+      ws.hval[k] = reinterpret_cast<unsigned long long *>(q);
+      q += 8 * H;
+    }
+    auto take = [&](size_t n) {
+      int *r = reinterpret_cast<int *>(q);
+      q += 4 * n;
+      return r;
+    };
+    for (int k = 0; k < 2; k++) {
+      ws.hkey[k] = take(H);
+      ws.hidx[k] = take(H);
+      ws.ins_list[k] = take(H);
+      ws.tok_state[k] = take(H);
+      ws.tok_cost[k] = reinterpret_cast<float *>(take(H));
+      ws.frontier[k] = take(H);
+    }
+    ws.inq = take(H);
+    ws.tok_slot = take(H);
+    ws.pfx = reinterpret_cast<unsigned *>(take(H + 4));
+    for (int i = threadIdx.x; i < smem_slots; i += NT) {
+      ws.hkey[0][i] = ws.hkey[1][i] = kEmptyKey;
+      ws.hval[0][i] = ws.hval[1][i] = kEmptyVal;
+      ws.hidx[0][i] = ws.hidx[1][i] = -1;
+      ws.inq[i] = 0;
+    }
+    __syncthreads();
+  }
+  const unsigned mask = (unsigned)hash_size - 1u;
+  const bool identity = g.num_states <= hash_size;
   const unsigned NE = g.num_earcs;
   const float kInf = __int_as_float(0x7f800000);
 
@@ -263,8 +309,8 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         const int n_ins = S.n_ins[tb];
         for (int i = tid; i < n_ins; i += NT) {
           int s = T.ins_list[i];
-          int st = __ldcg(T.hkey + s);
-          float c = unord((unsigned)(__ldcg(T.hval + s) >> 32));
+          int st = ldv(T.hkey + s);
+          float c = unord((unsigned)(ldv(T.hval + s) >> 32));
           if (c < cutoff && g.p_begin[st + 1] > g.p_begin[st]) {
             ws.inq[s] = 1;
             int idx = atomicAdd(&S.frontier_n[0], 1);
@@ -283,8 +329,8 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           int s = ws.frontier[fcur][i];
           atomicExch(ws.inq + s, 0);
           __threadfence_block();
-          int st = __ldcg(T.hkey + s);
-          float c = unord((unsigned)(__ldcg(T.hval + s) >> 32));
+          int st = ldv(T.hkey + s);
+          float c = unord((unsigned)(ldv(T.hval + s) >> 32));
           if (c >= cutoff) continue;
           for (unsigned a = g.p_begin[st]; a < g.p_begin[st + 1]; a++) {
             int4 arc = g.parc[a];
@@ -292,13 +338,13 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
             cnt_arcs++;
             if (tot < cutoff) {
               if (*(volatile int *)&S.overflow) break;
-              int s2 = insert_slot(T, arc.x, mask, identity, cfg.tok_cap, &S.overflow);
+              int s2 = insert_slot(T, arc.x, mask, identity, tok_cap, &S.overflow);
               unsigned long long pv = pack(tot, NE + a);
               unsigned long long old = atomicMin(T.hval + s2, pv);
               if (pv < old && g.p_begin[arc.x + 1] > g.p_begin[arc.x]) {
                 if (atomicExch(ws.inq + s2, 1) == 0) {
                   int idx = atomicAdd(&S.frontier_n[fcur ^ 1], 1);
-                  if (idx < cfg.tok_cap)
+                  if (idx < tok_cap)
                     ws.frontier[fcur ^ 1][idx] = s2;
                   else
                     S.overflow = 1;
@@ -323,9 +369,9 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         unsigned alive = 0;
         if (i < n_ins) {
           s = T.ins_list[i];
-          c = unord((unsigned)(__ldcg(T.hval + s) >> 32));
+          c = unord((unsigned)(ldv(T.hval + s) >> 32));
           alive = c < cutoff ? 1u : 0u;
-          st = __ldcg(T.hkey + s);
+          st = ldv(T.hkey + s);
         }
         unsigned total;
         unsigned pos = running + block_excl_scan(alive, S, &total);
@@ -345,7 +391,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       // ---- traceback records: the arc stored with the winning cost names the predecessor state
       for (int pos = tid; pos < n_new; pos += NT) {
         int s = ws.tok_slot[pos];
-        unsigned arc = (unsigned)(__ldcg(T.hval + s) & 0xffffffffULL);
+        unsigned arc = (unsigned)(ldv(T.hval + s) & 0xffffffffULL);
         int prev = -1;
         if (arc == kArcNone) {
           prev = -1;
@@ -362,7 +408,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       return n_new;
     };
     auto clear_table = [&](int tb) {
-      const int n_ins = min(S.n_ins[tb], cfg.tok_cap);
+      const int n_ins = min(S.n_ins[tb], tok_cap);
       for (int i = tid; i < n_ins; i += NT) {
         int s = ws.ins_list[tb][i];
         ws.hkey[tb][s] = kEmptyKey;
@@ -375,11 +421,11 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     };
     auto wipe_tables = [&]() {  // after an overflow: entries may exist that are not in the lists
       for (int tb = 0; tb < 2; tb++)
-        for (int i = tid; i < cfg.hash_size; i += NT) {
+        for (int i = tid; i < hash_size; i += NT) {
           ws.hkey[tb][i] = kEmptyKey;
           ws.hval[tb][i] = kEmptyVal;
         }
-      for (int i = tid; i < cfg.hash_size; i += NT) ws.inq[i] = 0;
+      for (int i = tid; i < hash_size; i += NT) ws.inq[i] = 0;
       __syncthreads();
       if (tid == 0) {
         S.n_ins[0] = S.n_ins[1] = 0;
@@ -391,7 +437,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     // ---- InitDecoding (:56-73): start token, then epsilon closure under cutoff = beam
     if (tid == 0) {
       Table T{ws.hkey[0], ws.hval[0], ws.hidx[0], ws.ins_list[0], &S.n_ins[0]};
-      int s = insert_slot(T, g.start, mask, identity, cfg.tok_cap, &S.overflow);
+      int s = insert_slot(T, g.start, mask, identity, tok_cap, &S.overflow);
       atomicMin(T.hval + s, pack(0.f, kArcNone));
     }
     __syncthreads();
@@ -514,7 +560,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           const float cand = __fadd_rn(tot, adaptive_beam);
           if (cand < ncv) atomicMin(&S.nc_ord, ord(cand));
           if (*(volatile int *)&S.overflow) break;
-          int s2 = insert_slot(T, arc.x, mask, identity, cfg.tok_cap, &S.overflow);
+          int s2 = insert_slot(T, arc.x, mask, identity, tok_cap, &S.overflow);
           atomicMin(T.hval + s2, pack(tot, ai));
         }
       }
@@ -638,9 +684,20 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
   }
 }
 
+size_t DecodeSmemBytes(int slots) { return (size_t)slots * (2 * 8 + 15 * 4) + 64; }
+
 void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream) {
   if (p.n_utts == 0) return;
-  decode_kernel<<<n_lanes, DecodeCtaThreads(), 0, stream>>>(p);
+  size_t smem = 0;
+  if (p.cfg.smem_slots) {
+    smem = DecodeSmemBytes(p.cfg.smem_slots);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+  }
+  decode_kernel<<<n_lanes, DecodeCtaThreads(), smem, stream>>>(p);
 }
 
 }  // namespace rs

@@ -722,6 +722,13 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   p.cfg.hash_size = hash_size;
   p.cfg.arena_cap = o.max_tokens_per_utt;
   p.cfg.max_words = W;
+  {
+    // shared-memory tables when the graph is small enough for two lanes per SM (<= 1024 states)
+    int slots = 64;
+    while (slots < d->graph->g.num_states) slots <<= 1;
+    const char *e = getenv("RS_B200_DECODE_SMEM");
+    p.cfg.smem_slots = (slots <= 1024 && !(e && e[0] == '0')) ? slots : 0;
+  }
   p.loglikes = loglikes;
   p.ld = ld;
   p.ll_row0 = d_ll_row0;

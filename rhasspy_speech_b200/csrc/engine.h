@@ -154,6 +154,7 @@ struct DecodeConfig {
   int hash_size;    // power of two >= 2 * tok_cap ; identity addressing if num_states <= hash_size
   int arena_cap;    // max tokens per utterance (traceback records)
   int max_words;
+  int smem_slots;   // > 0: state tables in shared memory, addressed by state id (power of two >= num_states)
 };
 
 struct LaneWorkspace {  // one per resident CTA; all pointers are device memory
@@ -189,5 +190,6 @@ struct DecodeParams {
 };
 void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream);
 int DecodeCtaThreads();
+size_t DecodeSmemBytes(int slots);
 
 }  // namespace rs
