@@ -54,7 +54,10 @@ typedef struct rs_result {
   float *graph_cost;     /* [n_utts] */
   float *acoustic_cost;  /* [n_utts] */
   int32_t *num_frames;   /* [n_utts] decoded (subsampled) frames */
-  int32_t *status;       /* [n_utts] 0 ok; bit0 token capacity, bit1 arena capacity, bit2 no surviving tokens, bit3 word capacity */
+  int32_t *status;       /* [n_utts] 0 ok; errors: bit0 token capacity, bit1 arena capacity, bit2 no surviving tokens,
+                          * bit3 word capacity; information: bit4 (16) --max-active limited the beam on some frame:
+                          * the reference's pruning is then order-dependent (lattice-faster-decoder.cc:780-787) and the
+                          * hypothesis, although found with the same cutoff values, is not guaranteed word-identical */
 } rs_result;
 
 typedef struct rs_timings {

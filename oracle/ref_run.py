@@ -141,6 +141,29 @@ def transcribe_wavs(final_mdl: str, online_conf: str, hclg: str, words_txt: str,
     return parse_int_ark_text(out), out, err
 
 
+def transcribe_wavs_costs(final_mdl: str, online_conf: str, hclg: str, words_txt: str, wavs: Sequence[str],
+                          beam: float = 24.0, max_active: int = 7000, lattice_beam: float = 8.0,
+                          ) -> Tuple[Dict[str, List[int]], Dict[str, Tuple[float, float]]]:
+    """As transcribe_wavs (n = 1), plus the (graph, acoustic) cost of each best path
+    (the two extra outputs of nbest-to-linear, kaldi/src/latbin/nbest-to-linear.cc:70-92)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        _write_lists(tmp, wavs)
+        cmd = ("online2-wav-nnet3-latgen-faster --online=false --do-endpointing=false --word-symbol-table=%s "
+               "--config=%s --max-active=%d --lattice-beam=%g --acoustic-scale=1.0 --beam=%g %s %s "
+               "ark:%s/spk2utt scp:%s/wav.scp ark:- 2>/dev/null | lattice-to-nbest --n=1 --acoustic-scale=1.0 ark:- ark:- 2>/dev/null | "
+               "nbest-to-linear ark:- ark:/dev/null ark,t:%s/tr.txt ark,t:%s/lm.txt ark,t:%s/ac.txt 2>/dev/null"
+               % (words_txt, online_conf, max_active, lattice_beam, beam, final_mdl, hclg, tmp, tmp, tmp, tmp, tmp))
+        run(cmd)
+        with open(os.path.join(tmp, "tr.txt"), "rb") as f:
+            words = parse_int_ark_text(f.read())
+        costs: Dict[str, Tuple[float, float]] = {}
+        lm = {l.split()[0]: float(l.split()[1]) for l in open(os.path.join(tmp, "lm.txt")) if l.strip()}
+        ac = {l.split()[0]: float(l.split()[1]) for l in open(os.path.join(tmp, "ac.txt")) if l.strip()}
+        for k in lm:
+            costs[k] = (lm[k], ac.get(k, float("nan")))
+    return words, costs
+
+
 def transcribe_stream(final_mdl: str, online_conf: str, hclg: str, words_txt: str, pcm: np.ndarray,
                       nbest: int = 1, beam: float = 24.0, max_active: int = 7000, lattice_beam: float = 8.0,
                       acoustic_scale: float = 1.0) -> Tuple[Dict[str, List[int]], bytes]:

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     __syncthreads();
     unsigned long long cnt_tokens = 0, cnt_arcs = 0, cnt_created = 0;  // thread 0 / per-thread partials
     int status = 0;
+    int info = 0;  // bit 16: --max-active decided the beam on some frame (see rs_result.status)
     int cur = 0;
     int n_cur = 0;        // alive tokens of the current frame
     int base_cur = 0;     // arena index of the current frame's first token
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         float max_active_cutoff = kInf, min_active_cutoff = kInf;
         if (n_cur > cfg.max_active) max_active_cutoff = block_select(cost, n_cur, cfg.max_active, S);
         if (max_active_cutoff < beam_cutoff) {
+          info |= 16;
           adaptive_beam = __fadd_rn(__fsub_rn(max_active_cutoff, best), cfg.beam_delta);
           cur_cutoff = max_active_cutoff;
         } else {
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         P.counters[4 * (size_t)u + 2] = cnt_created;
         P.counters[4 * (size_t)u + 3] = (unsigned long long)arena_n;
         P.n_words[u] = (status & ~8) ? -1 : n_words;
-        P.status[u] = status;
+        P.status[u] = status | info;
         if (status & ~8) {
           P.cost[2 * u] = 0.f;
           P.cost[2 * u + 1] = 0.f;

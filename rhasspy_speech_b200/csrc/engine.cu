@@ -6,6 +6,9 @@
 #include <cstdarg>
 #include <cstring>
 #include <memory>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -231,6 +234,83 @@ static void BuildFeatTables(const MfccOptions &o, FeatTables *t) {
 }
 
 // --------------------------------------------------------------------------------------------
+// A few persistent host threads that pack the caller's PCM buffers into pinned memory item by item
+// (thread creation per call cost more than the copies themselves).
+class PackPool {
+ public:
+  explicit PackPool(int n_threads) {
+    for (int i = 0; i < n_threads; i++) threads_.emplace_back([this] { Loop(); });
+  }
+  ~PackPool() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto &t : threads_) t.join();
+  }
+  void Start(int n_items, std::function<void(int)> fn) {
+    WaitAll();
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      job_ = std::move(fn);
+      n_items_ = n_items;
+      next_.store(0);
+      done_.reset(new std::atomic<int>[std::max(n_items, 1)]);
+      for (int i = 0; i < n_items; i++) done_[i].store(0);
+      active_ = (int)threads_.size();
+      gen_++;
+    }
+    cv_.notify_all();
+  }
+  bool Help() {  // run one item on the calling thread; false when none is left
+    const int i = next_.fetch_add(1);
+    if (i >= n_items_) return false;
+    job_(i);
+    done_[i].store(1, std::memory_order_release);
+    return true;
+  }
+  void WaitItem(int i) {
+    while (!done_[i].load(std::memory_order_acquire))
+      if (!Help()) std::this_thread::yield();
+  }
+  void WaitAll() {  // every worker has left the current job (its captures may go out of scope)
+    std::unique_lock<std::mutex> l(mu_);
+    idle_cv_.wait(l, [this] { return active_ == 0; });
+  }
+
+ private:
+  void Loop() {
+    uint64_t seen = 0;
+    while (true) {
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      while (Help()) {
+      }
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        active_--;
+      }
+      idle_cv_.notify_all();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_, idle_cv_;
+  std::function<void(int)> job_;
+  std::unique_ptr<std::atomic<int>[]> done_;
+  std::atomic<int> next_{0};
+  int n_items_ = 0, active_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+// --------------------------------------------------------------------------------------------
 struct ModelImpl {
   Model m;
   int device = 0;
@@ -292,6 +372,7 @@ struct DecoderImpl {
   int *d_next_utt = nullptr;
   int *d_range_flag = nullptr;  // set by a split store that had to saturate (fp16 planes)
   int *h_range_flag = nullptr;  // pinned
+  std::unique_ptr<PackPool> pool;
   std::vector<int4> earc_with_pdf;  // graph arcs with ilabel mapped to pdf for this model
   const int4 *d_earc = nullptr;
   rs_timings last{};
@@ -848,34 +929,34 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   const size_t desc_ints = (size_t)2 * n + 5 * (size_t)n + axis_len;
   char *hin = (char *)d->h_in.ensure(pcm_bytes + 16 + desc_ints * sizeof(int));
   int16_t *hpcm = (int16_t *)hin;
-  // Staging is split over a few host threads, and each thread's byte range goes to the device as
-  // soon as it is complete, so the H2D copy of the first ranges overlaps the packing of the rest.
-  int n_workers = 1;
-  if (pcm_bytes > (1u << 20)) n_workers = (int)std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u), (size_t)n);
-  std::vector<int> range_begin(n_workers + 1, n);
+  // Staging is split into items of ~2 MB packed by a small persistent thread pool; each item goes to
+  // the device as soon as it is complete, so the H2D copies overlap the packing of the later items.
+  int n_items = (int)std::min<size_t>(std::max<size_t>(pcm_bytes >> 21, 1), 64);
+  if (n_items > n) n_items = n;
+  std::vector<int> range_begin(n_items + 1, n);
   {
     int u = 0;
-    for (int w = 0; w < n_workers; w++) {
+    for (int w = 0; w < n_items; w++) {
       range_begin[w] = u;
-      const int64_t target = total_samples * (w + 1) / n_workers;
+      const int64_t target = total_samples * (w + 1) / n_items;
       while (u < n && pcm_offset[u] + nsamp[u] <= target) u++;
-      if (w == n_workers - 1) u = n;
+      if (w == n_items - 1) u = n;
     }
-    range_begin[n_workers] = n;
+    range_begin[n_items] = n;
   }
   auto pack = [&](int w) {
     for (int u = range_begin[w]; u < range_begin[w + 1]; u++)
       if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
   };
-  std::vector<std::thread> workers;
-  struct JoinAll {  // an error path must not leave joinable threads behind
-    std::vector<std::thread> *v;
-    ~JoinAll() {
-      for (auto &t : *v)
-        if (t.joinable()) t.join();
+  const bool pooled = n_items > 1;
+  if (pooled && !d->pool) d->pool.reset(new PackPool((int)std::min(6u, std::max(1u, std::thread::hardware_concurrency() - 1))));
+  struct PoolGuard {  // an error path must not leave workers running on this frame's captures
+    PackPool *p;
+    ~PoolGuard() {
+      if (p) p->WaitAll();
     }
-  } join_all{&workers};
-  for (int w = 1; w < n_workers; w++) workers.emplace_back(pack, w);
+  } pool_guard{pooled ? d->pool.get() : nullptr};
+  if (pooled) d->pool->Start(n_items, pack);
   size_t desc_off = (pcm_bytes + 15) & ~(size_t)15;
   int *hdesc = (int *)(hin + desc_off);
   memcpy(hdesc, pcm_offset.data(), sizeof(int64_t) * n);
@@ -898,9 +979,9 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   int *ddesc = (int *)d->d_desc.ensure(desc_ints * sizeof(int));
   CUDA_OK(cudaEventRecord(d->ev[0], d->stream));
   CUDA_OK(cudaMemcpyAsync(ddesc, hdesc, desc_ints * sizeof(int), cudaMemcpyHostToDevice, d->stream));
-  pack(0);
-  for (int w = 0; w < n_workers; w++) {
-    if (w > 0) workers[w - 1].join();
+  for (int w = 0; w < n_items; w++) {
+    if (pooled) d->pool->WaitItem(w);
+    else pack(w);
     const int64_t s0 = range_begin[w] < n ? pcm_offset[range_begin[w]] : total_samples;
     const int64_t s1 = range_begin[w + 1] < n ? pcm_offset[range_begin[w + 1]] : total_samples;
     if (s1 > s0)
@@ -1133,8 +1214,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
         break;
       case Step::kLogSoftmax:
         if (g.out_lo) RS_FAIL("internal: a log-softmax output feeding a tensor-core layer is not supported");
-        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].src_lo, g.slabs[0].ld, reinterpret_cast<float *>(g.out), g.out_ld, g.m, g.n,
-                         d->stream);
+        LaunchLogSoftmax(g.slabs[0].src, g.slabs[0].src_lo, g.slabs[0].ld, g, d->stream);
         break;
     }
     launches++;

@@ -121,8 +121,8 @@ struct GemmParams {
 };
 void LaunchGemm(const GemmParams &p, cudaStream_t stream);
 void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int col_offset, cudaStream_t stream);
-void LaunchLogSoftmax(const void *in, const void *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
-                      cudaStream_t stream);
+// log-softmax over the rows of `in` into p.out (plain fp32), then p.ops
+void LaunchLogSoftmax(const void *in, const void *in_lo, int in_ld, const GemmParams &p, cudaStream_t stream);
 
 struct AssembleParams {
   const float *feats;  // [total_frames, dim]

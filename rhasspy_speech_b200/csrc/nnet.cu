@@ -266,8 +266,11 @@ void LaunchElementwise(const GemmParams &p, const float *term_scale_host, int co
 }
 
 // --------------------------------------------------------------------------- log-softmax (warp/row)
-__global__ void __launch_bounds__(256) logsoftmax_kernel(const void *in, const void *in_lo, int in_ld, float *out, int out_ld,
-                                                         int rows, int n) {
+// `p` carries the output matrix and the ops fused behind the log-softmax (log-prior subtraction and
+// acoustic scale when the log-softmax is the network output, decodable-online-looped.cc:218-223)
+__global__ void __launch_bounds__(256) logsoftmax_kernel(const void *in, const void *in_lo, int in_ld, const __grid_constant__ GemmParams p) {
+  float *out = reinterpret_cast<float *>(p.out);
+  const int out_ld = p.out_ld, rows = p.m, n = p.n;
   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   auto at = [&](int c) { return ld_act(in, in_lo, (size_t)row * in_ld + c); };
@@ -278,13 +281,12 @@ __global__ void __launch_bounds__(256) logsoftmax_kernel(const void *in, const v
   for (int c = lane; c < n; c += 32) s += expf(at(c) - mx);
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float lse = mx + logf(s);
-  for (int c = lane; c < n; c += 32) out[(size_t)row * out_ld + c] = at(c) - lse;
+  for (int c = lane; c < n; c += 32) out[(size_t)row * out_ld + c] = apply_ops(at(c) - lse, row, c, p);
 }
 
-void LaunchLogSoftmax(const void *in, const void *in_lo, int in_ld, float *out, int out_ld, int rows, int n,
-                      cudaStream_t stream) {
-  if (rows <= 0) return;
-  logsoftmax_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(in, in_lo, in_ld, out, out_ld, rows, n);
+void LaunchLogSoftmax(const void *in, const void *in_lo, int in_ld, const GemmParams &p, cudaStream_t stream) {
+  if (p.m <= 0) return;
+  logsoftmax_kernel<<<(p.m + 7) / 8, 256, 0, stream>>>(in, in_lo, in_ld, p);
 }
 
 // --------------------------------------------------------------------------- input assembly

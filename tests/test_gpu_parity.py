@@ -150,3 +150,97 @@ def test_tensor_core_layer_matches_fp64(lib, k, n, offsets, stride):
         got, _ = lib.debug_gemm(src, w, offsets, stride, bias, True, path=path)
         err = np.abs(got - want)[valid].max()
         assert err <= 2e-5, (path, err)
+
+
+def _check_transcripts(lib, ref, synth, p, utts, tmp, **dec_opts):
+    """Whole pipeline through the C ABI vs the reference's 3-process pipeline on the same WAVs."""
+    m = lib.Model(p.final_mdl, p.online_conf, 0)
+    g = lib.Graph(p.hclg, p.words_txt, 0)
+    dec = lib.Decoder(m, g, **dec_opts)
+    wavs = _write_wavs(synth, tmp, utts)
+    ref_kw = {k: v for k, v in dec_opts.items() if k in ("beam", "max_active")}
+    want, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, **ref_kw)
+    got = dec.decode_wavs(wavs)
+    assert all(st in (0, 16) for st in got.status), list(got.status)   # 16 = informational (max-active bound)
+    n_words = 0
+    for u in range(len(wavs)):
+        w = want.get("utt%05d-1" % u)
+        assert got.words[u] == w, (u, got.words[u], w)
+        n_words += len(w or [])
+    return dec, got, n_words
+
+
+def test_arpa_graph_with_out_of_grammar_audio(lib, ref, synth, utterances, tmp_path):
+    """BASELINE config 3: ARPA-LM-shaped HCLG (back-off epsilon arcs, tens of thousands of arcs) and
+    out-of-grammar audio (time-reversed utterances); also with a tight --max-active so that
+    the max-active cutoff (GetCutoff's nth_element value) decides the beam on every frame."""
+    import dataclasses
+    spec = dataclasses.replace(synth.TINY, name="tiny_arpa", seed=11, graph="arpa", vocab_size=300, bigrams_per_word=8, eps_hops=2)
+    p = synth.write_model(str(tmp_path / "m"), spec)
+    utts = list(utterances) + [u[::-1].copy() for u in utterances[:3]]
+    dec, got, n_words = _check_transcripts(lib, ref, synth, p, utts, tmp_path)
+    assert n_words > 0 and dec.graph.num_states > 1024          # the global-memory table path
+    t = dec.timings()
+    assert t["tokens_expanded"] > 20 * t["frames_decoded"]
+    _check_transcripts(lib, ref, synth, p, utts, tmp_path, beam=12.0)
+    # A binding --max-active: the cutoff VALUE is reproduced (radix select == nth_element), but the
+    # reference's token list also holds the order-dependent tokens its transient next_cutoff let through
+    # (lattice-faster-decoder.cc:780-787); they change `toks.size() > max_active` and, under the then
+    # narrow adaptive beam, the search itself.  Such utterances carry status bit 16; the contract is:
+    # unflagged => word-identical, flagged => same cutoff arithmetic, agreement measured (DESIGN.md 4.2).
+    m = lib.Model(p.final_mdl, p.online_conf, 0)
+    g = lib.Graph(p.hclg, p.words_txt, 0)
+    wavs = _write_wavs(synth, tmp_path, utts)
+    flagged = 0
+    for max_active in (300, 1000, 7000):
+        want, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, max_active=max_active)
+        got = lib.Decoder(m, g, max_active=max_active).decode_wavs(wavs)
+        for u in range(len(wavs)):
+            assert got.status[u] in (0, 16) and got.n_hyp[u] == 1, (max_active, u, got.status[u])
+            if got.status[u] == 0:
+                assert got.words[u] == want.get("utt%05d-1" % u), (max_active, u)
+            else:
+                flagged += 1
+    assert flagged > 0          # max_active = 300 does bind on this graph
+
+
+@pytest.mark.parametrize("variant", ["softmax_sf1", "text_priors_ldabias", "nnet_cmvn"])
+def test_model_variants_match_reference(lib, ref, synth, utterances, tmp_path, variant):
+    """BASELINE config 5 in miniature: differently shaped models side by side in one process (the
+    reference's 8 language models differ in exactly these respects): frame-subsampling 1 with a
+    log-softmax output and priors, text-format files with an LDA offset column, CMVN on the nnet input."""
+    import dataclasses
+    if variant == "softmax_sf1":
+        spec = dataclasses.replace(synth.TINY, name=variant, seed=21, chain=False, frame_subsampling_factor=1, log_softmax=True,
+                                   priors=True, tdnnf_strides=(1, 0, 1, 1))
+    elif variant == "text_priors_ldabias":
+        spec = dataclasses.replace(synth.TINY, name=variant, seed=22, binary=False, priors=True, lda_bias=True)
+    else:
+        spec = dataclasses.replace(synth.TINY, name=variant, seed=23, nnet_cmvn=True, num_gauss=64, ivector_dim=40)
+    p = synth.write_model(str(tmp_path / "m"), spec)
+    dec, got, n_words = _check_transcripts(lib, ref, synth, p, utterances, tmp_path)
+    assert n_words > 0
+    # log-likelihoods of this variant against nnet3-compute (1e-4, the north-star tolerance)
+    feats = [dec.fetch(3 if spec.nnet_cmvn else 0, u) for u in range(len(utterances))]
+    ivs = [dec.fetch(1, u)[0] for u in range(len(utterances))]
+    want = ref.nnet_loglikes(p.final_mdl, feats, ivs, frame_subsampling_factor=spec.frame_subsampling_factor)
+    for u, w in enumerate(want):
+        ll = dec.fetch(2, u)
+        assert ll.shape == w.shape and np.abs(ll - w).max() <= 1e-4, (u, ll.shape, w.shape, np.abs(ll - w).max())
+
+
+def test_stream_surface(tiny, utterances):
+    """rs_stream_*: 80 ms chunks (BASELINE config 4 framing); many streams finish in one device batch and
+    give what the WAV path gives for the same audio (the stream surface decodes with offline semantics)."""
+    _, _, dec = tiny
+    streams = [dec.open_stream() for _ in utterances]
+    for s, pcm in zip(streams, utterances):
+        raw = np.asarray(pcm, dtype="<i2").tobytes()
+        for o in range(0, len(raw), 2560):
+            s.accept(raw[o:o + 2560])
+    got = dec.finish_streams(streams)
+    want = dec.decode_pcm(utterances)
+    assert got.words == want.words and list(got.num_frames) == list(want.num_frames)
+    one = streams[0]
+    one.accept(np.asarray(utterances[0], dtype="<i2").tobytes())
+    assert one.finish().words[0] == want.words[0]
