@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BATCH = 256
+# DRAM bytes the nnet stage moved in one step under ncu (profiles/r1_launches_i_dram.csv): 7.39 GB read + 3.06 GB written
+NNET_DRAM_BYTES_PER_STEP = 10454000000
 METRIC = "RTFx (audio-sec/wall-sec) en_US-zamia 16kHz at 1/2/4/8 B200; WER vs ref"
 UNIT = "audio-sec/wall-sec"
 
@@ -237,12 +239,13 @@ def run_ours(args):
         pk, pk_kind = peaks()
         t = dec.timings()
         nnet_ms = float(sm[:, 1].mean())
-        tf32_peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2.0
+        f16_peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])   # fp16 and bf16 share the pipe and the rate
         achieved = t["nnet_flops"] / (nnet_ms / 1e3) / 1e12
+        hbm_achieved = t["nnet_bytes"] / (nnet_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": audio_total / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_s_max * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (tensor-core products as 3 x fp16 split terms, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": "configs[1]: batch=256 per GPU, grammar-HCLG, 3-5 s 16 kHz utterances",
                        "model": "zamia-like TDNN-F chain (synthetic, seeded): 40-dim hires MFCC + 100-dim iVector, 1024/128 x 12 TDNN-F, 3026 pdfs, sf=3",
                        "graph": "en_US grammar HCLG (synthetic lexicon), %d states" % graph.num_states,
@@ -253,9 +256,20 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "stages_ms": {"feature": float(sm[:, 0].mean()), "nnet": nnet_ms, "decode": float(sm[:, 2].mean()),
                           "h2d": float(sm[:, 3].mean()), "d2h": float(sm[:, 4].mean())},
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (TDNN-F affine layers, all launches of the stage)",
-                         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                         "traffic": None, "peak_source": pk_kind + " bf16_tflops_sustained / 2 (TF32 pipe)"},
+            # dominant kernel = gemm_tc_kernel (30 launches per step, the whole nnet stage between two CUDA
+            # events on the decoder's stream).  achieved = algorithmic FLOPs (2*rows*K*N per layer, counted
+            # once although every product is 3 MMAs => attainable frac <= 1/3) / stage time.
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (TDNN-F affine layers, 30 launches = the nnet stage)",
+                         "achieved": achieved, "peak": f16_peak, "unit": "TFLOP/s", "frac": achieved / f16_peak,
+                         "traffic": NNET_DRAM_BYTES_PER_STEP,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the stage's launches, "
+                                           "profiles/r1_launches_i_dram.csv (same command, batch 256)",
+                         "peak_source": pk_kind + " bf16_tflops_sustained (fp16 tensor pipe)",
+                         "note": "3 MMAs per algorithmic product: attainable frac <= 0.333"},
+            # the same launches against HBM: the stage streams every layer's activations through HBM once
+            "roofline_hbm": {"bound": "hbm", "kernel": "gemm_tc_kernel (same 30 launches)", "achieved": hbm_achieved,
+                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
+                             "traffic": NNET_DRAM_BYTES_PER_STEP, "algorithmic_bytes": int(t["nnet_bytes"])},
             "decoder_counters": {k: int(t[k]) for k in ("frames_decoded", "tokens_expanded", "arcs_visited", "tokens_created")},
             "clocks": sampler.summary(),
             "wall_s_total": t_all,

@@ -67,6 +67,7 @@ typedef struct rs_timings {
   uint64_t nnet_flops;    /* algorithmic FLOPs of the acoustic model for the last batch */
   uint64_t h2d_bytes, d2h_bytes;
   int32_t kernel_launches;
+  uint64_t nnet_bytes;    /* algorithmic HBM bytes of the acoustic model: every layer input once, bypass input, output */
 } rs_timings;
 
 void rs_decoder_opts_default(rs_decoder_opts *opts);

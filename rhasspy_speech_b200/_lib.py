@@ -37,7 +37,8 @@ class Timings(C.Structure):
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("audio_seconds", C.c_double),
                 ("frames_decoded", C.c_uint64), ("tokens_expanded", C.c_uint64), ("arcs_visited", C.c_uint64),
                 ("tokens_created", C.c_uint64), ("records_written", C.c_uint64), ("nnet_flops", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32),
+                ("nnet_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -337,6 +337,7 @@ struct ModelImpl {
   std::vector<char> split;  // per plan buffer: stored as two TF32 planes
   int num_sms = 0;
   uint64_t flops_per_axis_unit = 0;  // sum over gemm steps of 2*n*ktot/step (per time unit of the axis)
+  uint64_t bytes_per_axis_unit = 0;  // algorithmic HBM bytes of the same steps: each input once, bypass, output (x1000)
   ~ModelImpl() {
     for (void *p : owned) cudaFree(p);
   }
@@ -545,6 +546,17 @@ static void UploadModel(ModelImpl *mi) {
       uint64_t k = 0;
       for (const auto &s : st.slabs) k += s.k;
       mi->flops_per_axis_unit += 2ull * st.n * k * 1000 / pl.buffers[st.out].step;  // x1000 fixed point
+      // 4 bytes per element: a split buffer is two fp16 planes, a plain one fp32
+      uint64_t b = 4ull * st.n * 1000 / pl.buffers[st.out].step;
+      std::vector<int> seen;
+      for (const auto &sl : st.slabs)
+        if (!pl.buffers[sl.src].per_utt && std::find(seen.begin(), seen.end(), sl.src) == seen.end()) {
+          seen.push_back(sl.src);
+          b += 4ull * pl.buffers[sl.src].dim * 1000 / pl.buffers[sl.src].step;
+        }
+      for (const auto &op : st.ops)
+        if (op.type == EpiOp::kAddScaled && op.buffer >= 0) b += 4ull * pl.buffers[op.buffer].dim * 1000 / pl.buffers[op.buffer].step;
+      mi->bytes_per_axis_unit += b;
     }
   }
   mi->plan_text = DescribePlan(pl);
@@ -1223,6 +1235,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   CUDA_OK(cudaMemcpyAsync(d->h_range_flag, d->d_range_flag, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
   CUDA_OK(cudaEventRecord(d->ev[3], d->stream));
   d->last.nnet_flops = (uint64_t)((double)mi->flops_per_axis_unit / 1000.0 * axis_len);
+  d->last.nnet_bytes = (uint64_t)((double)mi->bytes_per_axis_unit / 1000.0 * axis_len);
   // ---- stage (iii)
   B.loglikes = slot_ptr(pl.output_buffer);
   B.ll_ld = buf_ld(pl.output_buffer);
