@@ -222,18 +222,39 @@ def run_ours(args):
         launches += t["kernel_launches"]
     barrier()
     t_all = time.perf_counter() - t_all0
+    # the same call with two batches in flight per GPU (two decoders, two host threads): the host staging
+    # and result assembly of one batch overlap the kernels of the other.  Every batch still pays its own
+    # pinned staging, H2D, kernels and D2H inside the timed region.
+    dec2 = _lib.Decoder(model, graph)
+    for _ in range(2):
+        dec2.decode_pcm(utts)
+    n_pipe = max(args.steps, 4)
+
+    def worker(dx, k):
+        for _ in range(k):
+            dx.decode_pcm(utts)
+    barrier()
+    tp0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(dx, (n_pipe + 1) // 2)) for dx in (dec, dec2)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join()
+    torch.cuda.synchronize()
+    pipe_s = (time.perf_counter() - tp0) / (2 * ((n_pipe + 1) // 2))
+    barrier()
     sampler.stop_flag.set()
     sampler.join()
     sm = np.asarray(stage_ms)
     dev_s = float((sm[:, 0] + sm[:, 1] + sm[:, 2]).mean() / 1e3)
     e2e_s = float(np.mean(wall_s))
     # max over ranks (device time and wall time), sum of audio
-    vec = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
+    vec = torch.tensor([dev_s, e2e_s, pipe_s], dtype=torch.float64, device="cuda")
     aud = torch.tensor([audio_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(aud, op=dist.ReduceOp.SUM)
-    dev_s_max, e2e_s_max = [float(x) for x in vec.tolist()]
+    dev_s_max, e2e_s_max, pipe_s_max = [float(x) for x in vec.tolist()]
     audio_total = float(aud.item())
     if rank == 0:
         pk, pk_kind = peaks()
@@ -253,6 +274,8 @@ def run_ours(args):
                        "audio_seconds_per_step": audio_total},
             "e2e": {"value": audio_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(t["h2d_bytes"]),
                     "d2h_bytes_per_step": int(t["d2h_bytes"]), "ms_per_step": e2e_s_max * 1e3},
+            "e2e_two_in_flight": {"value": audio_total / pipe_s_max, "unit": UNIT, "ms_per_batch": pipe_s_max * 1e3,
+                                  "how": "two decoders per GPU driven by two host threads, same call, same per-batch copies"},
             "gpu_launches": int(launches),
             "stages_ms": {"feature": float(sm[:, 0].mean()), "nnet": nnet_ms, "decode": float(sm[:, 2].mean()),
                           "h2d": float(sm[:, 3].mean()), "d2h": float(sm[:, 4].mean())},
