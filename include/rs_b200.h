@@ -105,7 +105,11 @@ int rs_decode_loglikes(rs_decoder *d, const float *const *loglikes, const int32_
 void rs_result_free(rs_result *r);
 
 /* Streaming surface (online2-cli-nnet3-decode-faster fed raw s16le on stdin,
- * transcribe_stream.py:51-82).  Audio is buffered; the utterance is decoded at finish. */
+ * transcribe_stream.py:51-82).  Audio is buffered and the utterance is decoded at finish WITH THE ONLINE
+ * SEMANTICS of that binary: it re-chunks its input into reads of 1024 samples, so its result is a function
+ * of the audio only -- each nnet chunk uses the iVector estimated (warm-started CG) from the frames that had
+ * arrived when the chunk became ready (decodable-online-looped.cc:56-84, 186-194).  rs_decode_pcm / _wavs
+ * use the offline schedule of online2-wav-nnet3-latgen-faster --online=false (one iVector per utterance). */
 rs_stream *rs_stream_open(rs_decoder *d, char *err, size_t errlen);
 int rs_stream_accept(rs_stream *s, const int16_t *pcm, int32_t num_samples, char *err, size_t errlen);
 int rs_stream_finish(rs_stream *s, rs_result **out, char *err, size_t errlen);
@@ -116,7 +120,7 @@ int rs_streams_finish(rs_stream *const *streams, int32_t n, rs_result **out, cha
 /* Instrumentation of the last decode call on this decoder. */
 int rs_decoder_timings(const rs_decoder *d, rs_timings *t);
 /* Intermediate results of the last rs_decode_pcm / rs_decode_wavs call, for the parity tests:
- * what = 0 MFCC [T x dim], 1 iVector [1 x dim], 2 log-likelihoods [T/sf x num_pdfs],
+ * what = 0 MFCC [T x dim], 1 iVector [solves x dim] (1 row offline, one per CG solve online), 2 log-likelihoods [T/sf x num_pdfs],
  *        3 CMVN-normalised MFCC, 4 LDA features (normalised stream).
  * Call with dst == NULL to query rows/cols. */
 int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t *rows, int32_t *cols, char *err,

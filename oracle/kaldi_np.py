@@ -756,3 +756,63 @@ def ivectors_periodic(s: IvectorSetup, mfcc_feats: np.ndarray) -> np.ndarray:
             cur = st.get_ivector(cur)
             rows.append(cur.copy())
     return np.asarray(rows)
+
+
+def online_schedule(nsamp: int, num_frames: int, chunk: int, right_context: int, splice_right: int, sf: int,
+                    window: int = 400, shift: int = 160) -> Tuple[List[int], List[int]]:
+    """Which frames each nnet chunk's iVector has seen when audio is streamed to the reference's stream binary
+    (online2bin/online2-cli-nnet3-decode-faster.cc:139-160: reads of 1024 samples, AdvanceDecoding after each).
+    Chunks become ready per nnet3/decodable-online-looped.cc:56-84; a chunk takes the iVector of frame
+    min(features_ready, ivector_frames_ready) - 1 (:186-194), the iVector stream lags by the splice right context
+    until InputFinished (feat/online-feature.cc:496-502), and a new CG is run only when new frames were added
+    (online2/online-ivector-feature.cc:248-279).  Returns (solve_frames, chunk_solve)."""
+    solve_frames: List[int] = []
+    chunk_solve: List[int] = []
+    stats = 0
+
+    def advance(F, iv_ready, ready_chunks):
+        nonlocal stats
+        while len(chunk_solve) < ready_chunks:
+            frames = min(F - 1, iv_ready - 1) + 1 if iv_ready > 0 else 0
+            if not solve_frames or frames > stats:
+                solve_frames.append(frames)
+                stats = frames
+            chunk_solve.append(len(solve_frames) - 1)
+
+    got = 0
+    while got < nsamp:
+        got = min(got + 1024, nsamp)
+        F = 0 if got < window else 1 + (got - window) // shift
+        if F == 0:
+            continue
+        advance(F, max(0, F - splice_right), max(0, F - right_context) // chunk)
+    if num_frames > 0:
+        total_out = (num_frames + sf - 1) // sf
+        per = chunk // sf
+        advance(num_frames, num_frames, (total_out + per - 1) // per)
+    return solve_frames, chunk_solve
+
+
+def ivectors_online(s: IvectorSetup, mfcc_feats: np.ndarray, solve_frames: Sequence[int]) -> np.ndarray:
+    """The iVectors of the successive solves of online_schedule(): statistics of the first `frames` frames,
+    CG warm-started from the previous solve (use_most_recent_ivector = true, greedy = false).  Rows are the
+    nnet inputs (float32, prior offset removed)."""
+    R = s.M[0].shape[1]
+    xn = lda_feats(s, mfcc_feats, True) if mfcc_feats.shape[0] else np.zeros((0, 1))
+    xr = xn if s.online_cmvn_iextractor or not mfcc_feats.shape[0] else lda_feats(s, mfcc_feats, False)
+    post = gmm_posteriors(s, xn) if mfcc_feats.shape[0] else []
+    st = IvectorStats(s)
+    cur = np.zeros(R)
+    start = 0
+    rows = []
+    for f in solve_frames:
+        if f > start:
+            st.acc(xr[start:f], post[start:f])
+            start = f
+            cur = st.get_ivector(cur)
+        out = cur.astype(f32)
+        out[0] = f32(out[0] - f32(s.prior_offset)) if f > 0 or start > 0 else f32(0.0)
+        if start == 0:
+            out[:] = 0
+        rows.append(out)
+    return np.asarray(rows)

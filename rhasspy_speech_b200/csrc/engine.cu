@@ -381,6 +381,7 @@ struct DecoderImpl {
   struct Batch {
     int n = 0, total_frames = 0, axis_len = 0;
     std::vector<int> num_frames, frame_offset, origin, n_out, ll_row0;
+    std::vector<int> v_begin;  // first iVector solve (row of the per-utterance buffers) of each utterance
     bool from_loglikes = false;
     const float *loglikes = nullptr;
     int ll_ld = 0;
@@ -890,7 +891,46 @@ static void FinishTimings(DecoderImpl *d, int launches) {
   t.kernel_launches = launches;
 }
 
-static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int32_t *nsamp, int n) {
+// Online decoding (online2-cli-nnet3-decode-faster.cc:139-160): audio arrives in reads of 1024 samples,
+// after each read the decoder advances over the nnet chunks that have become ready
+// (decodable-online-looped.cc:56-84) and every chunk is computed with the iVector estimated from the
+// frames available at that moment (:186-194, online-ivector-feature.cc:248-279, 327-355).  The sequence is
+// a pure function of the sample count.  Returns, for one utterance, the frame counts of the successive
+// iVector solves and, per nnet chunk, the index of the solve it uses.
+struct OnlineSchedule {
+  std::vector<int> solve_frames;  // solve j covers frames [0, solve_frames[j])  (0 = no data: zero iVector)
+  std::vector<int> chunk_solve;   // per chunk
+};
+static OnlineSchedule ComputeOnlineSchedule(int nsamp, int T, int length, int shift, int chunk, int right_context,
+                                            int splice_right, int sf) {
+  OnlineSchedule s;
+  int chunks_done = 0, stats_frames = 0;
+  auto advance = [&](int F, int iv_ready, int ready_chunks) {
+    while (chunks_done < ready_chunks) {
+      int frames = 0;
+      if (iv_ready > 0) frames = std::min(F - 1, iv_ready - 1) + 1;
+      if (s.solve_frames.empty() || frames > stats_frames) {  // GetFrame processes new frames, then one CG
+        s.solve_frames.push_back(frames);
+        stats_frames = frames;
+      }
+      s.chunk_solve.push_back((int)s.solve_frames.size() - 1);
+      chunks_done++;
+    }
+  };
+  for (long long got = 0; got < nsamp;) {
+    got = std::min<long long>(got + 1024, nsamp);
+    const int F = got < length ? 0 : 1 + (int)((got - length) / shift);
+    if (F == 0) continue;
+    advance(F, std::max(0, F - splice_right), std::max(0, F - right_context) / chunk);
+  }
+  if (T > 0) {  // InputFinished: every frame is ready, the tail is padded with the last frame
+    const int out_per_chunk = chunk / sf, total_out = (T + sf - 1) / sf;
+    advance(T, T, (total_out + out_per_chunk - 1) / out_per_chunk);
+  }
+  return s;
+}
+
+static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int32_t *nsamp, int n, bool online = false) {
   ModelImpl *mi = d->model;
   const Model &m = mi->m;
   const Plan &pl = m.plan;
@@ -935,10 +975,34 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   B.total_frames = total_frames;
   B.axis_len = axis_len;
   d->last.audio_seconds = audio_s;
+  // ---- iVector solves: one per utterance (offline, online2-wav-nnet3-latgen-faster --online=false) or
+  // one per nnet chunk that saw new frames (online, the stream binary)
+  int chunk = m.frames_per_chunk;  // GetChunkSize (nnet-compile-looped.cc:81-94), modulus 1 for TDNN models
+  while (chunk % sf) chunk++;
+  std::vector<int> v_num_frames, v_frame_offset;
+  std::vector<OnlineSchedule> sched(online && m.has_ivector ? n : 0);
+  B.v_begin.assign(n + 1, 0);
+  for (int u = 0; u < n; u++) {
+    B.v_begin[u] = (int)v_num_frames.size();
+    if (!sched.empty()) {
+      sched[u] = ComputeOnlineSchedule(nsamp[u], B.num_frames[u], length, shift, chunk, R, m.ivec.splice_right, sf);
+      if (sched[u].solve_frames.empty()) sched[u].solve_frames.push_back(0);
+      for (int f : sched[u].solve_frames) {
+        v_num_frames.push_back(f);
+        v_frame_offset.push_back(B.frame_offset[u]);
+      }
+    } else {
+      v_num_frames.push_back(B.num_frames[u]);
+      v_frame_offset.push_back(B.frame_offset[u]);
+    }
+  }
+  const int v_n = (int)v_num_frames.size();
+  B.v_begin[n] = v_n;
   // ---- host staging: pcm + descriptor block, one H2D copy each
   const size_t pcm_bytes = sizeof(int16_t) * (size_t)std::max<int64_t>(total_samples, 1);
   // descriptor: pcm_offset[n] (i64) | num_frames | frame_offset | origin | n_out | ll_row0 | row_utt[axis_len]
-  const size_t desc_ints = (size_t)2 * n + 5 * (size_t)n + axis_len;
+  //             | v_num_frames[v_n] | v_frame_offset[v_n] | v_begin[n + 1]
+  const size_t desc_ints = (size_t)2 * n + 5 * (size_t)n + axis_len + 2 * (size_t)v_n + n + 1;
   char *hin = (char *)d->h_in.ensure(pcm_bytes + 16 + desc_ints * sizeof(int));
   int16_t *hpcm = (int16_t *)hin;
   // Staging is split into items of ~2 MB packed by a small persistent thread pool; each item goes to
@@ -980,12 +1044,24 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     h_no[u] = B.n_out[u];
     h_r0[u] = B.ll_row0[u];
   }
-  {
+  {  // row of the per-utterance buffers (iVector, its bias contribution) that axis time t uses
     int u = 0;
+    const int lag = (R + chunk - 1) / chunk;  // iVector time k * chunk first appears in chunk max(0, k - lag)
     for (int t = 0; t < axis_len; t++) {
       while (u + 1 < n && t >= B.origin[u + 1] - L) u++;
-      h_ru[t] = u;
+      int row = B.v_begin[u];
+      if (!sched.empty() && !sched[u].chunk_solve.empty()) {
+        const int tl = t - B.origin[u];
+        const int k = tl >= 0 ? tl / chunk : -((-tl + chunk - 1) / chunk);  // t - Mod(t, period), nnet-compile-looped.cc:188-208
+        const int c = std::min(std::max(k - lag, 0), (int)sched[u].chunk_solve.size() - 1);
+        row += sched[u].chunk_solve[c];
+      }
+      h_ru[t] = row;
     }
+    int *h_v = h_ru + axis_len;
+    memcpy(h_v, v_num_frames.data(), sizeof(int) * v_n);
+    memcpy(h_v + v_n, v_frame_offset.data(), sizeof(int) * v_n);
+    memcpy(h_v + 2 * v_n, B.v_begin.data(), sizeof(int) * (n + 1));
   }
   int16_t *dpcm = (int16_t *)d->d_pcm.ensure(pcm_bytes);
   int *ddesc = (int *)d->d_desc.ensure(desc_ints * sizeof(int));
@@ -1027,7 +1103,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   auto slot_ptr = [&](int buffer) -> float * { return d->slots[pl.buffers[buffer].slot].as<float>(); };
   // row pitch in elements: fp32 buffers are padded to 16 bytes, split (2 x fp16 plane) buffers too
   auto buf_ld = [&](int buffer) { return RoundUp(pl.buffers[buffer].dim, mi->split[buffer] ? 8 : 4); };
-  auto buf_rows = [&](int buffer) { return pl.buffers[buffer].per_utt ? n : axis_len / pl.buffers[buffer].step; };
+  auto buf_rows = [&](int buffer) { return pl.buffers[buffer].per_utt ? v_n : axis_len / pl.buffers[buffer].step; };
   // split buffers hold two planes back to back: hi at slot_ptr, lo right behind it
   auto slot_lo = [&](int buffer) -> __half * {
     return mi->split[buffer] ? reinterpret_cast<__half *>(slot_ptr(buffer)) + (size_t)buf_rows(buffer) * buf_ld(buffer) : nullptr;
@@ -1061,6 +1137,10 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     iv.num_frames = d_nf;
     iv.frame_offset = d_fo;
     iv.n_utts = n;
+    iv.v_n = v_n;
+    iv.v_num_frames = d_ru + axis_len;
+    iv.v_frame_offset = d_ru + axis_len + v_n;
+    iv.v_begin = d_ru + axis_len + 2 * v_n;
     iv.total_frames = total_frames;
     iv.max_frames = max_frames;
     const size_t tf = std::max(total_frames, 1);
@@ -1068,11 +1148,11 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     iv.x_norm = (float *)d->d_xnorm.ensure(tf * LD * sizeof(float));
     iv.post_idx = (int *)d->d_post_idx.ensure(tf * iv.num_gselect * sizeof(int));
     iv.post_w = (float *)d->d_post_w.ensure(tf * iv.num_gselect * sizeof(float));
-    iv.wf = (double *)d->d_wf.ensure((size_t)n * G * LD * sizeof(double));
-    iv.gw = (float *)d->d_gw.ensure((size_t)n * G * sizeof(float));
+    iv.wf = (double *)d->d_wf.ensure((size_t)v_n * G * LD * sizeof(double));
+    iv.gw = (float *)d->d_gw.ensure((size_t)v_n * G * sizeof(float));
     iv.linear_chunks = (G * LD + 511) / 512;
-    iv.linear_part = (double *)d->d_linear.ensure((size_t)iv.linear_chunks * n * Rv * sizeof(double));
-    iv.quad = (double *)d->d_quad.ensure((size_t)n * P * sizeof(double));
+    iv.linear_part = (double *)d->d_linear.ensure((size_t)iv.linear_chunks * v_n * Rv * sizeof(double));
+    iv.quad = (double *)d->d_quad.ensure((size_t)v_n * P * sizeof(double));
     d_ivector = slot_ptr(pl.ivector_buffer);
     ivector_ld = buf_ld(pl.ivector_buffer);
     iv.ivector = d_ivector;
@@ -1430,7 +1510,7 @@ int rs_streams_finish(rs_stream *const *streams, int32_t n, rs_result **out, cha
     ptrs[i] = s->pcm.data();
     ns[i] = (int32_t)s->pcm.size();
   }
-  *out = DecodePcm(d, ptrs.data(), ns.data(), n);
+  *out = DecodePcm(d, ptrs.data(), ns.data(), n, /*online=*/true);
   for (int i = 0; i < n; i++) reinterpret_cast<StreamImpl *>(streams[i])->pcm.clear();
   return 0;
   API_GUARD_END(1)
@@ -1658,10 +1738,10 @@ int rs_debug_fetch(rs_decoder *d_, int32_t what, int32_t utt, float *dst, int32_
       src = b.as<float>() + (size_t)B.frame_offset[utt] * ld;
     } else if (what == 1) {
       if (!m.has_ivector) RS_FAIL("rs_debug_fetch: model has no iVector input");
-      r = 1;
+      r = B.v_begin[utt + 1] - B.v_begin[utt];  // one row per iVector solve (1 when decoding offline)
       c = m.ie.ivector_dim;
       ld = RoundUp(c, 4);
-      src = d->slots[m.plan.buffers[m.plan.ivector_buffer].slot].as<float>() + (size_t)utt * ld;
+      src = d->slots[m.plan.buffers[m.plan.ivector_buffer].slot].as<float>() + (size_t)B.v_begin[utt] * ld;
     } else if (what == 4) {
       if (!m.has_ivector) RS_FAIL("rs_debug_fetch: model has no iVector input");
       r = B.num_frames[utt];

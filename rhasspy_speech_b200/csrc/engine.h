@@ -50,6 +50,12 @@ struct IvecParams {
   const float *mfcc, *mfcc_norm;      // [total_frames, dim]
   const int *num_frames, *frame_offset;
   int n_utts, total_frames, max_frames;
+  // iVector solves: solve j accumulates the statistics of the first v_num_frames[j] frames of the
+  // utterance whose features start at v_frame_offset[j]; utterance u owns solves [v_begin[u], v_begin[u+1])
+  // and runs them in order, each CG warm-started from the previous one.  Offline decoding has one solve
+  // per utterance over all its frames; online decoding one per nnet chunk (online-ivector-feature.cc:248-279).
+  int v_n;
+  const int *v_num_frames, *v_frame_offset, *v_begin;
   int dim, left, right;               // splice
   const float *lda_t;                 // [K = dim*(left+1+right)][ldim]  (transposed), bias may be null
   const float *lda_bias;
@@ -72,12 +78,12 @@ struct IvecParams {
   float max_count;
   int num_cg_iters;
   int online_cmvn_iextractor;
-  double *wf;                         // [n_utts][G][ldim] weighted feature sums
-  float *gw;                          // [n_utts][G] per-Gaussian total weights (float, as the reference)
-  double *linear_part;                // [linear_chunks][n_utts][R] split-K partial sums of the linear term
+  double *wf;                         // [v_n][G][ldim] weighted feature sums
+  float *gw;                          // [v_n][G] per-Gaussian total weights (float, as the reference)
+  double *linear_part;                // [linear_chunks][v_n][R] split-K partial sums of the linear term
   int linear_chunks;                  // ceil(G * ldim / 512)
-  double *quad;                       // [n_utts][R(R+1)/2] packed lower triangle
-  float *ivector;                     // [n_utts][ivector_ld] nnet input (prior offset removed)
+  double *quad;                       // [v_n][R(R+1)/2] packed lower triangle
+  float *ivector;                     // [v_n][ivector_ld] nnet input (prior offset removed), one row per solve
   int ivector_ld;
 };
 void LaunchIvector(const IvecParams &p, cudaStream_t stream);

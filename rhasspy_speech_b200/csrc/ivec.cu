@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
 // wf[u][g][:] += w * x_t  (double; order-insensitive at 1e-16) ; gw[u][g] = float sum over frames in
 // frame order (GaussInfo::tot_weight is a float accumulated in frame order).
 __global__ void __launch_bounds__(256) ivec_acc_kernel(IvecParams p) {
-  const int u = blockIdx.y;
-  const int T = p.num_frames[u];
-  const size_t base = (size_t)p.frame_offset[u];
+  const int u = blockIdx.y;  // solve index
+  const int T = p.v_num_frames[u];
+  const size_t base = (size_t)p.v_frame_offset[u];
   const float *feats = p.online_cmvn_iextractor ? p.x_norm : p.x_raw;
   const int D = p.ldim, S = p.num_gselect;
   double *wf = p.wf + (size_t)u * p.num_gauss * D;
@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(256) ivec_acc_kernel(IvecParams p) {
 }
 
 __global__ void __launch_bounds__(256) ivec_gw_kernel(IvecParams p) {
-  const int u = blockIdx.y;
+  const int u = blockIdx.y;  // solve index
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int T = p.num_frames[u], S = p.num_gselect;
-  const size_t base = (size_t)p.frame_offset[u];
+  const int T = p.v_num_frames[u], S = p.num_gselect;
+  const size_t base = (size_t)p.v_frame_offset[u];
   extern __shared__ int spost[];  // tile of posteriors: idx then weight bits
   float acc = 0.f;
   const int tile = 256;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(128) ivec_linear_kernel(IvecParams p) {
   const int n = min(kLinChunk, GD - k0);
   for (int i = threadIdx.x; i < kUT * n; i += blockDim.x) {
     int j = i / n, k = i - j * n;
-    swf[j][k] = (u0 + j < p.n_utts) ? p.wf[(size_t)(u0 + j) * GD + k0 + k] : 0.0;
+    swf[j][k] = (u0 + j < p.v_n) ? p.wf[(size_t)(u0 + j) * GD + k0 + k] : 0.0;
   }
   __syncthreads();
   for (int rr = r; rr < R; rr += blockDim.x) {
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128) ivec_linear_kernel(IvecParams p) {
       for (int j = 0; j < kUT; j++) acc[j] = fma(mv, swf[j][k], acc[j]);
     }
     for (int j = 0; j < kUT; j++)
-      if (u0 + j < p.n_utts) p.linear_part[((size_t)blockIdx.x * p.n_utts + u0 + j) * R + rr] = acc[j];
+      if (u0 + j < p.v_n) p.linear_part[((size_t)blockIdx.x * p.v_n + u0 + j) * R + rr] = acc[j];
   }
 }
 
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128) ivec_quad_kernel(IvecParams p) {
   extern __shared__ double sgw[];  // [kUT][G]
   for (int i = threadIdx.x; i < kUT * G; i += blockDim.x) {
     int j = i / G, g = i - j * G;
-    sgw[i] = (u0 + j < p.n_utts) ? (double)p.gw[(size_t)(u0 + j) * G + g] : 0.0;
+    sgw[i] = (u0 + j < p.v_n) ? (double)p.gw[(size_t)(u0 + j) * G + g] : 0.0;
   }
   __syncthreads();
   if (k >= P) return;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(128) ivec_quad_kernel(IvecParams p) {
     for (int j = 0; j < kUT; j++) acc[j] = fma(sgw[j * G + g], uv, acc[j]);
   }
   for (int j = 0; j < kUT; j++)
-    if (u0 + j < p.n_utts) p.quad[(size_t)(u0 + j) * P + k] = acc[j];
+    if (u0 + j < p.v_n) p.quad[(size_t)(u0 + j) * P + k] = acc[j];
 }
 
 // ------------------------------------------------------------------------------- CG solve
@@ -365,91 +365,101 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 }
 
 __global__ void __launch_bounds__(128) ivec_cg_kernel(IvecParams p) {
-  const int u = blockIdx.x, R = p.ivector_dim, P = R * (R + 1) / 2;
+  const int utt = blockIdx.x, R = p.ivector_dim, P = R * (R + 1) / 2;
   extern __shared__ double sh[];
   double *A = sh;            // [R*R] dense symmetric
   double *b = A + (size_t)R * R, *x = b + R, *r = x + R, *pv = r + R, *Ap = pv + R, *red = Ap + R;
   const int tid = threadIdx.x;
-  // total weight (double sum of the float per-Gaussian totals)
-  double tw = 0.0;
-  for (int g = tid; g < p.num_gauss; g += blockDim.x) tw += (double)p.gw[(size_t)u * p.num_gauss + g];
-  tw = block_sum(tw, red);
-  double prior_scale_change = 0.0;
-  if (p.max_count > 0.f) {
-    double mc = (double)p.max_count;
-    double old_scale = fmax(0.0, mc) / mc, new_scale = fmax(tw, mc) / mc;
-    prior_scale_change = new_scale - old_scale;
-  }
-  const double *q = p.quad + (size_t)u * P;
-  for (int i = tid; i < R * R; i += blockDim.x) {
-    int a = i / R, c = i - a * R;
-    int hi = a > c ? a : c, lo = a > c ? c : a;
-    double v = q[(size_t)hi * (hi + 1) / 2 + lo];
-    if (a == c) v += 1.0 + prior_scale_change;
-    A[i] = v;
-  }
-  for (int i = tid; i < R; i += blockDim.x) {
-    double v = 0.0;  // fold the split-K partials of ivec_linear_kernel in chunk order
-    for (int c = 0; c < p.linear_chunks; c++) v += p.linear_part[((size_t)c * p.n_utts + u) * R + i];
-    if (i == 0) v += p.prior_offset + p.prior_offset * prior_scale_change;
-    b[i] = v;
-    x[i] = i == 0 ? p.prior_offset : 0.0;
-  }
+  // current_ivector_ of the reference: starts at the prior mean and is carried from solve to solve
+  for (int i = tid; i < R; i += blockDim.x) x[i] = i == 0 ? p.prior_offset : 0.0;
   __syncthreads();
-  const bool have_data = tw > 0.0;
-  auto matvec = [&](const double *v, double *out) {  // out = A v
+  for (int u = p.v_begin[utt]; u < p.v_begin[utt + 1]; u++) {  // the utterance's solves, in order
+    // total weight (double sum of the float per-Gaussian totals)
+    double tw = 0.0;
+    for (int g = tid; g < p.num_gauss; g += blockDim.x) tw += (double)p.gw[(size_t)u * p.num_gauss + g];
+    tw = block_sum(tw, red);
+    double prior_scale_change = 0.0;
+    if (p.max_count > 0.f) {
+      double mc = (double)p.max_count;
+      double old_scale = fmax(0.0, mc) / mc, new_scale = fmax(tw, mc) / mc;
+      prior_scale_change = new_scale - old_scale;
+    }
+    const double *q = p.quad + (size_t)u * P;
+    for (int i = tid; i < R * R; i += blockDim.x) {
+      int a = i / R, c = i - a * R;
+      int hi = a > c ? a : c, lo = a > c ? c : a;
+      double v = q[(size_t)hi * (hi + 1) / 2 + lo];
+      if (a == c) v += 1.0 + prior_scale_change;
+      A[i] = v;
+    }
     for (int i = tid; i < R; i += blockDim.x) {
-      double acc = 0.0;
-      const double *row = A + (size_t)i * R;
-      for (int k = 0; k < R; k++) acc = fma(row[k], v[k], acc);
-      out[i] = acc;
+      double v = 0.0;  // fold the split-K partials of ivec_linear_kernel in chunk order
+      for (int c = 0; c < p.linear_chunks; c++) v += p.linear_part[((size_t)c * p.v_n + u) * R + i];
+      if (i == 0) v += p.prior_offset + p.prior_offset * prior_scale_change;
+      b[i] = v;
     }
     __syncthreads();
-  };
-  auto dot = [&](const double *a, const double *c) {
-    double v = 0.0;
-    for (int i = tid; i < R; i += blockDim.x) v += a[i] * c[i];
-    return block_sum(v, red);
-  };
-  if (have_data) {
-    matvec(x, Ap);
-    for (int i = tid; i < R; i += blockDim.x) {
-      pv[i] = b[i] - Ap[i];
-      r[i] = -pv[i];
-    }
-    __syncthreads();
-    double r_cur = dot(r, r), r_init = r_cur, r_recompute = r_cur;
-    const double max_err_sq = DBL_MIN, rf = 0.01 * 0.01, inv_rf = 1.0 / rf;
-    for (int k = 0; k < R + 5 && k != p.num_cg_iters; k++) {
-      matvec(pv, Ap);
-      double alpha = -dot(pv, r) / dot(pv, Ap);
+    const bool have_data = tw > 0.0;
+    auto matvec = [&](const double *v, double *out) {  // out = A v
       for (int i = tid; i < R; i += blockDim.x) {
-        x[i] += alpha * pv[i];
-        r[i] += alpha * Ap[i];
+        double acc = 0.0;
+        const double *row = A + (size_t)i * R;
+        for (int k = 0; k < R; k++) acc = fma(row[k], v[k], acc);
+        out[i] = acc;
       }
       __syncthreads();
-      double r_next = dot(r, r);
-      if (r_next < rf * r_recompute || r_next > inv_rf * r_recompute) {
-        matvec(x, Ap);
-        for (int i = tid; i < R; i += blockDim.x) r[i] = Ap[i] - b[i];
+    };
+    auto dot = [&](const double *a, const double *c) {
+      double v = 0.0;
+      for (int i = tid; i < R; i += blockDim.x) v += a[i] * c[i];
+      return block_sum(v, red);
+    };
+    if (have_data) {
+      // GetIvector (ivector-extractor.cc:732-756): warm start, "better initial guess" if x[0] == 0
+      if (tid == 0 && x[0] == 0.0) x[0] = p.prior_offset;
+      __syncthreads();
+      matvec(x, Ap);
+      for (int i = tid; i < R; i += blockDim.x) {
+        pv[i] = b[i] - Ap[i];
+        r[i] = -pv[i];
+      }
+      __syncthreads();
+      double r_cur = dot(r, r), r_recompute = r_cur;
+      const double max_err_sq = DBL_MIN, rf = 0.01 * 0.01, inv_rf = 1.0 / rf;
+      for (int k = 0; k < R + 5 && k != p.num_cg_iters; k++) {
+        matvec(pv, Ap);
+        double alpha = -dot(pv, r) / dot(pv, Ap);
+        for (int i = tid; i < R; i += blockDim.x) {
+          x[i] += alpha * pv[i];
+          r[i] += alpha * Ap[i];
+        }
         __syncthreads();
-        r_next = dot(r, r);
-        r_recompute = r_next;
+        double r_next = dot(r, r);
+        if (r_next < rf * r_recompute || r_next > inv_rf * r_recompute) {
+          matvec(x, Ap);
+          for (int i = tid; i < R; i += blockDim.x) r[i] = Ap[i] - b[i];
+          __syncthreads();
+          r_next = dot(r, r);
+          r_recompute = r_next;
+        }
+        if (r_next <= max_err_sq) break;
+        double beta = r_next / r_cur;
+        for (int i = tid; i < R; i += blockDim.x) pv[i] = beta * pv[i] - r[i];
+        __syncthreads();
+        r_cur = r_next;
       }
-      if (r_next <= max_err_sq) break;
-      double beta = r_next / r_cur;
-      for (int i = tid; i < R; i += blockDim.x) pv[i] = beta * pv[i] - r[i];
+    } else {
+      for (int i = tid; i < R; i += blockDim.x) x[i] = i == 0 ? p.prior_offset : 0.0;
       __syncthreads();
-      r_cur = r_next;
     }
-    (void)r_init;
-  }
-  // nnet input: float copy, prior offset removed from the first element
-  // (online-ivector-feature.cc:344-347)
-  for (int i = tid; i < R; i += blockDim.x) {
-    float f = (float)x[i];
-    if (i == 0) f = (float)((double)f - p.prior_offset);
-    p.ivector[(size_t)u * p.ivector_ld + i] = f;
+    // nnet input: float copy, prior offset removed from the first element
+    // (online-ivector-feature.cc:344-347)
+    for (int i = tid; i < R; i += blockDim.x) {
+      float f = (float)x[i];
+      if (i == 0) f = (float)((double)f - p.prior_offset);
+      p.ivector[(size_t)u * p.ivector_ld + i] = f;
+    }
+    __syncthreads();
   }
 }
 
@@ -468,15 +478,15 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
     }
     ubm_post_kernel<<<(p.total_frames + kUbmFrames - 1) / kUbmFrames, 256, sm2, stream>>>(p);
   }
-  cudaMemsetAsync(p.wf, 0, (size_t)p.n_utts * G * D * sizeof(double), stream);
+  cudaMemsetAsync(p.wf, 0, (size_t)p.v_n * G * D * sizeof(double), stream);
   if (p.total_frames > 0) {
     int per_utt_blocks = (p.max_frames * p.num_gselect * D + 255) / 256;
     if (per_utt_blocks > 64) per_utt_blocks = 64;
     if (per_utt_blocks < 1) per_utt_blocks = 1;
-    ivec_acc_kernel<<<dim3(per_utt_blocks, p.n_utts), 256, 0, stream>>>(p);
+    ivec_acc_kernel<<<dim3(per_utt_blocks, p.v_n), 256, 0, stream>>>(p);
   }
-  ivec_gw_kernel<<<dim3((G + 255) / 256, p.n_utts), 256, 2 * 256 * sizeof(int), stream>>>(p);
-  int groups = (p.n_utts + kUT - 1) / kUT;
+  ivec_gw_kernel<<<dim3((G + 255) / 256, p.v_n), 256, 2 * 256 * sizeof(int), stream>>>(p);
+  int groups = (p.v_n + kUT - 1) / kUT;
   ivec_linear_kernel<<<dim3(p.linear_chunks, groups), 128, 0, stream>>>(p);
   ivec_quad_kernel<<<dim3((P + 127) / 128, groups), 128, (size_t)kUT * G * sizeof(double), stream>>>(p);
   size_t sm3 = ((size_t)R * R + 5 * R + 8) * sizeof(double);

@@ -728,7 +728,7 @@ void LoadModel(const std::string &final_mdl, const std::string &online_conf, Mod
   Take(kv, "frame-subsampling-factor", &m->frame_subsampling_factor);
   bool add_pitch = false;
   Take(kv, "add-pitch", &add_pitch);
-  int extra_left_initial = 0, frames_per_chunk = 20;
+  int extra_left_initial = 0, frames_per_chunk = 24;  // NnetSimpleLoopedComputationOptions (decodable-simple-looped.h:54-58)
   Take(kv, "extra-left-context-initial", &extra_left_initial);
   Take(kv, "frames-per-chunk", &frames_per_chunk);
   // endpointing and silence weighting are inactive as the reference invokes the decoders
@@ -745,6 +745,8 @@ void LoadModel(const std::string &final_mdl, const std::string &online_conf, Mod
   if (feature_type != "mfcc") RS_FAIL(online_conf << ": only --feature-type=mfcc is supported, got " << feature_type);
   if (add_pitch) RS_FAIL(online_conf << ": --add-pitch=true is not supported");
   if (extra_left_initial != 0) RS_FAIL(online_conf << ": --extra-left-context-initial != 0 is not supported");
+  if (frames_per_chunk < 1) RS_FAIL(online_conf << ": bad --frames-per-chunk");
+  m->frames_per_chunk = frames_per_chunk;
   if (m->frame_subsampling_factor < 1) RS_FAIL(online_conf << ": bad --frame-subsampling-factor");
   if (!mfcc_config.empty()) ParseMfccConf(mfcc_config, &m->mfcc);
   if (!cmvn_config.empty()) {

@@ -176,6 +176,7 @@ struct Model {
   CmvnOptions nnet_cmvn_opts;
   MatrixD nnet_global_cmvn;
   int frame_subsampling_factor = 1;
+  int frames_per_chunk = 24;  // online decoding: nnet chunk (and iVector period) before rounding to sf
   float acoustic_scale = 1.0f;
   TransitionModel trans;
   Nnet3 nnet;

@@ -229,18 +229,37 @@ def test_model_variants_match_reference(lib, ref, synth, utterances, tmp_path, v
         assert ll.shape == w.shape and np.abs(ll - w).max() <= 1e-4, (u, ll.shape, w.shape, np.abs(ll - w).max())
 
 
-def test_stream_surface(tiny, utterances):
-    """rs_stream_*: 80 ms chunks (BASELINE config 4 framing); many streams finish in one device batch and
-    give what the WAV path gives for the same audio (the stream surface decodes with offline semantics)."""
-    _, _, dec = tiny
+def test_stream_surface_matches_reference_stream_binary(tiny, tiny_model, utterances, ref):
+    """rs_stream_*: 80 ms chunks (BASELINE config 4 framing), many streams finished in one device batch.
+    The stream surface reproduces the ONLINE schedule of online2-cli-nnet3-decode-faster (1024-sample reads,
+    one warm-started iVector per nnet chunk): iVectors of every solve against the restatement, words against
+    the reference binary fed the same bytes."""
+    from oracle import kaldi_np as K
+    model, _, dec = tiny
+    assert dec.finish_streams([]).n_utts == 0
     streams = [dec.open_stream() for _ in utterances]
     for s, pcm in zip(streams, utterances):
         raw = np.asarray(pcm, dtype="<i2").tobytes()
         for o in range(0, len(raw), 2560):
             s.accept(raw[o:o + 2560])
     got = dec.finish_streams(streams)
-    want = dec.decode_pcm(utterances)
-    assert got.words == want.words and list(got.num_frames) == list(want.num_frames)
-    one = streams[0]
-    one.accept(np.asarray(utterances[0], dtype="<i2").tobytes())
-    assert one.finish().words[0] == want.words[0]
+    conf = os.path.join(tiny_model.model_dir, "model", "online", "conf")
+    setup = K.IvectorSetup.from_conf(os.path.join(conf, "ivector_extractor.conf"))
+    n_multi = 0
+    for u, pcm in enumerate(utterances):
+        mf = dec.fetch(0, u)
+        solves, _ = K.online_schedule(len(pcm), mf.shape[0], 24, model.right_context, setup.splice_right, 3)
+        want_iv = K.ivectors_online(setup, mf, solves)
+        iv = dec.fetch(1, u)
+        assert iv.shape == want_iv.shape, (iv.shape, want_iv.shape, solves)
+        assert np.abs(iv - want_iv).max() <= 1e-4, np.abs(iv - want_iv).max()
+        n_multi += len(solves) > 1
+        want, _ = ref.transcribe_stream(tiny_model.final_mdl, tiny_model.online_conf, tiny_model.hclg, tiny_model.words_txt, pcm)
+        assert got.words[u] == want.get("utt-1"), (u, got.words[u], want.get("utt-1"))
+    assert n_multi == len(utterances)
+    # the WAV path keeps the offline schedule: one solve per utterance
+    dec.decode_pcm(utterances[:1])
+    assert dec.fetch(1, 0).shape[0] == 1
+    # a stream object is reusable after finish
+    streams[0].accept(np.asarray(utterances[0], dtype="<i2").tobytes())
+    assert streams[0].finish().words[0] == got.words[0]

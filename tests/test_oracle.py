@@ -103,3 +103,23 @@ def test_cmvn_window_and_smoothing(K):
     # frame 650: the window holds exactly frames 51..650, no smoothing
     mean = x[51:651].astype(np.float64).mean(axis=0)
     assert np.allclose(out[650], x[650] - mean, atol=1e-5)
+
+
+def test_online_schedule_properties():
+    """The stream binary's iVector schedule (oracle restatement): solves grow monotonically, the last one has
+    seen every frame, every chunk maps to a solve, and a chunk never uses frames that had not arrived."""
+    from oracle import kaldi_np as K
+    for nsamp in (0, 399, 400, 5000, 16000, 47311, 80000):
+        T = 0 if nsamp < 400 else 1 + (nsamp - 400) // 160
+        for chunk, right, sf in ((24, 8, 3), (24, 28, 3), (24, 0, 1), (21, 5, 3)):
+            solves, chunk_solve = K.online_schedule(nsamp, T, chunk, right, 3, sf)
+            assert solves == sorted(solves) and len(set(solves)) == len(solves)
+            n_chunks = -(-(-(-T // sf)) // (chunk // sf)) if T else 0
+            assert len(chunk_solve) == n_chunks
+            if T:
+                assert solves[-1] == T and chunk_solve == sorted(chunk_solve) and chunk_solve[-1] == len(solves) - 1
+                for c, j in enumerate(chunk_solve[:-1]):
+                    # chunk c needs input frames < (c + 1) * chunk + right; while streaming the iVector lags by the splice
+                    assert solves[j] <= T
+            else:
+                assert solves == [] and chunk_solve == []
