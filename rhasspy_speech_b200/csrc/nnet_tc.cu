@@ -152,7 +152,8 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
 // ReLU / BatchNorm / bypass / split-store tail of the previous tile.
 constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
 
-// 10 warps = up to 3 per SM sub-partition (16 K registers each): at most 168 registers per thread
+// 12 warps = 3 per SM sub-partition (16 K registers each): 168 registers per thread at launch, then
+// re-allocated by setmaxnreg to 40 (TMA / MMA warpgroup) and 232 (epilogue warpgroups)
 // PAT >= 0: the epilogue op sequence is a compile-time constant (4 bits per op: EpiOp::Type + 1,
 // first op in the low bits, see TcPattern); PAT < 0: run-time op list.
 template <int PAT>
@@ -171,9 +172,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
   auto setf_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + a); };
+  // main-accumulator barriers are indexed (epilogue group, physical set) = g * 2 + s: an mbarrier waiter
+  // may be at most one phase behind, so the two groups, which alternate tiles, cannot share a barrier
   auto sete_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 4 + a); };
-  auto crosse_bar = [&](int a) { return sete_bar(2 + a); };  // cross accumulator a (tile parity) drained
-  const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 8);
+  auto crosse_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 8 + a); };  // cross accumulator a drained
+  const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -183,8 +186,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
     for (int a = 0; a < 4; a++) {
       mbar_init(setf_bar(a), 1);
-      mbar_init(sete_bar(a), 8);
+      mbar_init(sete_bar(a), 4);  // released by the 4 warps of one group
     }
+    mbar_init(crosse_bar(0), 4);
+    mbar_init(crosse_bar(1), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -198,10 +203,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+
   const int num_tiles = p.tiles_m * p.tiles_n;
   int total_kb = 0;
   for (int s = 0; s < p.n_slabs; s++) total_kb += p.slabs[s].kblocks;
 
+  // register re-allocation between the warpgroups: 40 for {TMA, MMA, 2 idle warps}, 232 for the epilogue groups
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
@@ -246,14 +255,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       // instruction descriptor: D fp32, A/B fp16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
       int stage = 0;
-      uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; accumulator pair = kbc & 1
+      uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; physical main set = kbc & 1
+      uint32_t use_par = 0;         // bit b: parity of the number of blocks committed on barrier pair b = group * 2 + set
+      int last_b[2] = {-1, -1};     // barrier pair of the block that last occupied each physical set
       uint32_t tcount = 0;  // tiles issued so far: cross accumulator = tcount & 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
         const uint32_t d_cross = tmem_base + (uint32_t)((2 + (tcount & 1)) * p.bn);
         mbar_wait(crosse_bar(tcount & 1), ((tcount >> 1) & 1u) ^ 1u);
         for (int kb = 0; kb < total_kb; kb++, kbc++) {
-          const int set = kbc & 1;
-          mbar_wait(sete_bar(set), ((kbc >> 1) & 1u) ^ 1u);
+          const int set = kbc & 1, bsel = (int)(tcount & 1) * 2 + set;
+          if (last_b[set] >= 0) mbar_wait(sete_bar(last_b[set]), ((use_par >> last_b[set]) & 1u) ^ 1u);  // set drained
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t d_main = tmem_base + (uint32_t)(set * p.bn);
@@ -268,7 +279,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
-          tc_commit(setf_bar(set));     // this block's main sum (and, on the last block, the cross sum) complete
+          tc_commit(setf_bar(bsel));    // this block's main sum (and, on the last block, the cross sum) complete
+          use_par ^= 1u << bsel;
+          last_b[set] = bsel;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -277,19 +290,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       }
     }
     __syncwarp();
+  }
   } else {
-    // ------------------------------------------------- epilogue warps 2..9
-    // warp -> (TMEM lane quadrant q, column half h): each thread owns one output row and up to 64
-    // columns of the tile, i.e. 64 fp32 running sums in registers
-    const int q = warp & 3, h = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ------------------------------------------------- epilogue groups: warps 4..7 and 8..11
+    // The groups alternate tiles, so the tail of tile i (bias .. split store) overlaps the main loop and
+    // the folds of tile i+1.  warp -> TMEM lane quadrant q; a thread owns one output row and all (<= 128)
+    // columns of the tile: 128 fp32 running sums in registers (the warpgroup holds 232 registers per
+    // thread after setmaxnreg, the TMA / MMA warpgroup 40).
+    const int q = warp & 3, group = (warp - 4) >> 2;
+    constexpr int h = 0;
     // this warp's 32 x 32 fp32 staging tile (float4 columns XOR-swizzled by row: conflict-free both ways)
-    float4 *stg = reinterpret_cast<float4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 2) * 4096u);
-    uint32_t kbc = 0, tcount = 0;  // K blocks / tiles consumed so far (ring positions and parities)
+    float4 *stg = reinterpret_cast<float4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 4) * 4096u);
+    uint32_t tcount = group;  // local index of this group's current tile: K-block ring position = tcount * total_kb
+    uint32_t cnt_par = 0;     // bit s: parity of the number of blocks this group has taken from physical set s
     int ib = -1;  // the op whose split bypass input is prefetched (first kAddScaled with a split source)
     for (int i = 0; i < p.n_ops && ib < 0; i++)
       if (p.ops[i].type == EpiOp::kAddScaled && p.ops[i].buf_lo) ib = i;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+    for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, tcount += 2) {
       const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
+      uint32_t kbc = tcount * (uint32_t)total_kb;
       // bypass input of one 32-column chunk: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B
       // cover a row segment, 8 rows per instruction; issued early so that HBM latency is hidden
       uint4 pf_h[4], pf_l[4];
@@ -315,13 +335,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       // static op list: lane l keeps column l of each per-column vector (bias, BatchNorm scale /
       // offset) of both chunks in a register, loaded here so that the latency hides behind the main
       // loop; the tail broadcasts a column with a shuffle (a warp works on one column set for 32 rows)
-      float vr0[4][2], vr1[4][2];
+      float vr0[4][kTcChunks], vr1[4][kTcChunks];
       if constexpr (kStatic) {
         constexpr int types[4] = {kT0, kT1, kT2, kT3};
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int jc = 0; jc < 2; jc++) {
+          for (int jc = 0; jc < kTcChunks; jc++) {
             const int c = n0 + h * 64 + jc * 32 + lane;
             const bool ok = h * 64 + jc * 32 + lane < p.bn && c < p.n;
             vr0[i][jc] = vr1[i][jc] = 0.f;
@@ -329,17 +349,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if (types[i] == EpiOp::kScaleOffset) vr1[i][jc] = ok ? __ldg(p.ops[i].v1 + c) : 0.f;
           }
       }
-      float acc[kTcMaxBN / 2];
+      float acc[kTcMaxBN];
 #pragma unroll
-      for (int j = 0; j < kTcMaxBN / 2; j++) acc[j] = 0.f;
+      for (int j = 0; j < kTcMaxBN; j++) acc[j] = 0.f;
       for (int kb = 0; kb < total_kb; kb++, kbc++) {
         if (kb == total_kb - 1 && ib >= 0) prefetch(0);
-        const int set = kbc & 1;
-        mbar_wait(setf_bar(set), (kbc >> 1) & 1u);
+        const int set = kbc & 1, bsel = group * 2 + set;
+        mbar_wait(setf_bar(bsel), (cnt_par >> set) & 1u);
+        cnt_par ^= 1u << set;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn + h * 64);
 #pragma unroll
-        for (int jc = 0; jc < 2; jc++)
+        for (int jc = 0; jc < kTcChunks; jc++)
           if (h * 64 + jc * 32 < p.bn) {
             uint32_t raw[32];
             tmem_ld32_nowait(taddr + jc * 32, raw);
@@ -350,12 +371,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(sete_bar(set));
+        if (lane == 0) mbar_arrive(sete_bar(bsel));
       }
       {  // the tile's cross sum: acc += cross * 2^-11 (the last block's commit covers it)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + (tcount & 1)) * p.bn + h * 64);
 #pragma unroll
-        for (int jc = 0; jc < 2; jc++)
+        for (int jc = 0; jc < kTcChunks; jc++)
           if (h * 64 + jc * 32 < p.bn) {
             uint32_t raw[32];
             tmem_ld32_nowait(taddr + jc * 32, raw);
@@ -370,7 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       const int r = m0 + q * 32 + lane;
       const int rr = r < p.m ? r : p.m - 1;
 #pragma unroll
-      for (int jc = 0; jc < 2; jc++) {
+      for (int jc = 0; jc < kTcChunks; jc++) {
         const int c0 = n0 + h * 64 + jc * 32;
         if (h * 64 + jc * 32 >= p.bn || c0 >= p.n) continue;
         float v[32];
@@ -449,7 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                   stg[ii * 8 + ((2 * c8) ^ (ii & 7))] = make_float4(x[0], x[1], x[2], x[3]);
                   stg[ii * 8 + ((2 * c8 + 1) ^ (ii & 7))] = make_float4(x[4], x[5], x[6], x[7]);
                 }
-                if (i == ib && jc == 0) prefetch(1);  // next chunk's bypass while this one is finished
+                if (i == ib && jc + 1 < kTcChunks) prefetch(jc + 1);  // next chunk's bypass while this one is finished
               } else {
                 // plain fp32 source: 8 lanes x 16 B cover a 128-byte row segment, 4 rows per instruction
                 float4 bf[8];
@@ -699,7 +720,7 @@ static void LaunchPattern(const TcParams &p, int grid, int smem, cudaStream_t st
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream) {
   if (p.m <= 0 || p.n <= 0) return;
   const int stage_bytes = 2 * kStageABytes + 2 * p.bn * 128;
-  const int smem = 1024 + p.stages * stage_bytes + 8 * 4096 + 8 * (2 * p.stages + 8) + 16;
+  const int smem = 1024 + p.stages * stage_bytes + 8 * 4096 + 8 * (2 * p.stages + 10) + 16;
   int grid = p.tiles_m * p.tiles_n;
   if (grid > num_sms) grid = num_sms;
   switch (TcPattern(p)) {

@@ -263,3 +263,28 @@ def test_stream_surface_matches_reference_stream_binary(tiny, tiny_model, uttera
     # a stream object is reusable after finish
     streams[0].accept(np.asarray(utterances[0], dtype="<i2").tobytes())
     assert streams[0].finish().words[0] == got.words[0]
+
+
+@pytest.mark.parametrize("k,n,offsets,relu", [(64, 128, (0,), False), (100, 200, (-1, 0), True), (256, 96, (0, 3), True)])
+def test_tensor_core_layer_many_tiles_per_cta(lib, k, n, offsets, relu):
+    """More tiles than SMs: every persistent CTA walks several tiles, so both epilogue groups, the TMEM
+    accumulator ring and the shared-memory stage ring wrap around many times (odd and even K-block counts)."""
+    rng = np.random.default_rng(k + n)
+    rows = 128 * 148 * 3 + 77
+    src = rng.standard_normal((rows, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k * len(offsets))) / np.sqrt(k * len(offsets))).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    r = np.arange(rows)
+    want = np.zeros((rows, n))
+    valid = np.ones(rows, dtype=bool)
+    for i, o in enumerate(offsets):
+        idx = r + o
+        valid &= (idx >= 0) & (idx < rows)
+        want += src[np.clip(idx, 0, rows - 1)].astype(np.float64) @ w[:, i * k:(i + 1) * k].astype(np.float64).T
+    want += bias
+    if relu:
+        want = np.maximum(want, 0)
+    for path in (1, 2):
+        got, _ = lib.debug_gemm(src, w, offsets, 1, bias, relu, path=path)
+        err = np.abs(got - want)[valid].max()
+        assert err <= 2e-5, (path, err)
