@@ -127,6 +127,13 @@ __device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1) {
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
 }
+__device__ __forceinline__ void mul2(float &a0, float &a1, float b0, float b1) {
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
 // split two values into the packed hi / lo fp16 pairs of the plane format (split.cuh); conversions
 // saturate at +-65504, `amax` collects max |x| so that the caller can flag a saturation
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo, float &amax) {
@@ -349,9 +356,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if (types[i] == EpiOp::kScaleOffset) vr1[i][jc] = ok ? __ldg(p.ops[i].v1 + c) : 0.f;
           }
       }
+      // AffineComponent / TdnnComponent::Propagate copy the bias into the output and let the GEMM accumulate
+      // onto it (nnet-simple-component.cc, nnet-tdnn-component.cc:181-211): same order here when the op list
+      // starts with the bias
+      constexpr bool kBiasFirst = kStatic && kT0 == EpiOp::kBias;
       float acc[kTcMaxBN];
 #pragma unroll
-      for (int j = 0; j < kTcMaxBN; j++) acc[j] = 0.f;
+      for (int j = 0; j < kTcMaxBN; j++) acc[j] = kBiasFirst ? __shfl_sync(0xffffffffu, vr0[0][j >> 5], j & 31) : 0.f;
       for (int kb = 0; kb < total_kb; kb++, kbc++) {
         if (kb == total_kb - 1 && ib >= 0) prefetch(0);
         const int set = kbc & 1, bsel = group * 2 + set;
@@ -423,8 +434,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             case EpiOp::kScaleOffset:
               if constexpr (kStatic) {
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                  v[j] = __fadd_rn(__fmul_rn(v[j], __shfl_sync(0xffffffffu, vb0, j)), __shfl_sync(0xffffffffu, vb1, j));
+                for (int j = 0; j < 32; j += 2) {  // y = x * scale, then + offset: two roundings as the reference, two columns per instruction
+                  mul2(v[j], v[j + 1], __shfl_sync(0xffffffffu, vb0, j), __shfl_sync(0xffffffffu, vb0, j + 1));
+                  add2(v[j], v[j + 1], __shfl_sync(0xffffffffu, vb1, j), __shfl_sync(0xffffffffu, vb1, j + 1));
+                }
                 break;
               }
 #pragma unroll
@@ -497,15 +510,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               for (int j = 0; j < 32; j += 4) {
                 float4 o = stg[lane * 8 + ((j >> 2) ^ (lane & 7))];
                 if (op.alpha != 1.f) {
-                  o.x = __fmul_rn(op.alpha, o.x);
-                  o.y = __fmul_rn(op.alpha, o.y);
-                  o.z = __fmul_rn(op.alpha, o.z);
-                  o.w = __fmul_rn(op.alpha, o.w);
+                  mul2(o.x, o.y, op.alpha, op.alpha);
+                  mul2(o.z, o.w, op.alpha, op.alpha);
                 }
-                v[j] = __fadd_rn(o.x, v[j]);
-                v[j + 1] = __fadd_rn(o.y, v[j + 1]);
-                v[j + 2] = __fadd_rn(o.z, v[j + 2]);
-                v[j + 3] = __fadd_rn(o.w, v[j + 3]);
+                add2(v[j], v[j + 1], o.x, o.y);
+                add2(v[j + 2], v[j + 3], o.z, o.w);
               }
               break;
             }
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           }
         };
         if constexpr (kStatic) {
-          if constexpr (kT0 >= 0) apply(0, kT0, vr0[0][jc], vr1[0][jc]);
+          if constexpr (kT0 >= 0 && !kBiasFirst) apply(0, kT0, vr0[0][jc], vr1[0][jc]);
           if constexpr (kT1 >= 0) apply(1, kT1, vr0[1][jc], vr1[1][jc]);
           if constexpr (kT2 >= 0) apply(2, kT2, vr0[2][jc], vr1[2][jc]);
           if constexpr (kT3 >= 0) apply(3, kT3, vr0[3][jc], vr1[3][jc]);
