@@ -122,16 +122,22 @@ __device__ __forceinline__ void block_min(float v, int i, Shared &S) {
     S.red_i[warp] = i;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float bv = S.red_v[0];
-    int bi = S.red_i[0];
-    for (int w = 1; w < NW; w++)
-      if (S.red_v[w] < bv || (S.red_v[w] == bv && S.red_i[w] < bi)) {
-        bv = S.red_v[w];
-        bi = S.red_i[w];
+  if (warp == 0) {  // second level: one shuffle reduction over the warp results
+    float bv = lane < NW ? S.red_v[lane] : __int_as_float(0x7f800000);
+    int bi = lane < NW ? S.red_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
       }
-    S.best_cost = bv;
-    S.best_idx = bi;
+    }
+    if (lane == 0) {
+      S.best_cost = bv;
+      S.best_idx = bi;
+    }
   }
   __syncthreads();
 }
@@ -154,17 +160,37 @@ __device__ float block_select(const float *a, int n, int k, Shared &S) {
       if ((key & mask) == prefix) atomicAdd(&S.hist[(key >> shift) & 255], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int kk = S.sel_k;
-      unsigned b = 0;
-      for (; b < 256; b++) {
-        int h = (int)S.hist[b];
-        if (kk < h) break;
-        kk -= h;
+    if (threadIdx.x < 32) {
+      // warp 0 locates the bin that holds the k-th key: 8 bins per lane, shuffle scan over the lane sums
+      // (a serial scan of the 256 bins by one thread cost ~7 k cycles per pass, 4 passes per call)
+      const int lane = threadIdx.x;
+      unsigned h[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        h[i] = S.hist[lane * 8 + i];
+        sum += h[i];
       }
-      S.sel_k = kk;
-      S.sel_prefix = prefix | (b << shift);
-      S.sel_mask = mask | (255u << shift);
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const unsigned excl = incl - sum, kk = (unsigned)S.sel_k;
+      const bool mine = kk >= excl && kk < incl;  // exactly one lane (k < n)
+      if (mine) {
+        unsigned rem = kk - excl, b = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (b == (unsigned)i && rem >= h[i]) {
+            rem -= h[i];
+            b = i + 1;
+          }
+        }
+        S.sel_k = (int)rem;
+        S.sel_prefix = prefix | ((unsigned)(lane * 8 + b) << shift);
+        S.sel_mask = mask | (255u << shift);
+      }
     }
     __syncthreads();
   }
