@@ -25,8 +25,18 @@ __global__ void cmvn_kernel(CmvnParams p) {
   float *out = p.out + (size_t)p.frame_offset[u] * p.dim;
   const double g0 = p.global_stats[d], g1 = p.global_stats[(p.dim + 1) + d], gcount = p.global_stats[p.dim];
   double s0 = 0.0, s1 = 0.0, cnt = 0.0;
+  constexpr int kPf = 8;  // frames fetched per batch: one exposed memory latency per 8 sequential updates
+  float xbuf[kPf];
   for (int t = 0; t < T; t++) {
-    double x = (double)in[(size_t)t * p.dim + d];
+    if ((t & (kPf - 1)) == 0) {
+#pragma unroll
+      for (int i = 0; i < kPf; i++) xbuf[i] = t + i < T ? in[(size_t)(t + i) * p.dim + d] : 0.f;
+    }
+    float xin_t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPf; i++)
+      if ((t & (kPf - 1)) == i) xin_t = xbuf[i];
+    double x = (double)xin_t;
     s0 += x;
     if (p.normalize_variance) s1 += x * x;
     cnt += 1.0;
@@ -49,7 +59,7 @@ __global__ void cmvn_kernel(CmvnParams p) {
         c += f * gcount;
       }
     }
-    float xin = in[(size_t)t * p.dim + d], y;
+    float xin = xin_t, y;
     if (!p.normalize_mean) {
       y = xin;
     } else if (!p.normalize_variance) {
@@ -96,22 +106,47 @@ __global__ void __launch_bounds__(256) splice_lda_kernel(IvecParams p) {
   }
   __syncthreads();
   const int K = p.dim * (p.left + 1 + p.right);
-  for (int o = threadIdx.x; o < kLdaFrames * p.ldim; o += blockDim.x) {
-    int f = o / p.ldim, j = o - f * p.ldim;
-    if (t0 + f >= T) continue;
-    const float *xr = sraw + (size_t)f * p.dim, *xn = snorm + (size_t)f * p.dim;
-    float ar = 0.f, an = 0.f;
-    for (int k = 0; k < K; k++) {
-      float w = p.lda_t[(size_t)k * p.ldim + j];
-      ar = fmaf(w, xr[k], ar);
-      an = fmaf(w, xn[k], an);
+  // thread = (output column j, group of 4 frames): each LDA weight is loaded once and used for 4 frames x 2
+  // streams; the sum over k runs in ascending order exactly as before
+  for (int o = threadIdx.x; o < (kLdaFrames / 4) * p.ldim; o += blockDim.x) {
+    const int fg = o / p.ldim, j = o - fg * p.ldim;
+    const float *xr = sraw + (size_t)fg * 4 * p.dim, *xn = snorm + (size_t)fg * 4 * p.dim;
+    float ar[4] = {0.f, 0.f, 0.f, 0.f}, an[4] = {0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    if ((p.dim & 3) == 0) {  // 16-byte shared-memory reads along k (rows of the staged window stay 16-byte aligned)
+      for (; k + 4 <= K; k += 4) {
+        float w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __ldg(p.lda_t + (size_t)(k + i) * p.ldim + j);
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+          const float4 a = *reinterpret_cast<const float4 *>(xr + f * p.dim + k);
+          const float4 b = *reinterpret_cast<const float4 *>(xn + f * p.dim + k);
+          ar[f] = fmaf(w[3], a.w, fmaf(w[2], a.z, fmaf(w[1], a.y, fmaf(w[0], a.x, ar[f]))));
+          an[f] = fmaf(w[3], b.w, fmaf(w[2], b.z, fmaf(w[1], b.y, fmaf(w[0], b.x, an[f]))));
+        }
+      }
     }
-    if (p.lda_bias) {
-      ar += p.lda_bias[j];
-      an += p.lda_bias[j];
+    for (; k < K; k++) {
+      const float w = __ldg(p.lda_t + (size_t)k * p.ldim + j);
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        ar[f] = fmaf(w, xr[f * p.dim + k], ar[f]);
+        an[f] = fmaf(w, xn[f * p.dim + k], an[f]);
+      }
     }
-    p.x_raw[(base + t0 + f) * p.ldim + j] = ar;
-    p.x_norm[(base + t0 + f) * p.ldim + j] = an;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int t = t0 + fg * 4 + f;
+      if (t >= T) continue;
+      float r = ar[f], n = an[f];
+      if (p.lda_bias) {
+        r += p.lda_bias[j];
+        n += p.lda_bias[j];
+      }
+      p.x_raw[(base + t) * p.ldim + j] = r;
+      p.x_norm[(base + t) * p.ldim + j] = n;
+    }
   }
 }
 
