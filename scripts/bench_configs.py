@@ -1,0 +1,60 @@
+"""Extra measurements for the BASELINE configs that are parity cases rather than the bench line:
+config 3 (ARPA-shaped HCLG, batch 256, 10 % out-of-grammar audio) and config 4 (64 concurrent streams fed
+80 ms chunks, online schedule).  Prints one JSON line per config with the stage times of rs_timings."""
+import dataclasses, json, os, sys, tempfile, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rhasspy_speech_b200 import synth, _lib
+
+
+def run(name, dec, fn, audio_s, reps=4):
+    for _ in range(2):
+        hyp = fn()
+    ts, wall = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        hyp = fn()
+        wall.append(time.perf_counter() - t0)
+        ts.append(dec.timings())
+    t = {k: float(np.mean([x[k] for x in ts])) for k in ("h2d_ms", "feature_ms", "nnet_ms", "decode_ms", "total_ms")}
+    dev = t["feature_ms"] + t["nnet_ms"] + t["decode_ms"]
+    flags = {int(s): int((np.asarray(hyp.status) == s).sum()) for s in set(int(x) for x in hyp.status)}
+    print(json.dumps({"config": name, "audio_s": audio_s, "rtfx_device": audio_s / (dev / 1e3), "rtfx_e2e": audio_s / float(np.mean(wall)),
+                      "stages_ms": t, "status_counts": flags, "tokens_per_frame": ts[-1]["tokens_expanded"] / max(1, ts[-1]["frames_decoded"])}),
+          flush=True)
+
+
+def main():
+    tmp = tempfile.mkdtemp()
+    # config 3: zamia-like model, ARPA-shaped graph
+    spec = dataclasses.replace(synth.ZAMIA_LIKE, name="zamia_arpa", graph="arpa", vocab_size=2000, bigrams_per_word=20, eps_hops=2)
+    p = synth.write_model(os.path.join(tmp, "arpa"), spec)
+    utts = synth.make_utterances(256, seed=1234)
+    for i in range(0, 256, 10):
+        utts[i] = utts[i][::-1].copy()          # out-of-grammar audio: time-reversed
+    m = _lib.Model(p.final_mdl, p.online_conf, 0)
+    g = _lib.Graph(p.hclg, p.words_txt, 0)
+    dec = _lib.Decoder(m, g)
+    audio_s = sum(len(u) for u in utts) / 16000.0
+    run("3: ARPA-shaped HCLG (%d states, %d arcs), batch 256, 10%% reversed audio" % (g.num_states, g.num_arcs), dec,
+        lambda: dec.decode_pcm(utts), audio_s)
+    # config 4: 64 streams, 80 ms chunks, grammar graph, online schedule
+    p2 = synth.write_model(os.path.join(tmp, "gram"), synth.ZAMIA_LIKE)
+    m2 = _lib.Model(p2.final_mdl, p2.online_conf, 0)
+    g2 = _lib.Graph(p2.hclg, p2.words_txt, 0)
+    dec2 = _lib.Decoder(m2, g2)
+    utts64 = synth.make_utterances(64, seed=4321)
+    raws = [np.asarray(u, dtype="<i2").tobytes() for u in utts64]
+    streams = [dec2.open_stream() for _ in utts64]
+
+    def stream_pass():
+        for s, raw in zip(streams, raws):
+            for o in range(0, len(raw), 2560):
+                s.accept(raw[o:o + 2560])
+        return dec2.finish_streams(streams)
+    run("4: 64 streams x 80 ms chunks, online iVector schedule, grammar HCLG", dec2, stream_pass,
+        sum(len(u) for u in utts64) / 16000.0)
+
+
+if __name__ == "__main__":
+    main()
