@@ -21,6 +21,7 @@
 // and therefore the surviving token sets are bit-identical wherever the reference itself is
 // order-independent ("decoder semantics").
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 
 #include "engine.h"
@@ -317,6 +318,15 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     }
     __syncthreads();
     unsigned long long cnt_tokens = 0, cnt_arcs = 0, cnt_created = 0;  // thread 0 / per-thread partials
+    // optional phase timing (cfg.profile): thread 0 accumulates SM clocks between phase boundaries
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_last = clock64();
+    auto tick = [&](int k) {
+      if (cfg.profile && tid == 0) {
+        const long long now = clock64();
+        ph[k] += now - ph_last;
+        ph_last = now;
+      }
+    };
     int status = 0;
     int info = 0;  // bit 16: --max-active decided the beam on some frame (see rs_result.status)
     int cur = 0;
@@ -386,6 +396,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       }
       __syncthreads();
       if (S.overflow) return -1;
+      tick(3);
       // ---- compact the alive entries (cost < cutoff)
       const int n_ins = S.n_ins[tb];
       unsigned running = 0;
@@ -415,6 +426,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       __syncthreads();
       const int n_new = (int)running;
       if (base_new + n_new > cfg.arena_cap) return -2;
+      tick(4);
       // ---- traceback records: the arc stored with the winning cost names the predecessor state
       for (int pos = tid; pos < n_new; pos += NT) {
         int s = ws.tok_slot[pos];
@@ -432,6 +444,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         ws.arena[base_new + pos] = make_int2(prev, (int)arc);
       }
       __syncthreads();
+      tick(5);
       return n_new;
     };
     auto clear_table = [&](int tb) {
@@ -539,6 +552,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           }
         }
       }
+      tick(0);
       // ---- ProcessEmitting (:714-804)
       const float cost_offset = -best;
       if (warp == 0) {  // seed next_cutoff from the best token's arcs (:744-759)
@@ -569,6 +583,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       }
       if (tid == 0) ws.pfx[n_cur] = n_arcs;
       __syncthreads();
+      tick(1);
       {
         Table T{ws.hkey[nxt], ws.hval[nxt], ws.hidx[nxt], ws.ins_list[nxt], &S.n_ins[nxt]};
         volatile unsigned *nc = &S.nc_ord;
@@ -597,6 +612,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         status |= 1;
         break;
       }
+      tick(2);
       const float next_cutoff = unord(S.nc_ord);
       cnt_tokens += n_cur;
       cnt_arcs += (tid == 0) ? n_arcs : 0;
@@ -607,6 +623,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         break;
       }
       clear_table(cur);
+      tick(6);
       base_cur = base_new;
       n_cur = r;
       arena_n = base_new + r;
@@ -614,6 +631,9 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       cur = nxt;
     }
 
+    if (cfg.profile && tid == 0 && blockIdx.x == 0)
+      printf("decode phases (clocks, utt %d, %d frames): cutoff %lld seed+prefix %lld expand %lld epsilon %lld compact %lld records %lld clear %lld\n", u,
+             n_frames, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
     // ---- best path (lattice-faster-online-decoder.cc:78-173)
     int n_words = -1;
     if (status == 0 && n_cur == 0) status |= 4;

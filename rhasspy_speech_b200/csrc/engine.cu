@@ -816,6 +816,7 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   p.cfg.hash_size = hash_size;
   p.cfg.arena_cap = o.max_tokens_per_utt;
   p.cfg.max_words = W;
+  p.cfg.profile = getenv("RS_B200_DECODE_PROFILE") != nullptr;
   {
     // shared-memory tables when the graph is small enough for two lanes per SM (<= 1024 states)
     int slots = 64;
@@ -1025,7 +1026,12 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
       if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
   };
   const bool pooled = n_items > 1;
-  if (pooled && !d->pool) d->pool.reset(new PackPool((int)std::min(6u, std::max(1u, std::thread::hardware_concurrency() - 1))));
+  if (pooled && !d->pool) {
+    // RS_B200_PACK_THREADS: worker threads of the staging pool (default: up to 6, leaving one core to the caller)
+    int nt = (int)std::min(6u, std::max(2u, std::thread::hardware_concurrency()) - 1);
+    if (const char *e = getenv("RS_B200_PACK_THREADS")) nt = std::max(1, std::min(32, atoi(e)));
+    d->pool.reset(new PackPool(nt));
+  }
   struct PoolGuard {  // an error path must not leave workers running on this frame's captures
     PackPool *p;
     ~PoolGuard() {

@@ -160,6 +160,7 @@ struct DecodeConfig {
   int hash_size;    // power of two >= 2 * tok_cap ; identity addressing if num_states <= hash_size
   int arena_cap;    // max tokens per utterance (traceback records)
   int max_words;
+  int profile;      // debug: block 0 prints its per-phase clock counts (RS_B200_DECODE_PROFILE=1)
   int smem_slots;   // > 0: state tables in shared memory, addressed by state id (power of two >= num_states)
 };
 
