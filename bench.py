@@ -182,7 +182,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     # host staging threads per rank: share the box's cores between the ranks
-    os.environ.setdefault("RS_B200_PACK_THREADS", str(max(1, min(6, (os.cpu_count() or 8) // max(world, 1) - 1))))
+    os.environ.setdefault("RS_B200_PACK_THREADS", str(max(1, min(3, (os.cpu_count() or 8) // max(world, 1) - 1))))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as g

@@ -145,6 +145,13 @@ def debug_gemm(src: np.ndarray, w: np.ndarray, offsets: Sequence[int] = (0,), st
     return out, ms.value
 
 
+def _address(a: np.ndarray) -> int:
+    """Address of a contiguous array's data (from_buffer is ~2x cheaper than ndarray.ctypes.data)."""
+    if a.size and a.flags.writeable:
+        return C.addressof(C.c_char.from_buffer(a))
+    return a.ctypes.data
+
+
 class Hypotheses:
     """Python copy of an rs_result."""
 
@@ -153,9 +160,11 @@ class Hypotheses:
         self.n_utts = n
 
         def arr(ptr, count):
+            dt = np.dtype(ptr._type_)
             if count <= 0 or not ptr:
-                return np.zeros(0, dtype=np.ctypeslib.as_array((ptr._type_ * 1)()).dtype)
-            return np.ctypeslib.as_array(ptr, shape=(count,)).copy()
+                return np.zeros(0, dtype=dt)
+            # one memcpy out of the library's buffer (np.ctypeslib.as_array costs ~0.1 ms per call)
+            return np.frombuffer(C.string_at(ptr, count * dt.itemsize), dtype=dt)
 
         off = arr(r.word_offset, n + 1) if n else np.zeros(1, np.int32)
         ids = arr(r.word_ids, int(off[-1]))
@@ -239,7 +248,7 @@ class Decoder:
     def decode_pcm(self, pcm: Sequence[np.ndarray]) -> Hypotheses:
         arrs = [np.ascontiguousarray(p, dtype=np.int16) for p in pcm]
         n = len(arrs)
-        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        ptrs = (C.c_void_p * max(n, 1))(*[_address(a) for a in arrs])
         ns = (C.c_int32 * max(n, 1))(*[a.size for a in arrs])
         res = C.POINTER(Result)()
         err = C.create_string_buffer(ERRLEN)

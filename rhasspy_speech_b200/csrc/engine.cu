@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -939,6 +940,9 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   if (n < 0) RS_FAIL("negative batch size");
   d->last = rs_timings{};
   if (n == 0) return NewResult(0);
+  const bool host_prof = getenv("RS_B200_HOST_PROFILE") != nullptr;
+  auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double hp0 = now_ms();
   for (int i = 0; i < n; i++)
     if (nsamp[i] < 0 || (nsamp[i] > 0 && !pcm[i])) RS_FAIL("utterance " << i << ": bad sample buffer");
   const int sf = m.frame_subsampling_factor, D = m.mfcc.num_ceps;
@@ -1008,7 +1012,8 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   int16_t *hpcm = (int16_t *)hin;
   // Staging is split into items of ~2 MB packed by a small persistent thread pool; each item goes to
   // the device as soon as it is complete, so the H2D copies overlap the packing of the later items.
-  int n_items = (int)std::min<size_t>(std::max<size_t>(pcm_bytes >> 21, 1), 64);
+  static const int item_shift = getenv("RS_B200_PACK_ITEM_SHIFT") ? atoi(getenv("RS_B200_PACK_ITEM_SHIFT")) : 21;
+  int n_items = (int)std::min<size_t>(std::max<size_t>(pcm_bytes >> item_shift, 1), 64);
   if (n_items > n) n_items = n;
   std::vector<int> range_begin(n_items + 1, n);
   {
@@ -1027,8 +1032,9 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   };
   const bool pooled = n_items > 1;
   if (pooled && !d->pool) {
-    // RS_B200_PACK_THREADS: worker threads of the staging pool (default: up to 6, leaving one core to the caller)
-    int nt = (int)std::min(6u, std::max(2u, std::thread::hardware_concurrency()) - 1);
+    // RS_B200_PACK_THREADS: worker threads of the staging pool; the caller's thread packs too.  Measured on the
+    // 16-core B200 host: 3-4 workers are the optimum (1.3 ms for 33 MB), 6 and more are slower (1.8-2.9 ms)
+    int nt = (int)std::min(3u, std::max(2u, std::thread::hardware_concurrency()) - 1);
     if (const char *e = getenv("RS_B200_PACK_THREADS")) nt = std::max(1, std::min(32, atoi(e)));
     d->pool.reset(new PackPool(nt));
   }
@@ -1082,6 +1088,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
       CUDA_OK(cudaMemcpyAsync(dpcm + s0, hpcm + s0, sizeof(int16_t) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, d->stream));
   }
   CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  const double hp1 = now_ms();
   d->last.h2d_bytes = pcm_bytes + desc_ints * sizeof(int);
   const int64_t *d_pcm_off = (const int64_t *)ddesc;
   int *d_nf = ddesc + 2 * n, *d_fo = d_nf + n, *d_or = d_fo + n, *d_no = d_or + n, *d_r0 = d_no + n, *d_ru = d_r0 + n;
@@ -1325,8 +1332,12 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   // ---- stage (iii)
   B.loglikes = slot_ptr(pl.output_buffer);
   B.ll_ld = buf_ld(pl.output_buffer);
+  const double hp2 = now_ms();
   rs_result *r = RunDecodeStage(d, B.loglikes, B.ll_ld, d_r0, d_no, launches);
   FinishTimings(d, launches);
+  if (host_prof)
+    fprintf(stderr, "host ms: layout+pack+h2d issue %.3f | feature+nnet launches %.3f | decode launch+wait+result %.3f\n", hp1 - hp0,
+            hp2 - hp1, now_ms() - hp2);
   if (*d->h_range_flag) {
     rs_result_free(r);
     RS_FAIL("an activation exceeded the fp16 range (+-65504) of the tensor-core path; set RS_B200_GEMM=simt for this model");
