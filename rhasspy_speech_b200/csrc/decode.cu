@@ -43,7 +43,7 @@ int DecodeCtaThreads() {
   if (g_decode_threads == 0) {
     const char *e = getenv("RS_B200_DECODE_THREADS");
     int v = e ? atoi(e) : 512;
-    if (v != 128 && v != 256 && v != 512) v = 512;
+    if (v != 32 && v != 64 && v != 128 && v != 256 && v != 512) v = 512;
     g_decode_threads = v;
   }
   return g_decode_threads;

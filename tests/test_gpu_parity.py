@@ -183,6 +183,9 @@ def test_arpa_graph_with_out_of_grammar_audio(lib, ref, synth, utterances, tmp_p
     t = dec.timings()
     assert t["tokens_expanded"] > 20 * t["frames_decoded"]
     _check_transcripts(lib, ref, synth, p, utts, tmp_path, beam=12.0)
+    # fewer table slots than graph states: the open-addressing (hashed) path of the state tables
+    dec_h, got_h, _ = _check_transcripts(lib, ref, synth, p, utts, tmp_path, beam=9.0, max_tokens_per_frame=2048)
+    assert dec_h.graph.num_states > 2 * 2048 and all(st == 0 for st in got_h.status)
     # A binding --max-active: the cutoff VALUE is reproduced (radix select == nth_element), but the
     # reference's token list also holds the order-dependent tokens its transient next_cutoff let through
     # (lattice-faster-decoder.cc:780-787); they change `toks.size() > max_active` and, under the then
