@@ -178,9 +178,34 @@ struct LaneWorkspace {  // one per resident CTA; all pointers are device memory
   int2 *arena;       // {prev token gid, arc id}
 };
 
+// State-level lattice of one batch (GetRawLattice, lattice-faster-decoder.cc:106-189): written by
+// decode_kernel<true>, pruned by lattice_prune_kernel, compacted by lattice_emit_kernel.
+// Token time t = 0 .. n_frames (t = 0: closure of the start state); utterance u owns the slices
+// tok[u * tok_cap ..], link[u * link_cap ..], tok_base[u * (max_t + 2) ..], link_pos[u * (2 * max_t + 4) ..].
+struct LatticeBuf {
+  int2 *tok;           // {state, forward cost bits} per token, in arena order (time-major)
+  float *extra;        // extra_cost per token (>= 0, +inf = pruned)
+  int *newid;          // compact node id of the surviving tokens
+  int4 *link;          // {source token, destination token, arc id, link_extra bits (>=0) or -1 = pruned}
+  int *tok_base;       // [max_t + 2] first token of each time; [n_frames + 1] = token count
+  int *link_pos;       // [2 * max_t + 4]: [2t] start of the emitting links (t-1 -> t), [2t+1] start of the epsilon links at t
+  float *cost_offset;  // [max_t + 1] offset added to the acoustic costs of the frame leaving time t (:733)
+  int tok_cap, link_cap, max_t;
+};
+
+// compact lattice as the host receives it: one header per utterance, then its arcs in `arcs`
+struct LatticeHeader {
+  int arc_begin, n_arcs, n_nodes, ok;
+};
+struct LatticeArc {  // dst == -1: final weight of src (graph = final cost, acoustic = 0)
+  int src, dst, olabel;
+  float graph, acoustic;
+};
+
 struct DecodeParams {
   DevGraph g;
   DecodeConfig cfg;
+  LatticeBuf lat;         // only read by the lattice instantiation
   const float *loglikes;  // [rows, ld]
   int ld;
   const int *ll_row0;     // [n_utts] first row of each utterance
@@ -195,7 +220,11 @@ struct DecodeParams {
   int *status;            // [n_utts] 0 ok, bit0 token overflow, bit1 arena overflow, bit2 no tokens, bit3 word overflow
   unsigned long long *counters;  // [n_utts, 4] tokens expanded, arcs visited, tokens created, records written
 };
-void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream);
+void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream, bool lattice = false);
+// a20: PruneForwardLinksFinal / PruneForwardLinks (lattice-faster-decoder.cc:299-458) over the recorded lattice,
+// then renumbering + compaction of the surviving arcs into `arcs` (global cursor `cursor`), one CTA per utterance
+void LaunchLatticePrune(const DecodeParams &p, float lattice_beam, LatticeHeader *headers, LatticeArc *arcs,
+                        int arcs_cap, int *cursor, cudaStream_t stream);
 int DecodeCtaThreads();
 size_t DecodeSmemBytes(int slots);
 
