@@ -36,7 +36,7 @@ typedef struct rs_decoder_opts {
   float beam;           /* --beam            (24.0) */
   int32_t max_active;   /* --max-active      (7000) */
   int32_t min_active;   /* --min-active      (200)  */
-  float lattice_beam;   /* --lattice-beam    (8.0); lattice output is a "next" row, kept for the surface */
+  float lattice_beam;   /* --lattice-beam    (8.0); prunes the lattice the n-best tail reads (rs_decoder_set_nbest) */
   float acoustic_scale; /* --acoustic-scale  (1.0; rhasspy always passes 1.0 to the decoder) */
   float beam_delta;     /* --beam-delta      (0.5)  */
   int32_t max_tokens_per_frame; /* device capacity per lane and frame (65536) */
@@ -48,16 +48,25 @@ typedef struct rs_decoder_opts {
 
 typedef struct rs_result {
   int32_t n_utts;
-  int32_t *n_hyp;        /* [n_utts] hypotheses per utterance: 0 (nothing decoded) or 1 */
+  int32_t *n_hyp;        /* [n_utts] hypotheses per utterance: 0 (nothing decoded) .. nbest */
   int32_t *word_offset;  /* [n_utts + 1] into word_ids */
   int32_t *word_ids;     /* olabels of the best path, in order (words.txt ids) */
-  float *graph_cost;     /* [n_utts] */
-  float *acoustic_cost;  /* [n_utts] */
+  float *graph_cost;     /* [n_utts] of the best path */
+  float *acoustic_cost;  /* [n_utts] of the best path */
   int32_t *num_frames;   /* [n_utts] decoded (subsampled) frames */
   int32_t *status;       /* [n_utts] 0 ok; errors: bit0 token capacity, bit1 arena capacity, bit2 no surviving tokens,
                           * bit3 word capacity; information: bit4 (16) --max-active limited the beam on some frame:
                           * the reference's pruning is then order-dependent (lattice-faster-decoder.cc:780-787) and the
-                          * hypothesis, although found with the same cutoff values, is not guaranteed word-identical */
+                          * hypothesis, although found with the same cutoff values, is not guaranteed word-identical;
+                          * bit5 (32) n-best requested but the lattice did not fit its device buffers: only the best path
+                          * is returned */
+  /* every hypothesis, best first (what lattice-to-nbest | nbest-to-linear print as utt-1 .. utt-n and the two
+   * cost archives of nbest-to-linear): hypothesis h of utterance u is entry hyp_offset[u] + h */
+  int32_t *hyp_offset;       /* [n_utts + 1] */
+  int32_t *hyp_word_offset;  /* [hyp_offset[n_utts] + 1] into hyp_word_ids */
+  int32_t *hyp_word_ids;
+  float *hyp_graph_cost;     /* [hyp_offset[n_utts]] */
+  float *hyp_acoustic_cost;  /* [hyp_offset[n_utts]] unscaled */
 } rs_result;
 
 typedef struct rs_timings {
@@ -68,6 +77,9 @@ typedef struct rs_timings {
   uint64_t h2d_bytes, d2h_bytes;
   int32_t kernel_launches;
   uint64_t nnet_bytes;    /* algorithmic HBM bytes of the acoustic model: every layer input once, bypass input, output */
+  uint64_t lattice_states, lattice_arcs; /* n-best calls: states and arcs (final weights included) of the pruned
+                                          * state-level lattices of the batch -- what GetRawLattice would return */
+  uint64_t lattice_links_recorded;       /* forward links recorded before pruning */
 } rs_timings;
 
 void rs_decoder_opts_default(rs_decoder_opts *opts);
@@ -89,6 +101,13 @@ const char *rs_graph_word(const rs_graph *g, int32_t id);
 
 rs_decoder *rs_decoder_create(rs_model *m, rs_graph *g, const rs_decoder_opts *opts, char *err, size_t errlen);
 void rs_decoder_free(rs_decoder *d);
+/* Replaces the `lattice-to-nbest --n=<nbest> --acoustic-scale=<acoustic_scale>` stage of the pipeline
+ * (transcribe_wav.py:62-75, kaldi/src/latbin/lattice-to-nbest.cc:84-113) for every later decode call on this
+ * decoder.  nbest == 1 with scale 1.0 (the default) returns the device back-trace of the best path; anything
+ * else records the state-level lattice on the device (GetRawLattice, lattice-faster-decoder.cc:106-189), prunes
+ * it with --lattice-beam (:299-458) and returns the n cheapest distinct word sequences under
+ * graph + acoustic_scale * acoustic, each with the costs of its best path. */
+int rs_decoder_set_nbest(rs_decoder *d, int32_t nbest, float acoustic_scale, char *err, size_t errlen);
 
 /* Replaces one run of `online2-wav-nnet3-latgen-faster --online=false ... | lattice-to-nbest --n=1 |
  * nbest-to-linear` per utterance (transcribe_wav.py:45-75), for n utterances at once.
@@ -121,7 +140,9 @@ int rs_streams_finish(rs_stream *const *streams, int32_t n, rs_result **out, cha
 int rs_decoder_timings(const rs_decoder *d, rs_timings *t);
 /* Intermediate results of the last rs_decode_pcm / rs_decode_wavs call, for the parity tests:
  * what = 0 MFCC [T x dim], 1 iVector [solves x dim] (1 row offline, one per CG solve online), 2 log-likelihoods [T/sf x num_pdfs],
- *        3 CMVN-normalised MFCC, 4 LDA features (normalised stream).
+ *        3 CMVN-normalised MFCC, 4 LDA features (normalised stream),
+ *        5 (after an n-best call) the pruned state-level lattice: rows of (src, dst, olabel, graph cost, acoustic cost),
+ *          dst = -1 marks a final weight, state 0 is the start.
  * Call with dst == NULL to query rows/cols. */
 int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t *rows, int32_t *cols, char *err,
                    size_t errlen);
@@ -135,6 +156,13 @@ int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t
 int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offsets, int n_offsets, int stride,
                   const float *w, int n, const float *bias, int relu, int path, int iters, float *out, float *ms,
                   char *err, size_t errlen);
+/* Test hook for the host half of the n-best tail: n-best of a caller-provided state-level lattice (arcs
+ * src/dst/olabel/graph/acoustic; dst == -1 marks a final weight; node 0 is the start; node ids ascend with time).
+ * Fills up to n hypotheses: words into word_ids (capacity max_words in total) delimited by word_offset[n + 1],
+ * costs into cost[2 * n] (graph, acoustic).  Returns the number of hypotheses, < 0 on error. */
+int rs_debug_lattice_nbest(const int32_t *src, const int32_t *dst, const int32_t *olabel, const float *graph,
+                           const float *acoustic, int32_t n_arcs, int32_t n_nodes, int32_t n, float acoustic_scale,
+                           int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost);
 /* Text description of the compiled acoustic-model plan (one line per launch). */
 const char *rs_model_plan(const rs_model *m);
 

@@ -237,3 +237,65 @@ def decode_loglikes(final_mdl: str, hclg: str, loglikes: Sequence[np.ndarray], b
                      "nbest-to-linear ark:- ark:/dev/null ark,t:- 2>/dev/null"
                      % (beam, max_active, min_active, lattice_beam, final_mdl, hclg, tmp, nbest))
     return parse_int_ark_text(out)
+
+
+def parse_lattice_text(text: str) -> Dict[str, dict]:
+    """Text Lattice archive (kaldi/src/lat/kaldi-lattice.cc WriteLattice: key line, OpenFst text with
+    'graph,acoustic' weights, blank line) -> {key: {src, dst, ilabel, olabel, graph, acoustic, n_states}};
+    final weights are rows with dst == -1."""
+    out: Dict[str, dict] = {}
+    key = None
+    rows: List[tuple] = []
+
+    def weight(tok):
+        g, a = tok.split(",")
+        return float(g), float(a)
+
+    def flush():
+        if key is None:
+            return
+        a = np.array(rows, dtype=np.float64).reshape(-1, 6)
+        n_states = int(max(a[:, 0].max(), a[:, 1].max())) + 1 if len(a) else 0
+        out[key] = dict(src=a[:, 0].astype(np.int32), dst=a[:, 1].astype(np.int32), ilabel=a[:, 2].astype(np.int32),
+                        olabel=a[:, 3].astype(np.int32), graph=a[:, 4].astype(np.float32),
+                        acoustic=a[:, 5].astype(np.float32), n_states=n_states)
+    for line in text.splitlines():
+        parts = line.split()
+        if not parts:
+            flush()
+            key, rows = None, []
+            continue
+        if key is None:
+            key = parts[0]
+            continue
+        if len(parts) >= 4:      # arc: src dst ilabel olabel [weight]
+            g, a = weight(parts[4]) if len(parts) > 4 else (0.0, 0.0)
+            rows.append((int(parts[0]), int(parts[1]), int(parts[2]), int(parts[3]), g, a))
+        else:                    # final: state [weight]
+            g, a = weight(parts[1]) if len(parts) > 1 else (0.0, 0.0)
+            rows.append((int(parts[0]), -1, 0, 0, g, a))
+    flush()
+    return out
+
+
+def decode_loglikes_lattice(final_mdl: str, hclg: str, loglikes: Sequence[np.ndarray], nbest: int, beam: float = 24.0,
+                            max_active: int = 7000, min_active: int = 200, lattice_beam: float = 8.0,
+                            acoustic_scale: float = 1.0):
+    """latgen-faster-mapped twice on the same log-likelihoods: (a) --determinize-lattice=false, the raw state-level
+    lattice (GetRawLattice after FinalizeDecoding) as text; (b) the determinised lattice through
+    lattice-to-nbest --n | nbest-to-linear with both cost archives.
+    Returns ({key: raw lattice}, {key-k: (words, graph cost, acoustic cost)})."""
+    with tempfile.TemporaryDirectory() as tmp:
+        keys = ["utt%05d" % i for i in range(len(loglikes))]
+        write_mat_ark(os.path.join(tmp, "ll.ark"), dict(zip(keys, loglikes)))
+        common = ("latgen-faster-mapped --acoustic-scale=1.0 --beam=%g --max-active=%d --min-active=%d --lattice-beam=%g "
+                  "--allow-partial=true" % (beam, max_active, min_active, lattice_beam))
+        raw, _ = run("%s --determinize-lattice=false %s %s ark:%s/ll.ark ark,t:- 2>/dev/null" % (common, final_mdl, hclg, tmp))
+        run("%s %s %s ark:%s/ll.ark ark:- 2>/dev/null | lattice-to-nbest --n=%d --acoustic-scale=%g ark:- ark:- 2>/dev/null | "
+            "nbest-to-linear ark:- ark:/dev/null ark,t:%s/tr.txt ark,t:%s/lm.txt ark,t:%s/ac.txt 2>/dev/null"
+            % (common, final_mdl, hclg, tmp, nbest, acoustic_scale, tmp, tmp, tmp))
+        with open(os.path.join(tmp, "tr.txt"), "rb") as f:
+            words = parse_int_ark_text(f.read())
+        lm = {l.split()[0]: float(l.split()[1]) for l in open(os.path.join(tmp, "lm.txt")) if l.strip()}
+        ac = {l.split()[0]: float(l.split()[1]) for l in open(os.path.join(tmp, "ac.txt")) if l.strip()}
+    return parse_lattice_text(raw.decode()), {k: (words[k], lm[k], ac[k]) for k in words}

@@ -29,7 +29,9 @@ class Result(C.Structure):
     _fields_ = [("n_utts", C.c_int32), ("n_hyp", C.POINTER(C.c_int32)), ("word_offset", C.POINTER(C.c_int32)),
                 ("word_ids", C.POINTER(C.c_int32)), ("graph_cost", C.POINTER(C.c_float)),
                 ("acoustic_cost", C.POINTER(C.c_float)), ("num_frames", C.POINTER(C.c_int32)),
-                ("status", C.POINTER(C.c_int32))]
+                ("status", C.POINTER(C.c_int32)), ("hyp_offset", C.POINTER(C.c_int32)),
+                ("hyp_word_offset", C.POINTER(C.c_int32)), ("hyp_word_ids", C.POINTER(C.c_int32)),
+                ("hyp_graph_cost", C.POINTER(C.c_float)), ("hyp_acoustic_cost", C.POINTER(C.c_float))]
 
 
 class Timings(C.Structure):
@@ -38,7 +40,8 @@ class Timings(C.Structure):
                 ("frames_decoded", C.c_uint64), ("tokens_expanded", C.c_uint64), ("arcs_visited", C.c_uint64),
                 ("tokens_created", C.c_uint64), ("records_written", C.c_uint64), ("nnet_flops", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32),
-                ("nnet_bytes", C.c_uint64)]
+                ("nnet_bytes", C.c_uint64), ("lattice_states", C.c_uint64), ("lattice_arcs", C.c_uint64),
+                ("lattice_links_recorded", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,6 +61,8 @@ SYMBOLS = [
     ("rs_graph_word", C.c_char_p, [_P, C.c_int32]),
     ("rs_decoder_create", _P, [_P, _P, C.POINTER(DecoderOpts)] + _ERR),
     ("rs_decoder_free", None, [_P]),
+    ("rs_decoder_set_nbest", C.c_int, [_P, C.c_int32, C.c_float] + _ERR),
+    ("rs_debug_lattice_nbest", C.c_int, [_P] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, _P]),
     ("rs_decode_pcm", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
     ("rs_decode_wavs", C.c_int, [_P, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
     ("rs_decode_loglikes", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
@@ -145,6 +150,24 @@ def debug_gemm(src: np.ndarray, w: np.ndarray, offsets: Sequence[int] = (0,), st
     return out, ms.value
 
 
+def lattice_nbest(src, dst, olabel, graph, acoustic, n_nodes: int, n: int, acoustic_scale: float = 1.0):
+    """Host half of the n-best tail on a caller-provided state-level lattice (rs_debug_lattice_nbest):
+    returns [(word ids, graph cost, acoustic cost), ...], best first."""
+    lib = load_library()
+    src, dst, olabel = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, olabel)]
+    graph, acoustic = [np.ascontiguousarray(a, dtype=np.float32) for a in (graph, acoustic)]
+    max_words = 4096 * n
+    woff = np.zeros(n + 1, np.int32)
+    wid = np.zeros(max_words, np.int32)
+    cost = np.zeros(2 * n, np.float32)
+    k = lib.rs_debug_lattice_nbest(src.ctypes.data, dst.ctypes.data, olabel.ctypes.data, graph.ctypes.data,
+                                   acoustic.ctypes.data, len(src), n_nodes, n, acoustic_scale, woff.ctypes.data,
+                                   wid.ctypes.data, max_words, cost.ctypes.data)
+    if k < 0:
+        raise RsError("rs_debug_lattice_nbest failed (%d)" % k)
+    return [([int(x) for x in wid[woff[h]:woff[h + 1]]], float(cost[2 * h]), float(cost[2 * h + 1])) for h in range(k)]
+
+
 def _address(a: np.ndarray) -> int:
     """Address of a contiguous array's data (from_buffer is ~2x cheaper than ndarray.ctypes.data)."""
     if a.size and a.flags.writeable:
@@ -176,6 +199,21 @@ class Hypotheses:
         self.acoustic_cost = arr(r.acoustic_cost, n)
         self.num_frames = arr(r.num_frames, n)
         self.status = arr(r.status, n)
+        # every hypothesis, best first: nbest[u] = [(word ids, graph cost, acoustic cost), ...]
+        self.nbest: List[List[tuple]] = [[] for _ in range(n)]
+        if n and self.n_hyp.max(initial=0) > 1:
+            ho = arr(r.hyp_offset, n + 1)
+            total = int(ho[-1])
+            wo = arr(r.hyp_word_offset, total + 1)
+            wid = arr(r.hyp_word_ids, int(wo[-1]) if total else 0)
+            gc, ac = arr(r.hyp_graph_cost, total), arr(r.hyp_acoustic_cost, total)
+            for u in range(n):
+                self.nbest[u] = [([int(x) for x in wid[wo[h]:wo[h + 1]]], float(gc[h]), float(ac[h]))
+                                 for h in range(int(ho[u]), int(ho[u + 1]))]
+        else:
+            for u in range(n):
+                if self.n_hyp[u]:
+                    self.nbest[u] = [(self.words[u], float(self.graph_cost[u]), float(self.acoustic_cost[u]))]
 
 
 class Model:
@@ -237,6 +275,12 @@ class Decoder:
         err = C.create_string_buffer(ERRLEN)
         self.h = self.lib.rs_decoder_create(model.h, graph.h, C.byref(o), err, ERRLEN)
         _check(bool(self.h), err)
+
+    def set_nbest(self, nbest: int = 1, acoustic_scale: float = 1.0):
+        """lattice-to-nbest --n / --acoustic-scale for every later decode call (rs_decoder_set_nbest)."""
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_decoder_set_nbest(self.h, int(nbest), float(acoustic_scale), err, ERRLEN)
+        _check(rc == 0, err)
 
     def _take(self, rc: int, res, err) -> Hypotheses:
         _check(rc == 0, err)

@@ -78,6 +78,8 @@ struct Shared {
   float best_cost;
   int best_idx;
   int any_final;
+  int n_links;       // lattice mode: links recorded so far for the utterance
+  int lat_overflow;  // lattice mode: link capacity exceeded
 };
 
 __device__ __forceinline__ unsigned block_excl_scan(unsigned v, Shared &S, unsigned *total) {
@@ -244,6 +246,9 @@ __device__ __forceinline__ int insert_slot(const Table &t, int state, unsigned m
   }
 }
 
+// kLat = true additionally records the state-level lattice (every token with its forward cost, every
+// forward link the reference would hold after ProcessEmitting / ProcessNonemitting) for the n-best tail.
+template <bool kLat>
 __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant__ DecodeParams P) {
   __shared__ Shared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -315,8 +320,31 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       S.n_ins[0] = S.n_ins[1] = 0;
       S.frontier_n[0] = S.frontier_n[1] = 0;
       S.overflow = 0;
+      S.n_links = 0;
+      S.lat_overflow = 0;
     }
     __syncthreads();
+    // lattice slices of this utterance (LatticeBuf)
+    int2 *ltok = nullptr;
+    int4 *llink = nullptr;
+    int *ltb = nullptr, *lpos = nullptr;
+    float *loff = nullptr;
+    int arena_cap = cfg.arena_cap;
+    if constexpr (kLat) {
+      ltok = P.lat.tok + (size_t)u * P.lat.tok_cap;
+      llink = P.lat.link + (size_t)u * P.lat.link_cap;
+      ltb = P.lat.tok_base + (size_t)u * (P.lat.max_t + 2);
+      lpos = P.lat.link_pos + (size_t)u * (2 * P.lat.max_t + 4);
+      loff = P.lat.cost_offset + (size_t)u * (P.lat.max_t + 1);
+      arena_cap = min(arena_cap, P.lat.tok_cap);
+    }
+    auto add_link = [&](int src, int dst, unsigned arc) {
+      const int li = atomicAdd(&S.n_links, 1);
+      if (li < P.lat.link_cap)
+        llink[li] = make_int4(src, dst, (int)arc, 0);
+      else
+        S.lat_overflow = 1;
+    };
     unsigned long long cnt_tokens = 0, cnt_arcs = 0, cnt_created = 0;  // thread 0 / per-thread partials
     // optional phase timing (cfg.profile): thread 0 accumulates SM clocks between phase boundaries
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_last = clock64();
@@ -425,7 +453,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       }
       __syncthreads();
       const int n_new = (int)running;
-      if (base_new + n_new > cfg.arena_cap) return -2;
+      if (base_new + n_new > arena_cap) return -2;
       tick(4);
       // ---- traceback records: the arc stored with the winning cost names the predecessor state
       for (int pos = tid; pos < n_new; pos += NT) {
@@ -442,10 +470,29 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           prev = ss >= 0 ? base_new + T.hidx[ss] : -1;
         }
         ws.arena[base_new + pos] = make_int2(prev, (int)arc);
+        if constexpr (kLat) ltok[base_new + pos] = make_int2(ws.tok_state[tb][pos], __float_as_int(ws.tok_cost[tb][pos]));
       }
       __syncthreads();
       tick(5);
       return n_new;
+    };
+    // Lattice mode: the epsilon links of the finalised time (ProcessNonemitting :858-884 recreates the links
+    // of a token from its final cost: every epsilon arc with tot_cost < cutoff), then the positions
+    auto eps_links = [&](int tb, float cutoff, int base_new, int n_new) {
+      for (int pos = tid; pos < n_new; pos += NT) {
+        const int st = ws.tok_state[tb][pos];
+        const float c = ws.tok_cost[tb][pos];
+        for (unsigned a = g.p_begin[st]; a < g.p_begin[st + 1]; a++) {
+          const int4 arc = g.parc[a];
+          const float tot = __fadd_rn(c, __int_as_float(arc.z));
+          if (tot < cutoff) {
+            const int ss = find_slot(ws.hkey[tb], arc.x, mask, identity);
+            const int dpos = ss >= 0 ? ws.hidx[tb][ss] : -1;
+            if (dpos >= 0) add_link(base_new + pos, base_new + dpos, NE + a);
+          }
+        }
+      }
+      __syncthreads();
     };
     auto clear_table = [&](int tb) {
       const int n_ins = min(S.n_ins[tb], tok_cap);
@@ -490,6 +537,11 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         n_cur = r;
         arena_n = r;
         cnt_created += r;
+        if constexpr (kLat) {
+          if (tid == 0) ltb[0] = lpos[0] = lpos[1] = 0;
+          eps_links(0, cfg.beam, 0, r);
+          if (tid == 0) lpos[2] = S.n_links;
+        }
       }
     }
 
@@ -622,6 +674,41 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         status |= (r == -1 ? 1 : 2);
         break;
       }
+      if constexpr (kLat) {
+        // emitting links time frame -> frame + 1: every arc whose cost passed the frame's final next_cutoff
+        // (the reference's transient cutoff lets more through; those lie beyond the beam and never survive
+        // the lattice-beam pruning), then the epsilon links of the new time
+        for (unsigned a = tid; a < n_arcs; a += NT) {
+          int lo = 0, hi = n_cur;
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (ws.pfx[mid] <= a) lo = mid; else hi = mid;
+          }
+          const int st = state[lo];
+          const unsigned ai = g.e_begin[st] + (a - ws.pfx[lo]);
+          const int4 arc = g.earc[ai];
+          const float ac = __fsub_rn(cost_offset, ll[arc.y]);
+          const float tot = __fadd_rn(__fadd_rn(cost[lo], ac), __int_as_float(arc.z));
+          if (tot < next_cutoff) {
+            const int ss = find_slot(ws.hkey[nxt], arc.x, mask, identity);
+            const int dpos = ss >= 0 ? ws.hidx[nxt][ss] : -1;
+            if (dpos >= 0) add_link(base_cur + lo, base_new + dpos, ai);
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          lpos[2 * (frame + 1) + 1] = S.n_links;
+          ltb[frame + 1] = base_new;
+          loff[frame] = cost_offset;
+        }
+        __syncthreads();
+        eps_links(nxt, next_cutoff, base_new, r);
+        if (tid == 0) lpos[2 * (frame + 2)] = S.n_links;
+        if (S.lat_overflow) {
+          status |= 2;
+          break;
+        }
+      }
       clear_table(cur);
       tick(6);
       base_cur = base_new;
@@ -634,6 +721,9 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     if (cfg.profile && tid == 0 && blockIdx.x == 0)
       printf("decode phases (clocks, utt %d, %d frames): cutoff %lld seed+prefix %lld expand %lld epsilon %lld compact %lld records %lld clear %lld\n", u,
              n_frames, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
+    if constexpr (kLat) {
+      if (tid == 0) ltb[n_frames + 1] = arena_n;
+    }
     // ---- best path (lattice-faster-online-decoder.cc:78-173)
     int n_words = -1;
     if (status == 0 && n_cur == 0) status |= 4;
@@ -732,20 +822,208 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a20: lattice-beam pruning of the recorded lattice, PruneForwardLinksFinal (:376-458) on the last time and
+// PruneForwardLinks (:299-370) on every earlier one, back to front -- the state FinalizeDecoding (:625-640)
+// leaves behind.  extra_cost[token] = min over its links of extra_cost[next] + ((tot_cost + acoustic + graph)
+// - next.tot_cost), the reference's float expression; a link is excised when that exceeds lattice_beam, a
+// token when no link (and no final cost) survives.  Extra costs are >= 0, so their bit patterns order as
+// unsigned integers and one atomicMin per link replaces the reference's per-token loop; links inside one time
+// (epsilon arcs) are relaxed to the fix point.  The periodic PruneActiveTokens (:506-533) of the reference only
+// removes links this final pass removes as well (its extra costs are lower bounds of the final ones).
+// Then the survivors are renumbered and written as compact arcs (GetRawLattice :106-189: olabel, graph cost,
+// acoustic cost without the per-frame offset) behind a global cursor.
+__global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_constant__ DecodeParams P, float lattice_beam,
+                                                               LatticeHeader *headers, LatticeArc *arcs, int arcs_cap,
+                                                               int *cursor) {
+  __shared__ Shared S;
+  __shared__ int s_changed, s_base;
+  const int tid = threadIdx.x;
+  const int u = blockIdx.x;
+  const DevGraph &g = P.g;
+  const int T = P.n_frames[u];
+  const float kInf = __int_as_float(0x7f800000);
+  const unsigned NE = g.num_earcs;
+  if (T <= 0 || P.n_words[u] < 0) {
+    if (tid == 0) headers[u] = LatticeHeader{0, 0, 0, 0, 0, {0, 0, 0}};
+    return;
+  }
+  const int2 *ltok = P.lat.tok + (size_t)u * P.lat.tok_cap;
+  unsigned *extra = reinterpret_cast<unsigned *>(P.lat.extra + (size_t)u * P.lat.tok_cap);
+  int *newid = P.lat.newid + (size_t)u * P.lat.tok_cap;
+  int4 *llink = P.lat.link + (size_t)u * P.lat.link_cap;
+  const int *ltb = P.lat.tok_base + (size_t)u * (P.lat.max_t + 2);
+  const int *lpos = P.lat.link_pos + (size_t)u * (2 * P.lat.max_t + 4);
+  const float *loff = P.lat.cost_offset + (size_t)u * (P.lat.max_t + 1);
+  const int ntok = ltb[T + 1];
+  const int nlink = lpos[2 * (T + 1)];
+  for (int i = tid; i < ntok; i += NT) extra[i] = 0x7f800000u;
+  __syncthreads();
+  // ---- last time: final costs (ComputeFinalCosts :536-577)
+  const int f0 = ltb[T], f1 = ltb[T + 1];
+  int anyf = 0;
+  for (int i = f0 + tid; i < f1; i += NT) anyf |= g.final_cost[ltok[i].x] != kInf;
+  anyf = __syncthreads_or(anyf);
+  {
+    float bv = kInf;
+    int bi = 0x7fffffff;
+    for (int i = f0 + tid; i < f1; i += NT) {
+      const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
+      const float c = __fadd_rn(__int_as_float(ltok[i].y), fc);
+      if (c < bv) {
+        bv = c;
+        bi = i;
+      }
+    }
+    block_min(bv, bi, S);
+  }
+  const float final_best = S.best_cost;
+  __syncthreads();
+  for (int i = f0 + tid; i < f1; i += NT) {
+    const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
+    float e = __fsub_rn(__fadd_rn(__int_as_float(ltok[i].y), fc), final_best);
+    if (e < 0.f) e = 0.f;
+    if (!(e > lattice_beam)) extra[i] = __float_as_uint(e);
+  }
+  __syncthreads();
+  auto link_extra = [&](const int4 &l, float acoustic) -> float {
+    const float en = __uint_as_float(*reinterpret_cast<volatile unsigned *>(extra + l.y));
+    const int4 a = (unsigned)l.z < NE ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
+    const float through = __fadd_rn(__fadd_rn(__int_as_float(ltok[l.x].y), acoustic), __int_as_float(a.z));
+    return __fadd_rn(en, __fsub_rn(through, __int_as_float(ltok[l.y].y)));
+  };
+  for (int t = T; t >= 0; t--) {
+    const int e0 = lpos[2 * t + 2], e1 = t < T ? lpos[2 * t + 3] : e0;  // emitting links t -> t + 1
+    const int p0 = lpos[2 * t + 1], p1 = lpos[2 * t + 2];              // epsilon links inside t
+    const float *ll = P.loglikes + (size_t)(P.ll_row0[u] + t) * P.ld;
+    const float off = t < T ? loff[t] : 0.f;
+    for (int i = e0 + tid; i < e1; i += NT) {
+      const int4 l = llink[i];
+      float le = link_extra(l, __fsub_rn(off, ll[g.earc[l.z].y]));
+      if (!(le > lattice_beam)) atomicMin(extra + l.x, __float_as_uint(fmaxf(le, 0.f)));
+    }
+    __syncthreads();
+    while (true) {
+      if (tid == 0) s_changed = 0;
+      __syncthreads();
+      int ch = 0;
+      for (int i = p0 + tid; i < p1; i += NT) {
+        const int4 l = llink[i];
+        float le = link_extra(l, 0.f);
+        if (!(le > lattice_beam)) {
+          const unsigned v = __float_as_uint(fmaxf(le, 0.f));
+          if (v < atomicMin(extra + l.x, v)) ch = 1;
+        }
+      }
+      if (ch) s_changed = 1;
+      __syncthreads();
+      const int again = s_changed;
+      __syncthreads();
+      if (!again) break;
+    }
+    // extras of time t and t + 1 are final: excise / keep, and store the lattice's acoustic cost
+    // (GetRawLattice subtracts the frame's cost offset again, :158-165)
+    for (int i = e0 + tid; i < e1; i += NT) {
+      int4 l = llink[i];
+      const float ac = __fsub_rn(off, ll[g.earc[l.z].y]);
+      const float nll = __fsub_rn(ac, off);  // "l->acoustic_cost - cost_offset" (:160), rounding included
+      const float le = link_extra(l, ac);
+      if (le > lattice_beam) l.x = -1;
+      l.w = __float_as_int(nll);
+      llink[i] = l;
+    }
+    for (int i = p0 + tid; i < p1; i += NT) {
+      int4 l = llink[i];
+      const float le = link_extra(l, 0.f);
+      if (le > lattice_beam) l.x = -1;
+      l.w = 0;
+      llink[i] = l;
+    }
+    __syncthreads();
+  }
+  // ---- renumber the surviving tokens
+  unsigned n_nodes = 0;
+  for (int b0 = 0; b0 < ntok; b0 += NT) {
+    const int i = b0 + tid;
+    const unsigned alive = (i < ntok && extra[i] != 0x7f800000u) ? 1u : 0u;
+    unsigned total;
+    const unsigned ex = block_excl_scan(alive, S, &total);
+    if (i < ntok) newid[i] = alive ? (int)(n_nodes + ex) : -1;
+    n_nodes += total;
+  }
+  __syncthreads();
+  // ---- count, reserve, write
+  unsigned cnt = 0;
+  for (int i = tid; i < nlink; i += NT) {
+    const int4 l = llink[i];
+    cnt += (l.x >= 0 && newid[l.x] >= 0 && newid[l.y] >= 0) ? 1u : 0u;
+  }
+  for (int i = f0 + tid; i < f1; i += NT) {
+    const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
+    cnt += (newid[i] >= 0 && fc != kInf) ? 1u : 0u;
+  }
+  unsigned n_out;
+  block_excl_scan(cnt, S, &n_out);
+  if (tid == 0) s_base = atomicAdd(cursor, (int)n_out);
+  __syncthreads();
+  const int base = s_base;
+  if (base + (int)n_out > arcs_cap) {
+    if (tid == 0) headers[u] = LatticeHeader{0, 0, 0, 0, 0, {0, 0, 0}};
+    return;
+  }
+  unsigned running = 0;
+  for (int b0 = 0; b0 < nlink; b0 += NT) {
+    const int i = b0 + tid;
+    int4 l = make_int4(-1, 0, 0, 0);
+    if (i < nlink) l = llink[i];
+    const unsigned keep = (l.x >= 0 && newid[l.x] >= 0 && newid[l.y] >= 0) ? 1u : 0u;
+    unsigned total;
+    const unsigned ex = block_excl_scan(keep, S, &total);
+    if (keep) {
+      const int4 a = (unsigned)l.z < NE ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
+      arcs[base + running + ex] = LatticeArc{newid[l.x], newid[l.y], a.w, __int_as_float(a.z), __int_as_float(l.w)};
+    }
+    running += total;
+  }
+  for (int b0 = f0; b0 < f1; b0 += NT) {
+    const int i = b0 + tid;
+    float fc = kInf;
+    if (i < f1) fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
+    const unsigned keep = (i < f1 && newid[i] >= 0 && fc != kInf) ? 1u : 0u;
+    unsigned total;
+    const unsigned ex = block_excl_scan(keep, S, &total);
+    if (keep) arcs[base + running + ex] = LatticeArc{newid[i], -1, 0, fc, 0.f};
+    running += total;
+  }
+  if (tid == 0) headers[u] = LatticeHeader{base, (int)n_out, (int)n_nodes, 1, nlink, {0, 0, 0}};
+}
+
+void LaunchLatticePrune(const DecodeParams &p, float lattice_beam, LatticeHeader *headers, LatticeArc *arcs,
+                        int arcs_cap, int *cursor, cudaStream_t stream) {
+  if (p.n_utts == 0) return;
+  lattice_prune_kernel<<<p.n_utts, kMaxNT, 0, stream>>>(p, lattice_beam, headers, arcs, arcs_cap, cursor);
+}
+
 size_t DecodeSmemBytes(int slots) { return (size_t)slots * (2 * 8 + 15 * 4) + 64; }
 
-void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream) {
+void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream, bool lattice) {
   if (p.n_utts == 0) return;
   size_t smem = 0;
   if (p.cfg.smem_slots) {
     smem = DecodeSmemBytes(p.cfg.smem_slots);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-      cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = smem;
+    static size_t configured[2] = {48 * 1024, 48 * 1024};
+    if (smem > configured[lattice]) {
+      if (lattice)
+        cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      else
+        cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured[lattice] = smem;
     }
   }
-  decode_kernel<<<n_lanes, DecodeCtaThreads(), smem, stream>>>(p);
+  if (lattice)
+    decode_kernel<true><<<n_lanes, DecodeCtaThreads(), smem, stream>>>(p);
+  else
+    decode_kernel<false><<<n_lanes, DecodeCtaThreads(), smem, stream>>>(p);
 }
 
 }  // namespace rs

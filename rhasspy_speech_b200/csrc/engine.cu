@@ -17,6 +17,7 @@
 #include "engine.h"
 #include "model.h"
 #include "nnet_tc.h"
+#include "nbest.h"
 
 namespace rs {
 
@@ -38,6 +39,10 @@ struct DevBuf {  // grow-only device allocation
       p = nullptr;
       size_t want = bytes + bytes / 8 + 256;
       CUDA_OK(cudaMalloc(&p, want));
+      // zero on growth: padding columns of activation / feature buffers are multiplied by zero weights and must
+      // be finite; fresh driver memory is zero, memory recycled from an earlier decoder of the process is not
+      CUDA_OK(cudaMemset(p, 0, want));
+      CUDA_OK(cudaDeviceSynchronize());
       cap = want;
     }
     return p;
@@ -366,6 +371,12 @@ struct DecoderImpl {
   std::vector<void *> owned;
   DevBuf d_pcm, d_desc, d_mfcc, d_mfcc_norm, d_xraw, d_xnorm, d_post_idx, d_post_w, d_wf, d_gw, d_linear, d_quad;
   DevBuf d_out;  // decode outputs
+  // n-best tail (rs_decoder_set_nbest): lattice recorded by decode_kernel<true>, pruned + compacted on the device
+  int nbest = 1;
+  float nbest_scale = 1.0f;
+  DevBuf d_lat_tok, d_lat_extra, d_lat_newid, d_lat_link, d_lat_tb, d_lat_pos, d_lat_off, d_lat_hdr, d_lat_arcs;
+  PinBuf h_lat;
+  std::vector<LatticeHeader> lat_hdr;  // of the last n-best call (rs_debug_fetch item 5)
   std::vector<DevBuf> slots;
   DevBuf d_tid_pdf;
   DevBuf d_loglikes_ext;
@@ -777,6 +788,41 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
 
 void rs_decoder_free(rs_decoder *d) { delete reinterpret_cast<DecoderImpl *>(d); }
 
+int rs_decoder_set_nbest(rs_decoder *d_, int32_t nbest, float acoustic_scale, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d) RS_FAIL("rs_decoder_set_nbest: null decoder");
+  if (nbest < 1 || !(acoustic_scale == acoustic_scale)) RS_FAIL("rs_decoder_set_nbest: n must be >= 1");
+  d->nbest = nbest;
+  d->nbest_scale = acoustic_scale;
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_debug_lattice_nbest(const int32_t *src, const int32_t *dst, const int32_t *olabel, const float *graph,
+                           const float *acoustic, int32_t n_arcs, int32_t n_nodes, int32_t n, float acoustic_scale,
+                           int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost) {
+  if (!src || !dst || !olabel || !graph || !acoustic || !word_offset || !word_ids || !cost || n < 1) return -1;
+  try {
+    std::vector<LatticeArc> arcs(std::max(n_arcs, 0));
+    for (int i = 0; i < n_arcs; i++) arcs[i] = LatticeArc{src[i], dst[i], olabel[i], graph[i], acoustic[i]};
+    std::vector<NbestHyp> out;
+    LatticeNbest(arcs.data(), n_arcs, n_nodes, n, acoustic_scale, &out);
+    int w = 0;
+    for (size_t h = 0; h < out.size(); h++) {
+      word_offset[h] = w;
+      if (w + (int)out[h].words.size() > max_words) return -2;
+      for (int id : out[h].words) word_ids[w++] = id;
+      cost[2 * h] = out[h].graph;
+      cost[2 * h + 1] = out[h].acoustic;
+    }
+    word_offset[out.size()] = w;
+    return (int)out.size();
+  } catch (...) {
+    return -3;
+  }
+}
+
 }  // extern "C"
 
 namespace rs {
@@ -791,7 +837,52 @@ static rs_result *NewResult(int n) {
   r->acoustic_cost = new float[std::max(n, 1)]();
   r->num_frames = new int32_t[std::max(n, 1)]();
   r->status = new int32_t[std::max(n, 1)]();
+  r->hyp_offset = new int32_t[n + 1]();
+  r->hyp_word_offset = n == 0 ? new int32_t[1]() : nullptr;
+  r->hyp_word_ids = nullptr;
+  r->hyp_graph_cost = nullptr;
+  r->hyp_acoustic_cost = nullptr;
   return r;
+}
+
+// hypothesis-indexed arrays of a result from per-utterance lists (nb[u] empty: the best path alone, if any)
+static void FillHypotheses(rs_result *r, const std::vector<std::vector<NbestHyp>> &nb) {
+  const int n = r->n_utts;
+  int total = 0, words = 0;
+  for (int u = 0; u < n; u++) {
+    if (!nb.empty() && !nb[u].empty()) {
+      r->n_hyp[u] = (int)nb[u].size();
+      for (const NbestHyp &h : nb[u]) words += (int)h.words.size();
+    } else {
+      words += r->n_hyp[u] ? r->word_offset[u + 1] - r->word_offset[u] : 0;
+    }
+    total += r->n_hyp[u];
+  }
+  r->hyp_word_offset = new int32_t[total + 1]();
+  r->hyp_word_ids = new int32_t[std::max(words, 1)];
+  r->hyp_graph_cost = new float[std::max(total, 1)]();
+  r->hyp_acoustic_cost = new float[std::max(total, 1)]();
+  int h = 0, w = 0;
+  for (int u = 0; u < n; u++) {
+    r->hyp_offset[u] = h;
+    if (!nb.empty() && !nb[u].empty()) {
+      for (const NbestHyp &hy : nb[u]) {
+        r->hyp_word_offset[h] = w;
+        for (int id : hy.words) r->hyp_word_ids[w++] = id;
+        r->hyp_graph_cost[h] = hy.graph;
+        r->hyp_acoustic_cost[h] = hy.acoustic;
+        h++;
+      }
+    } else if (r->n_hyp[u]) {
+      r->hyp_word_offset[h] = w;
+      for (int i = r->word_offset[u]; i < r->word_offset[u + 1]; i++) r->hyp_word_ids[w++] = r->word_ids[i];
+      r->hyp_graph_cost[h] = r->graph_cost[u];
+      r->hyp_acoustic_cost[h] = r->acoustic_cost[u];
+      h++;
+    }
+  }
+  r->hyp_offset[n] = h;
+  r->hyp_word_offset[h] = w;
 }
 
 // Runs stage (iii) for the batch laid out in d->batch and collects the results.
@@ -838,15 +929,62 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   p.cost = (float *)(dout + off_cost);
   p.counters = (unsigned long long *)(dout + off_cnt);
   CUDA_OK(cudaMemsetAsync(d->d_next_utt, 0, sizeof(int), d->stream));
-  LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream);
+  // ---- n-best tail: per-utterance lattice slices inside a byte budget (RS_B200_LATTICE_MB, default 8192)
+  const bool lattice = d->nbest > 1 || d->nbest_scale != 1.0f;
+  LatticeHeader *d_hdr = nullptr;
+  LatticeArc *d_arcs = nullptr;
+  int arcs_cap = 0;
+  if (lattice) {
+    int max_t = 1;
+    for (int u = 0; u < n; u++) max_t = std::max(max_t, d->batch.n_out[u]);
+    const char *e = getenv("RS_B200_LATTICE_MB");
+    const size_t budget = (size_t)std::max(e ? atoi(e) : 8192, 16) << 20;
+    const int kLinksPerToken = 3;
+    const size_t per_tok = sizeof(int2) + sizeof(float) + sizeof(int) + kLinksPerToken * sizeof(int4);
+    const size_t tc = std::min<size_t>((size_t)o.max_tokens_per_utt, std::max<size_t>(budget / n / per_tok, 4096));
+    LatticeBuf &L = p.lat;
+    L.tok_cap = (int)tc;
+    L.link_cap = (int)std::min<size_t>(tc * kLinksPerToken, 0x7fffffff);
+    L.max_t = max_t;
+    L.tok = (int2 *)d->d_lat_tok.ensure(sizeof(int2) * tc * n);
+    L.extra = (float *)d->d_lat_extra.ensure(sizeof(float) * tc * n);
+    L.newid = (int *)d->d_lat_newid.ensure(sizeof(int) * tc * n);
+    L.link = (int4 *)d->d_lat_link.ensure(sizeof(int4) * (size_t)L.link_cap * n);
+    L.tok_base = (int *)d->d_lat_tb.ensure(sizeof(int) * (size_t)(max_t + 2) * n);
+    L.link_pos = (int *)d->d_lat_pos.ensure(sizeof(int) * (size_t)(2 * max_t + 4) * n);
+    L.cost_offset = (float *)d->d_lat_off.ensure(sizeof(float) * (size_t)(max_t + 1) * n);
+    // headers [n] + cursor, then the compact arcs of the pruned lattices
+    d_hdr = (LatticeHeader *)d->d_lat_hdr.ensure(sizeof(LatticeHeader) * n + sizeof(int));
+    arcs_cap = (int)std::min<size_t>((size_t)L.link_cap * n / 4 + 65536, 64u << 20);
+    d_arcs = (LatticeArc *)d->d_lat_arcs.ensure(sizeof(LatticeArc) * (size_t)arcs_cap);
+  }
+  LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream, lattice);
   launches += 1;
+  if (lattice) {
+    int *d_cursor = reinterpret_cast<int *>(d_hdr + n);
+    CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(int), d->stream));
+    LaunchLatticePrune(p, o.lattice_beam, d_hdr, d_arcs, arcs_cap, d_cursor, d->stream);
+    launches += 1;
+  }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(d->ev[4], d->stream));
-  char *hout = (char *)d->h_out.ensure(out_bytes);
+  const size_t hdr_bytes = lattice ? sizeof(LatticeHeader) * n + sizeof(int) : 0;
+  char *hout = (char *)d->h_out.ensure(out_bytes + hdr_bytes);
   CUDA_OK(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, d->stream));
+  if (lattice) CUDA_OK(cudaMemcpyAsync(hout + out_bytes, d_hdr, hdr_bytes, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_OK(cudaStreamSynchronize(d->stream));
+  d->last.d2h_bytes = out_bytes + hdr_bytes;
+  const LatticeHeader *hdr = reinterpret_cast<const LatticeHeader *>(hout + out_bytes);
+  const LatticeArc *harcs = nullptr;
+  if (lattice) {
+    const int n_arcs = std::min(*reinterpret_cast<const int *>(hout + out_bytes + sizeof(LatticeHeader) * n), arcs_cap);
+    harcs = (const LatticeArc *)d->h_lat.ensure(sizeof(LatticeArc) * (size_t)std::max(n_arcs, 1));
+    if (n_arcs > 0)
+      CUDA_OK(cudaMemcpyAsync((void *)harcs, d_arcs, sizeof(LatticeArc) * (size_t)n_arcs, cudaMemcpyDeviceToHost, d->stream));
+    d->last.d2h_bytes += sizeof(LatticeArc) * (size_t)n_arcs;
+  }
   CUDA_OK(cudaEventRecord(d->ev[5], d->stream));
   CUDA_OK(cudaStreamSynchronize(d->stream));
-  d->last.d2h_bytes = out_bytes;
   const int *words = (const int *)(hout + off_words), *nw = (const int *)(hout + off_nw), *status = (const int *)(hout + off_status);
   const float *cost = (const float *)(hout + off_cost);
   const unsigned long long *cnt = (const unsigned long long *)(hout + off_cnt);
@@ -872,6 +1010,55 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     d->last.frames_decoded += d->batch.n_out[u];
   }
   r->word_offset[n] = pos;
+  std::vector<std::vector<NbestHyp>> nb;
+  if (lattice) {
+    // host half of the tail: best-first search of each pruned lattice (nbest.cc), utterances across threads
+    nb.resize(n);
+    const int nthreads = std::max(1, std::min({n, 8, (int)std::thread::hardware_concurrency()}));
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int u = next++; u < n; u = next++) {
+        if (!hdr[u].ok || r->n_hyp[u] == 0) continue;
+        LatticeNbest(harcs + hdr[u].arc_begin, hdr[u].n_arcs, hdr[u].n_nodes, d->nbest, d->nbest_scale, &nb[u]);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nthreads; i++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    d->lat_hdr.assign(hdr, hdr + n);
+    d->last.lattice_states = d->last.lattice_arcs = d->last.lattice_links_recorded = 0;
+    for (int u = 0; u < n; u++) {
+      if (r->n_hyp[u] && nb[u].empty()) r->status[u] |= 32;
+      if (hdr[u].ok) {
+        d->last.lattice_states += hdr[u].n_nodes;
+        d->last.lattice_arcs += hdr[u].n_arcs;
+        d->last.lattice_links_recorded += hdr[u].n_links;
+      }
+    }
+  }
+  if (!lattice) d->lat_hdr.clear();
+  if (lattice && d->nbest_scale != 1.0f) {
+    // the per-utterance fields describe utt-1 of the list: under a ranking scale that need not be the
+    // back-traced path of the search (which ran at scale 1)
+    std::vector<int32_t> ids;
+    const std::vector<int32_t> old(r->word_offset, r->word_offset + n + 1);
+    for (int u = 0; u < n; u++) {
+      r->word_offset[u] = (int)ids.size();
+      if (!nb[u].empty()) {
+        ids.insert(ids.end(), nb[u][0].words.begin(), nb[u][0].words.end());
+        r->graph_cost[u] = nb[u][0].graph;
+        r->acoustic_cost[u] = nb[u][0].acoustic;
+      } else if (r->n_hyp[u]) {
+        ids.insert(ids.end(), r->word_ids + old[u], r->word_ids + old[u + 1]);
+      }
+    }
+    r->word_offset[n] = (int)ids.size();
+    delete[] r->word_ids;
+    r->word_ids = new int32_t[std::max<size_t>(ids.size(), 1)];
+    std::copy(ids.begin(), ids.end(), r->word_ids);
+  }
+  FillHypotheses(r, nb);
   return r;
 }
 
@@ -1505,6 +1692,11 @@ void rs_result_free(rs_result *r) {
   delete[] r->acoustic_cost;
   delete[] r->num_frames;
   delete[] r->status;
+  delete[] r->hyp_offset;
+  delete[] r->hyp_word_offset;
+  delete[] r->hyp_word_ids;
+  delete[] r->hyp_graph_cost;
+  delete[] r->hyp_acoustic_cost;
   delete r;
 }
 
@@ -1756,6 +1948,21 @@ int rs_debug_fetch(rs_decoder *d_, int32_t what, int32_t utt, float *dst, int32_
   CUDA_OK(cudaSetDevice(d->model->device));
   const float *src = nullptr;
   int r = 0, c = 0, ld = 0;
+  if (what == 5) {
+    // pruned state-level lattice of the last n-best call: rows of (src, dst, olabel, graph cost, acoustic cost)
+    if ((int)d->lat_hdr.size() != B.n) RS_FAIL("rs_debug_fetch: the last call did not build lattices (rs_decoder_set_nbest)");
+    const LatticeHeader &h = d->lat_hdr[utt];
+    if (rows) *rows = h.ok ? h.n_arcs : 0;
+    if (cols) *cols = 5;
+    if (dst && h.ok) {
+      const LatticeArc *a = reinterpret_cast<const LatticeArc *>(d->h_lat.p) + h.arc_begin;
+      for (int i = 0; i < h.n_arcs; i++) {
+        float *o = dst + (size_t)i * 5;
+        o[0] = (float)a[i].src, o[1] = (float)a[i].dst, o[2] = (float)a[i].olabel, o[3] = a[i].graph, o[4] = a[i].acoustic;
+      }
+    }
+    return 0;
+  }
   if (what == 2) {
     r = B.n_out[utt];
     c = m.trans.num_pdfs;

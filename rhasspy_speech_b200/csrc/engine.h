@@ -195,7 +195,7 @@ struct LatticeBuf {
 
 // compact lattice as the host receives it: one header per utterance, then its arcs in `arcs`
 struct LatticeHeader {
-  int arc_begin, n_arcs, n_nodes, ok;
+  int arc_begin, n_arcs, n_nodes, ok, n_links, pad[3];
 };
 struct LatticeArc {  // dst == -1: final weight of src (graph = final cost, acoustic = 0)
   int src, dst, olabel;

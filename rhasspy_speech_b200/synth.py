@@ -687,11 +687,11 @@ def write_const_fst(path: str, start: int, pos: np.ndarray, arc: np.ndarray, fin
     st["final"] = final
     st["pos"] = pos[:-1]
     st["narcs"] = np.diff(pos)
-    ieps = np.add.reduceat((arc["ilabel"] == 0).astype(np.int64), pos[:-1].clip(max=max(na - 1, 0))) if na else np.zeros(ns)
-    oeps = np.add.reduceat((arc["olabel"] == 0).astype(np.int64), pos[:-1].clip(max=max(na - 1, 0))) if na else np.zeros(ns)
-    empty = np.diff(pos) == 0
-    st["nieps"] = np.where(empty, 0, ieps)
-    st["noeps"] = np.where(empty, 0, oeps)
+    # per-state epsilon counts; the reference trusts them (ProcessNonemitting only queues states with
+    # NumInputEpsilons() != 0, lattice-faster-decoder.cc:846-850), so they must be exact
+    owner = np.repeat(np.arange(ns), np.diff(pos).astype(np.int64))
+    st["nieps"] = np.bincount(owner[arc["ilabel"] == 0], minlength=ns)
+    st["noeps"] = np.bincount(owner[arc["olabel"] == 0], minlength=ns)
     with open(path, "wb") as f:
         f.write(hdr)
         if aligned:

@@ -102,7 +102,9 @@ def nbest_text(hyp: "_lib.Hypotheses", utt: int) -> bytes:
     followed by a space); empty when nothing was decoded, as when the reference's lattice is empty."""
     if hyp.words[utt] is None:
         return b""
-    return ("utt-1 " + "".join("%d " % w for w in hyp.words[utt]) + "\n").encode()
+    # utt-<k>: lattice-to-nbest appends "-<k>" to the utterance key (latbin/lattice-to-nbest.cc:104-107)
+    return "".join("utt-%d %s\n" % (k + 1, "".join("%d " % w for w in words))
+                   for k, (words, _, _) in enumerate(hyp.nbest[utt])).encode()
 
 
 async def _fuzzy(nbest_stdout: bytes, lang_dir: Path, tools) -> Optional[Tuple[str, float]]:
@@ -137,10 +139,12 @@ class _Base:
         final_mdl, online_conf = self._paths()
         return _engine(final_mdl, online_conf, self.graph_dir, self.device, self.max_active, self.beam, self.lattice_beam)
 
-    def _check_nbest(self, nbest: int):
-        if nbest != 1 or self.acoustic_scale != 1.0:
-            raise NotImplementedError("n-best > 1 and lattice rescaling need the lattice output (scope row f1); "
-                                      "the GPU decoder returns the single best path")
+    def _set_nbest(self, eng: _Engine, nbest: int):
+        """`lattice-to-nbest --n=<nbest> --acoustic-scale=<acoustic_scale>` (transcribe_wav.py:62-67); call with
+        eng.lock held.  n = 1 at scale 1.0 is the device back-trace, anything else goes through the lattice."""
+        if nbest < 1:
+            raise RuntimeError("Unexpected error running command lattice-to-nbest: --n must be >= 1")
+        eng.decoder.set_nbest(nbest, self.acoustic_scale)
 
     async def _finish(self, eng: _Engine, nbest_stdout: bytes, lang_dir, max_fuzzy_cost, require_fuzzy) -> List[str]:
         lang_dir = Path(lang_dir)
@@ -163,20 +167,21 @@ class _Base:
 class KaldiNnet3WavTranscriber(_Base):
     async def async_transcribe(self, wav_path, lang_dir, nbest: int = 1, max_fuzzy_cost: Optional[float] = None,
                                require_fuzzy: bool = False) -> List[str]:
-        self._check_nbest(nbest)
         eng = self._get_engine()
         loop = asyncio.get_running_loop()
 
         def run():
             with eng.lock:
                 try:
+                    self._set_nbest(eng, nbest)
                     return eng.decoder.decode_wavs([str(wav_path)])
                 except _lib.RsError as e:
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
         hyp = await loop.run_in_executor(None, run)
         return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)
 
-    async def async_transcribe_many(self, wav_paths: Sequence, lang_dir, max_fuzzy_cost: Optional[float] = None,
+    async def async_transcribe_many(self, wav_paths: Sequence, lang_dir, nbest: int = 1,
+                                    max_fuzzy_cost: Optional[float] = None,
                                     require_fuzzy: bool = False) -> List[List[str]]:
         """Batched extension: one GPU batch for all files; element i equals async_transcribe(wav_paths[i])."""
         eng = self._get_engine()
@@ -185,6 +190,7 @@ class KaldiNnet3WavTranscriber(_Base):
         def run():
             with eng.lock:
                 try:
+                    self._set_nbest(eng, nbest)
                     return eng.decoder.decode_wavs([str(p) for p in wav_paths])
                 except _lib.RsError as e:
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
@@ -200,7 +206,6 @@ class KaldiNnet3StreamTranscriber(_Base):
     async def async_transcribe(self, audio_stream: AsyncIterable[Optional[bytes]], lang_dir, nbest: int = 1,
                                max_fuzzy_cost: Optional[float] = None, require_fuzzy: bool = False) -> List[str]:
         """audio_stream yields raw 16 kHz mono s16le chunks of any size (reference transcribe_stream.py:38-82)."""
-        self._check_nbest(nbest)
         eng = self._get_engine()
         stream = eng.decoder.open_stream()
         try:
@@ -217,6 +222,7 @@ class KaldiNnet3StreamTranscriber(_Base):
 
             def run():
                 with eng.lock:
+                    self._set_nbest(eng, nbest)
                     return stream.finish()
             hyp = await loop.run_in_executor(None, run)
         finally:
@@ -249,6 +255,7 @@ class KaldiTranscriber:
         eng = self._get_engine()
         with eng.lock:
             try:
+                eng.decoder.set_nbest(1, 1.0)
                 hyp = eng.decoder.decode_wavs([str(wav_path)])
             except _lib.RsError as e:
                 raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
@@ -257,6 +264,7 @@ class KaldiTranscriber:
     def transcribe_wavs(self, wav_paths: Sequence) -> List[str]:
         eng = self._get_engine()
         with eng.lock:
+            eng.decoder.set_nbest(1, 1.0)
             hyp = eng.decoder.decode_wavs([str(p) for p in wav_paths])
         return [self._text(eng, hyp, u) for u in range(len(wav_paths))]
 
@@ -274,6 +282,7 @@ class KaldiTranscriber:
                 if keep:
                     stream.accept(data[:keep])
             with eng.lock:
+                eng.decoder.set_nbest(1, 1.0)
                 hyp = stream.finish()
         finally:
             stream.close()

@@ -116,10 +116,12 @@ def test_decode_meta_and_nbest_text():
     assert T.decode_meta("turn on " + word + " " + sent) == "lights on in kitchen"
 
     class H:
-        words = [[12, 45, 7], None, []]
+        words = [[12, 45, 7], None, [], [3, 4]]
+        nbest = [[([12, 45, 7], 1.0, 2.0)], [], [([], 0.0, 0.0)], [([3, 4], 1.0, 2.0), ([3], 1.5, 2.5), ([], 9.0, 1.0)]]
     assert T.nbest_text(H, 0) == b"utt-1 12 45 7 \n"       # kaldi-holder-inl.h:244-251: each int is followed by a space
     assert T.nbest_text(H, 1) == b""
     assert T.nbest_text(H, 2) == b"utt-1 \n"
+    assert T.nbest_text(H, 3) == b"utt-1 3 4 \nutt-2 3 \nutt-3 \n"   # lattice-to-nbest.cc:104-107 keys
 
 
 def test_shard_utterances_balances_audio():
