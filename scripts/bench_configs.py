@@ -19,13 +19,29 @@ def run(name, dec, fn, audio_s, reps=4):
     t = {k: float(np.mean([x[k] for x in ts])) for k in ("h2d_ms", "feature_ms", "nnet_ms", "decode_ms", "total_ms")}
     dev = t["feature_ms"] + t["nnet_ms"] + t["decode_ms"]
     flags = {int(s): int((np.asarray(hyp.status) == s).sum()) for s in set(int(x) for x in hyp.status)}
-    print(json.dumps({"config": name, "audio_s": audio_s, "rtfx_device": audio_s / (dev / 1e3), "rtfx_e2e": audio_s / float(np.mean(wall)),
-                      "stages_ms": t, "status_counts": flags, "tokens_per_frame": ts[-1]["tokens_expanded"] / max(1, ts[-1]["frames_decoded"])}),
-          flush=True)
+    out = {"config": name, "audio_s": audio_s, "rtfx_device": audio_s / (dev / 1e3), "rtfx_e2e": audio_s / float(np.mean(wall)),
+           "wall_ms": float(np.mean(wall)) * 1e3, "stages_ms": t, "status_counts": flags,
+           "tokens_per_frame": ts[-1]["tokens_expanded"] / max(1, ts[-1]["frames_decoded"])}
+    if ts[-1]["lattice_arcs"]:
+        out["lattice"] = {k: ts[-1][k] for k in ("lattice_states", "lattice_arcs", "lattice_links_recorded", "d2h_bytes")}
+        out["hyps_per_utt"] = float(np.mean(hyp.n_hyp))
+    print(json.dumps(out), flush=True)
 
 
 def main():
     tmp = tempfile.mkdtemp()
+    if "--nbest" in sys.argv:
+        # the n-best tail on the bench workload (configs[1]): batch 256, grammar graph, n = 1 (device back-trace) vs
+        # n = 5 (lattice recorded + pruned on the device, best-first search on the host); decode_ms covers
+        # decode_kernel (+ lattice_prune_kernel), wall - total covers the host search
+        p = synth.write_model(os.path.join(tmp, "gram"), synth.ZAMIA_LIKE)
+        dec = _lib.Decoder(_lib.Model(p.final_mdl, p.online_conf, 0), _lib.Graph(p.hclg, p.words_txt, 0))
+        utts = synth.make_utterances(256, seed=1234)
+        audio_s = sum(len(u) for u in utts) / 16000.0
+        for n in (1, 5):
+            dec.set_nbest(n)
+            run("2: grammar HCLG, batch 256, nbest=%d" % n, dec, lambda: dec.decode_pcm(utts), audio_s)
+        return
     # config 3: zamia-like model, ARPA-shaped graph
     spec = dataclasses.replace(synth.ZAMIA_LIKE, name="zamia_arpa", graph="arpa", vocab_size=2000, bigrams_per_word=20, eps_hops=2)
     p = synth.write_model(os.path.join(tmp, "arpa"), spec)

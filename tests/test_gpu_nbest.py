@@ -155,3 +155,42 @@ def test_nbest_stream_and_python_surface(tiny_model, utterances, ref, synth, tmp
             yield raw[o:o + 2560]
     st = pkg.KaldiNnet3StreamTranscriber(model_dir, graph_dir, None)
     assert asyncio.run(st.async_transcribe(chunks(), tmp_path, nbest=4)) == swant_text
+
+
+def test_nbest_on_arpa_graph_with_epsilon_chains(lib, ref, synth, utterances, tmp_path):
+    """BASELINE config 3 in miniature: ARPA-shaped HCLG (back-off epsilon chains, global-memory state tables), plus
+    out-of-grammar audio; the lattices are an order of magnitude larger than on the grammar graph."""
+    import dataclasses
+    spec = dataclasses.replace(synth.TINY, name="tiny_arpa", seed=11, graph="arpa", vocab_size=300, bigrams_per_word=8, eps_hops=2)
+    p = synth.write_model(str(tmp_path / "m"), spec)
+    utts = list(utterances[:4]) + [utterances[0][::-1].copy()]
+    wavs = []
+    for i, pcm in enumerate(utts):
+        w = os.path.join(str(tmp_path), "a%03d.wav" % i)
+        synth.write_wav(w, pcm)
+        wavs.append(w)
+    m, g = lib.Model(p.final_mdl, p.online_conf, 0), lib.Graph(p.hclg, p.words_txt, 0)
+    assert g.num_states > 1024
+    n_lists = n_flagged = n_flagged_same = 0
+    # beam 16: fewer than --max-active tokens per frame, so nothing is order-dependent and the lists must be
+    # identical.  (With beam - lattice_beam of only a few units the reference's lattice itself depends on its hash
+    # order: tokens its transient next_cutoff let through, :780-787, can then lie inside the lattice beam.)
+    for beam in (24.0, 16.0):
+        dec = lib.Decoder(m, g, beam=beam)
+        want, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, nbest=5, beam=beam)
+        dec.set_nbest(5)
+        got = dec.decode_wavs(wavs)
+        t = dec.timings()
+        assert t["lattice_arcs"] > 0 and t["lattice_links_recorded"] > t["lattice_arcs"]
+        for u in range(len(wavs)):
+            assert got.status[u] in (0, 16), (beam, u, got.status[u])
+            keys = sorted((k for k in want if k.startswith("utt%05d-" % u)), key=lambda k: int(k.rsplit("-", 1)[1]))
+            same = [h[0] for h in got.nbest[u]] == [want[k] for k in keys]
+            if got.status[u] == 0:
+                assert same, (beam, u, got.nbest[u], [want[k] for k in keys])
+                n_lists += len(keys) > 1
+            else:   # 16: a binding --max-active makes the reference's token set order-dependent (DESIGN 4.2)
+                n_flagged += 1
+                n_flagged_same += same
+    print("arpa n-best: %d unflagged lists identical, %d of %d flagged lists identical" % (n_lists, n_flagged_same, n_flagged))
+    assert n_lists >= 2
