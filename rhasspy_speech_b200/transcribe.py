@@ -21,7 +21,10 @@ from __future__ import annotations
 
 import asyncio
 import base64
+import collections
+import concurrent.futures
 import json
+import os
 import re
 import threading
 from pathlib import Path
@@ -59,6 +62,96 @@ def decode_meta(text: str) -> str:
     return decode_meta_single(match.group(1)).format(**slots)
 
 
+class _OneHyp:
+    """The slice of a batch result that belongs to one request: what nbest_text() reads, for utterance 0."""
+
+    def __init__(self, hyp, u: int):
+        self.words = [hyp.words[u]]
+        self.nbest = [hyp.nbest[u]]
+        self.status = [int(hyp.status[u])]
+        self.n_hyp = [int(hyp.n_hyp[u])]
+
+
+class _Batcher:
+    """Host dynamic batcher (threading): concurrent requests on one engine become ONE device batch.
+
+    The reference runs one OS process per call, so 64 concurrent streams are 64 processes.  Here a request only
+    enqueues (kind, payload, nbest, ranking scale) and gets a future; one worker thread per engine drains the
+    queue: every request that arrived while the previous batch was on the GPU, and shares its n-best setting, goes
+    into the next rs_decode_wavs / rs_streams_finish call.  No linger by default (RS_B200_BATCH_LINGER_MS): a lone
+    request is decoded at once, a burst batches itself behind the request that is running.  A failing batch is
+    retried request by request so that only the offending call raises, as with the reference's independent
+    processes."""
+
+    def __init__(self, decoder, lock: threading.Lock, max_batch: int = 256):
+        self.decoder, self.lock, self.max_batch = decoder, lock, max_batch
+        self.linger = float(os.environ.get("RS_B200_BATCH_LINGER_MS", "0")) / 1e3
+        self.cv = threading.Condition()
+        self.pending: "collections.deque" = collections.deque()
+        self.batches: List[int] = []          # size of every device batch so far (instrumentation)
+        self.thread: Optional[threading.Thread] = None
+
+    def submit(self, kind: str, payload, nbest: int, scale: float) -> "concurrent.futures.Future":
+        fut: "concurrent.futures.Future" = concurrent.futures.Future()
+        with self.cv:
+            self.pending.append((kind, payload, int(nbest), float(scale), fut))
+            if self.thread is None or not self.thread.is_alive():
+                self.thread = threading.Thread(target=self._run, name="rs-b200-batcher", daemon=True)
+                self.thread.start()
+            self.cv.notify()
+        return fut
+
+    def _take(self):
+        """Next batch: the oldest request and every queued request with the same (kind, nbest, scale)."""
+        with self.cv:
+            while not self.pending:
+                if not self.cv.wait(timeout=1.0) and not self.pending:
+                    self.thread = None          # idle: let the thread end; submit() starts a new one
+                    return None
+            if self.linger > 0:
+                self.cv.wait(timeout=self.linger)
+            key = self.pending[0][:1] + self.pending[0][2:4]
+            batch, rest = [], collections.deque()
+            while self.pending:
+                item = self.pending.popleft()
+                if len(batch) < self.max_batch and item[:1] + item[2:4] == key:
+                    batch.append(item)
+                else:
+                    rest.append(item)
+            self.pending = rest
+            return batch
+
+    def _decode(self, kind: str, payloads, nbest: int, scale: float):
+        with self.lock:
+            self.decoder.set_nbest(nbest, scale)
+            self.batches.append(len(payloads))
+            if kind == "wav":
+                return self.decoder.decode_wavs([str(p) for p in payloads])
+            if kind == "stream":
+                return self.decoder.finish_streams(payloads)
+            return self.decoder.decode_pcm(payloads)
+
+    def _run(self):
+        while True:
+            batch = self._take()
+            if batch is None:
+                return
+            kind, _, nbest, scale, _ = batch[0]
+            try:
+                hyp = self._decode(kind, [b[1] for b in batch], nbest, scale)
+                for u, b in enumerate(batch):
+                    b[4].set_result(_OneHyp(hyp, u))
+            except Exception as first:  # noqa: BLE001 -- delivered to the caller(s) below
+                if len(batch) == 1:
+                    batch[0][4].set_exception(first)
+                    continue
+                for b in batch:             # isolate the offending request
+                    try:
+                        b[4].set_result(_OneHyp(self._decode(kind, [b[1]], nbest, scale), 0))
+                    except Exception as e:  # noqa: BLE001
+                        b[4].set_exception(e)
+
+
 class _Engine:
     """One resident (model, graph, decoder) triple; serialises calls (an rs_decoder is single-threaded)."""
 
@@ -71,6 +164,7 @@ class _Engine:
         self.graph = _lib.Graph(str(hclg), str(words_txt), device)
         self.decoder = _lib.Decoder(self.model, self.graph, **opts)
         self.lock = threading.Lock()
+        self.batcher = _Batcher(self.decoder, self.lock)
 
     def words(self, ids: Sequence[int]) -> str:
         out = []
@@ -139,6 +233,15 @@ class _Base:
         final_mdl, online_conf = self._paths()
         return _engine(final_mdl, online_conf, self.graph_dir, self.device, self.max_active, self.beam, self.lattice_beam)
 
+    async def _submit(self, eng: _Engine, kind: str, payload, nbest: int, command: str):
+        """One request through the engine's dynamic batcher; concurrent callers share a device batch."""
+        if nbest < 1:
+            raise RuntimeError("Unexpected error running command lattice-to-nbest: --n must be >= 1")
+        try:
+            return await asyncio.wrap_future(eng.batcher.submit(kind, payload, nbest, self.acoustic_scale))
+        except _lib.RsError as e:
+            raise RuntimeError("Unexpected error running command %s: %s" % (command, e)) from e
+
     def _set_nbest(self, eng: _Engine, nbest: int):
         """`lattice-to-nbest --n=<nbest> --acoustic-scale=<acoustic_scale>` (transcribe_wav.py:62-67); call with
         eng.lock held.  n = 1 at scale 1.0 is the device back-trace, anything else goes through the lattice."""
@@ -168,16 +271,7 @@ class KaldiNnet3WavTranscriber(_Base):
     async def async_transcribe(self, wav_path, lang_dir, nbest: int = 1, max_fuzzy_cost: Optional[float] = None,
                                require_fuzzy: bool = False) -> List[str]:
         eng = self._get_engine()
-        loop = asyncio.get_running_loop()
-
-        def run():
-            with eng.lock:
-                try:
-                    self._set_nbest(eng, nbest)
-                    return eng.decoder.decode_wavs([str(wav_path)])
-                except _lib.RsError as e:
-                    raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
-        hyp = await loop.run_in_executor(None, run)
+        hyp = await self._submit(eng, "wav", wav_path, nbest, "online2-wav-nnet3-latgen-faster")
         return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)
 
     async def async_transcribe_many(self, wav_paths: Sequence, lang_dir, nbest: int = 1,
@@ -218,13 +312,7 @@ class KaldiNnet3StreamTranscriber(_Base):
                 pending = data[keep:]
                 if keep:
                     stream.accept(data[:keep])
-            loop = asyncio.get_running_loop()
-
-            def run():
-                with eng.lock:
-                    self._set_nbest(eng, nbest)
-                    return stream.finish()
-            hyp = await loop.run_in_executor(None, run)
+            hyp = await self._submit(eng, "stream", stream, nbest, "online2-cli-nnet3-decode-faster")
         finally:
             stream.close()
         return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)

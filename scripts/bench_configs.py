@@ -30,6 +30,37 @@ def run(name, dec, fn, audio_s, reps=4):
 
 def main():
     tmp = tempfile.mkdtemp()
+    if "--surface" in sys.argv:
+        # config 4 through the Python mirror: 64 concurrent KaldiNnet3StreamTranscriber.async_transcribe coroutines fed
+        # 80 ms chunks; the host dynamic batcher turns them into a few device batches
+        import asyncio
+        import rhasspy_speech_b200 as pkg
+        p = synth.write_model(os.path.join(tmp, "gram"), synth.ZAMIA_LIKE)
+        st = pkg.KaldiNnet3StreamTranscriber(p.model_dir, os.path.dirname(p.hclg), None)
+        utts64 = synth.make_utterances(64, seed=4321)
+        raws = [np.asarray(u, dtype="<i2").tobytes() for u in utts64]
+
+        async def chunks(raw):
+            for o in range(0, len(raw), 2560):
+                yield raw[o:o + 2560]
+                await asyncio.sleep(0)
+
+        async def burst():
+            return await asyncio.gather(*[st.async_transcribe(chunks(r), tmp) for r in raws])
+        asyncio.run(burst())
+        eng = st._get_engine()
+        walls, sizes = [], []
+        for _ in range(4):
+            n0 = len(eng.batcher.batches)
+            t0 = time.perf_counter()
+            out = asyncio.run(burst())
+            walls.append(time.perf_counter() - t0)
+            sizes.append(eng.batcher.batches[n0:])
+        audio_s = sum(len(u) for u in utts64) / 16000.0
+        print(json.dumps({"config": "4 (Python surface): 64 concurrent async streams x 80 ms chunks", "audio_s": audio_s,
+                          "wall_ms": float(np.mean(walls)) * 1e3, "rtfx_e2e": audio_s / float(np.mean(walls)),
+                          "device_batches": sizes[-1], "decoded": sum(1 for o in out if o)}), flush=True)
+        return
     if "--nbest" in sys.argv:
         # the n-best tail on the bench workload (configs[1]): batch 256, grammar graph, n = 1 (device back-trace) vs
         # n = 5 (lattice recorded + pruned on the device, best-first search on the host); decode_ms covers

@@ -1,0 +1,58 @@
+"""The Python mirror of the reference's transcribers under concurrency (BASELINE config 4, SURVEY 8b threading):
+many coroutines on one engine share device batches through the host dynamic batcher, and every caller still gets
+exactly the result of a lone call."""
+import asyncio
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_concurrent_streams_and_wavs_share_device_batches(tiny_model, utterances, synth, tmp_path):
+    import rhasspy_speech_b200 as pkg
+    from rhasspy_speech_b200 import transcribe as T
+    graph_dir = os.path.dirname(tiny_model.hclg)
+    st = pkg.KaldiNnet3StreamTranscriber(tiny_model.model_dir, graph_dir, None)
+    wt = pkg.KaldiNnet3WavTranscriber(tiny_model.model_dir, graph_dir, None)
+    wavs = []
+    for i, pcm in enumerate(utterances):
+        w = os.path.join(str(tmp_path), "c%03d.wav" % i)
+        synth.write_wav(w, pcm)
+        wavs.append(w)
+
+    async def chunks(pcm):
+        raw = np.asarray(pcm, dtype="<i2").tobytes()
+        for o in range(0, len(raw), 2560):          # 80 ms
+            yield raw[o:o + 2560]
+            await asyncio.sleep(0)                    # interleave the streams
+
+    async def lone():
+        out = []
+        for pcm in utterances:
+            out.append(await st.async_transcribe(chunks(pcm), tmp_path))
+        return out, [await wt.async_transcribe(w, tmp_path, nbest=3) for w in wavs]
+
+    async def burst(k):
+        streams = [st.async_transcribe(chunks(utterances[i % len(utterances)]), tmp_path) for i in range(k)]
+        files = [wt.async_transcribe(wavs[i % len(wavs)], tmp_path, nbest=3) for i in range(k)]
+        return await asyncio.gather(*streams), await asyncio.gather(*files)
+
+    want_s, want_w = asyncio.run(lone())
+    assert all(len(x) == 1 for x in want_s) and any(len(x) > 1 for x in want_w)
+    eng = st._get_engine()
+    assert eng is wt._get_engine()                   # one resident (model, graph) pair for both surfaces
+    before = len(eng.batcher.batches)
+    k = 64
+    got_s, got_w = asyncio.run(burst(k))
+    assert got_s == [want_s[i % len(utterances)] for i in range(k)]
+    assert got_w == [want_w[i % len(wavs)] for i in range(k)]
+    sizes = eng.batcher.batches[before:]
+    assert sum(sizes) == 2 * k and len(sizes) <= 8 and max(sizes) >= k // 2, sizes
+    # a request that cannot be decoded raises like the reference's failing process, and only for its caller
+    async def mixed():
+        return await asyncio.gather(wt.async_transcribe(wavs[0], tmp_path), wt.async_transcribe(str(tmp_path / "missing.wav"), tmp_path),
+                                    return_exceptions=True)
+    ok, err = asyncio.run(mixed())
+    assert ok == want_w[0][:1] and isinstance(err, RuntimeError) and "online2-wav-nnet3-latgen-faster" in str(err)

@@ -134,3 +134,51 @@ def test_shard_utterances_balances_audio():
         loads = [sum(dur[i] for i in p) for p in parts]
         assert max(loads) - min(loads) <= 5.0
     assert shard_utterances([], 4) == [[], [], [], []]
+
+
+def test_dynamic_batcher_groups_concurrent_requests():
+    """transcribe._Batcher: requests that arrive while a batch is running share the next device batch, grouped
+    by their n-best setting; a failing batch is retried per request so only the bad call raises."""
+    import threading
+    import time
+    from types import SimpleNamespace
+    from rhasspy_speech_b200 import transcribe as T
+
+    class FakeDecoder:
+        def __init__(self):
+            self.calls = []
+            self.nbest = None
+            self.gate = threading.Event()
+
+        def set_nbest(self, n, scale):
+            self.nbest = (n, scale)
+
+        def decode_wavs(self, paths):
+            self.gate.wait(5)
+            self.calls.append((self.nbest, list(paths)))
+            if any("bad" in p for p in paths):
+                raise T._lib.RsError("cannot open bad.wav")
+            n = len(paths)
+            return SimpleNamespace(words=[[len(p)] for p in paths], nbest=[[([len(p)], 0.0, 0.0)] for p in paths],
+                                   status=[0] * n, n_hyp=[1] * n)
+
+    dec = FakeDecoder()
+    b = T._Batcher(dec, threading.Lock(), max_batch=4)
+    first = b.submit("wav", "a.wav", 1, 1.0)            # starts running, blocks on the gate
+    time.sleep(0.05)
+    rest = [b.submit("wav", "u%d.wav" % i, 1, 1.0) for i in range(6)]
+    other = b.submit("wav", "n5.wav", 5, 1.0)           # different n-best: its own batch
+    bad = [b.submit("wav", name, 1, 0.5) for name in ("ok1.wav", "bad.wav", "ok22.wav")]
+    dec.gate.set()
+    assert first.result(5).words == [[5]]
+    assert [f.result(5).words[0] for f in rest] == [[6]] * 6
+    assert other.result(5).nbest == [[([6], 0.0, 0.0)]]
+    assert bad[0].result(5).words == [[7]] and bad[2].result(5).words == [[8]]
+    with pytest.raises(T._lib.RsError):
+        bad[1].result(5)
+    sizes = [len(p) for _, p in dec.calls]
+    assert sizes[:3] == [1, 4, 2]                       # lone request, then the burst in max_batch pieces
+    assert ((5, 1.0), ["n5.wav"]) in dec.calls
+    assert ((1, 0.5), ["ok1.wav", "bad.wav", "ok22.wav"]) in dec.calls     # the batch that failed ...
+    assert ((1, 0.5), ["bad.wav"]) in dec.calls                            # ... and its per-request retry
+    assert b.batches[:3] == [1, 4, 2]
