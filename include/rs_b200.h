@@ -101,6 +101,12 @@ const char *rs_graph_word(const rs_graph *g, int32_t id);
 
 rs_decoder *rs_decoder_create(rs_model *m, rs_graph *g, const rs_decoder_opts *opts, char *err, size_t errlen);
 void rs_decoder_free(rs_decoder *d);
+/* Hot graph swap: binds the decoder to another HCLG without rebuilding its device workspace.  The
+ * reference re-reads HCLG.fst in every call (ReadFstKaldiGeneric, online2-wav-nnet3-latgen-faster.cc:181), so a graph
+ * retrained by KaldiTrainer._mkgraph (rhasspy_speech/kaldi.py:409-425) is picked up by the next transcription; a resident
+ * decoder gets the same behaviour from rs_graph_load(new files) + this call.  The previous rs_graph stays valid and
+ * is freed by its owner.  On error the decoder keeps its previous graph. */
+int rs_decoder_set_graph(rs_decoder *d, rs_graph *g, char *err, size_t errlen);
 /* Replaces the `lattice-to-nbest --n=<nbest> --acoustic-scale=<acoustic_scale>` stage of the pipeline
  * (transcribe_wav.py:62-75, kaldi/src/latbin/lattice-to-nbest.cc:84-113) for every later decode call on this
  * decoder.  nbest == 1 with scale 1.0 (the default) returns the device back-trace of the best path; anything

@@ -61,6 +61,7 @@ SYMBOLS = [
     ("rs_graph_word", C.c_char_p, [_P, C.c_int32]),
     ("rs_decoder_create", _P, [_P, _P, C.POINTER(DecoderOpts)] + _ERR),
     ("rs_decoder_free", None, [_P]),
+    ("rs_decoder_set_graph", C.c_int, [_P, _P] + _ERR),
     ("rs_decoder_set_nbest", C.c_int, [_P, C.c_int32, C.c_float] + _ERR),
     ("rs_debug_lattice_nbest", C.c_int, [_P] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, _P]),
     ("rs_decode_pcm", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
@@ -275,6 +276,13 @@ class Decoder:
         err = C.create_string_buffer(ERRLEN)
         self.h = self.lib.rs_decoder_create(model.h, graph.h, C.byref(o), err, ERRLEN)
         _check(bool(self.h), err)
+
+    def set_graph(self, graph: "Graph"):
+        """Bind the decoder to another HCLG (rs_decoder_set_graph); the device workspace is kept."""
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_decoder_set_graph(self.h, graph.h, err, ERRLEN)
+        _check(rc == 0, err)
+        self.graph = graph
 
     def set_nbest(self, nbest: int = 1, acoustic_scale: float = 1.0):
         """lattice-to-nbest --n / --acoustic-scale for every later decode call (rs_decoder_set_nbest)."""

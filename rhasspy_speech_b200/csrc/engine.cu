@@ -386,7 +386,7 @@ struct DecoderImpl {
   int *d_range_flag = nullptr;  // set by a split store that had to saturate (fp16 planes)
   int *h_range_flag = nullptr;  // pinned
   std::unique_ptr<PackPool> pool;
-  std::vector<int4> earc_with_pdf;  // graph arcs with ilabel mapped to pdf for this model
+  DevBuf d_earc_buf;                // graph arcs with ilabel mapped to pdf for this model
   const int4 *d_earc = nullptr;
   rs_timings last{};
   // layout of the last batch (for rs_debug_fetch)
@@ -696,6 +696,29 @@ const char *rs_graph_word(const rs_graph *g_, int32_t id) {
   return gi->g.words[id].c_str();
 }
 
+// arcs with ilabel -> pdf (TransitionIdToPdfFast, decodable-online-looped.cc:249-256) for (model, graph)
+static void BindGraph(DecoderImpl *d, GraphImpl *gi) {
+  const Graph &g = gi->g;
+  const auto &t2p = d->model->m.trans.tid2pdf;
+  std::vector<int4> earc(g.e_next.size());
+  for (size_t i = 0; i < earc.size(); i++) {
+    int il = g.e_ilabel[i];
+    if (il <= 0 || il >= (int)t2p.size())
+      RS_FAIL("HCLG has input label " << il << " but the model has only " << t2p.size() - 1 << " transition-ids");
+    int wbits;
+    memcpy(&wbits, &g.e_weight[i], 4);
+    earc[i] = make_int4(g.e_next[i], t2p[il], wbits, g.e_olabel[i]);
+  }
+  // a fresh allocation, so that a failed bind leaves the decoder on its previous graph
+  DevBuf fresh;
+  fresh.ensure(std::max<size_t>(earc.size() * sizeof(int4), 16));
+  if (!earc.empty()) CUDA_OK(cudaMemcpy(fresh.p, earc.data(), earc.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  std::swap(d->d_earc_buf.p, fresh.p);
+  std::swap(d->d_earc_buf.cap, fresh.cap);
+  d->d_earc = d->d_earc_buf.as<int4>();
+  d->graph = gi;
+}
+
 rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts *opts, char *err, size_t errlen) {
   API_GUARD_BEGIN
   ModelImpl *mi = reinterpret_cast<ModelImpl *>(m_);
@@ -718,19 +741,7 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
   if (o.max_words < 1) o.max_words = 1;
   CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   for (auto &e : d->ev) CUDA_OK(cudaEventCreate(&e));
-  // arcs with ilabel -> pdf (TransitionIdToPdfFast, decodable-online-looped.cc:249-256)
-  const Graph &g = gi->g;
-  const auto &t2p = mi->m.trans.tid2pdf;
-  std::vector<int4> earc(g.e_next.size());
-  for (size_t i = 0; i < earc.size(); i++) {
-    int il = g.e_ilabel[i];
-    if (il <= 0 || il >= (int)t2p.size())
-      RS_FAIL("HCLG has input label " << il << " but the model has only " << t2p.size() - 1 << " transition-ids");
-    int wbits;
-    memcpy(&wbits, &g.e_weight[i], 4);
-    earc[i] = make_int4(g.e_next[i], t2p[il], wbits, g.e_olabel[i]);
-  }
-  d->d_earc = Upload(earc, &d->owned);
+  BindGraph(d.get(), gi);
   // lanes
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
@@ -787,6 +798,20 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
 }
 
 void rs_decoder_free(rs_decoder *d) { delete reinterpret_cast<DecoderImpl *>(d); }
+
+int rs_decoder_set_graph(rs_decoder *d_, rs_graph *g_, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  GraphImpl *gi = reinterpret_cast<GraphImpl *>(g_);
+  if (!d || !gi) RS_FAIL("rs_decoder_set_graph: decoder and graph are required");
+  if (d->model->device != gi->device) RS_FAIL("model and graph live on different devices");
+  CUDA_OK(cudaSetDevice(gi->device));
+  CUDA_OK(cudaStreamSynchronize(d->stream));
+  BindGraph(d, gi);
+  d->lat_hdr.clear();
+  return 0;
+  API_GUARD_END(1)
+}
 
 int rs_decoder_set_nbest(rs_decoder *d_, int32_t nbest, float acoustic_scale, char *err, size_t errlen) {
   API_GUARD_BEGIN
@@ -908,6 +933,7 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   p.cfg.hash_size = hash_size;
   p.cfg.arena_cap = o.max_tokens_per_utt;
   p.cfg.max_words = W;
+  p.cfg.lattice_beam = o.lattice_beam;
   p.cfg.profile = getenv("RS_B200_DECODE_PROFILE") != nullptr;
   {
     // shared-memory tables when the graph is small enough for two lanes per SM (<= 1024 states)

@@ -162,6 +162,7 @@ struct DecodeConfig {
   int max_words;
   int profile;      // debug: block 0 prints its per-phase clock counts (RS_B200_DECODE_PROFILE=1)
   int smem_slots;   // > 0: state tables in shared memory, addressed by state id (power of two >= num_states)
+  float lattice_beam;  // lattice mode: links worse than their destination by more than this are not recorded
 };
 
 struct LaneWorkspace {  // one per resident CTA; all pointers are device memory

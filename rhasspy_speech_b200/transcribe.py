@@ -65,7 +65,8 @@ def decode_meta(text: str) -> str:
 class _OneHyp:
     """The slice of a batch result that belongs to one request: what nbest_text() reads, for utterance 0."""
 
-    def __init__(self, hyp, u: int):
+    def __init__(self, hyp, u: int, graph=None):
+        self.graph = graph              # the graph this request was decoded on (its words.txt names the ids)
         self.words = [hyp.words[u]]
         self.nbest = [hyp.nbest[u]]
         self.status = [int(hyp.status[u])]
@@ -126,10 +127,13 @@ class _Batcher:
             self.decoder.set_nbest(nbest, scale)
             self.batches.append(len(payloads))
             if kind == "wav":
-                return self.decoder.decode_wavs([str(p) for p in payloads])
-            if kind == "stream":
-                return self.decoder.finish_streams(payloads)
-            return self.decoder.decode_pcm(payloads)
+                hyp = self.decoder.decode_wavs([str(p) for p in payloads])
+            elif kind == "stream":
+                hyp = self.decoder.finish_streams(payloads)
+            else:
+                hyp = self.decoder.decode_pcm(payloads)
+            hyp.graph = getattr(self.decoder, "graph", None)
+            return hyp
 
     def _run(self):
         while True:
@@ -140,14 +144,15 @@ class _Batcher:
             try:
                 hyp = self._decode(kind, [b[1] for b in batch], nbest, scale)
                 for u, b in enumerate(batch):
-                    b[4].set_result(_OneHyp(hyp, u))
+                    b[4].set_result(_OneHyp(hyp, u, hyp.graph))
             except Exception as first:  # noqa: BLE001 -- delivered to the caller(s) below
                 if len(batch) == 1:
                     batch[0][4].set_exception(first)
                     continue
                 for b in batch:             # isolate the offending request
                     try:
-                        b[4].set_result(_OneHyp(self._decode(kind, [b[1]], nbest, scale), 0))
+                        one = self._decode(kind, [b[1]], nbest, scale)
+                        b[4].set_result(_OneHyp(one, 0, one.graph))
                     except Exception as e:  # noqa: BLE001
                         b[4].set_exception(e)
 
@@ -160,20 +165,55 @@ class _Engine:
             if not Path(f).is_file():
                 # the reference fails with the Kaldi binary's stderr; keep its exception type and prefix
                 raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: cannot open %s" % f)
+        self.device = device
+        self.graph_files = (Path(hclg), Path(words_txt))
+        self.model_sig = _file_sig((final_mdl, online_conf))
+        self.graph_sig = _file_sig(self.graph_files)
         self.model = _lib.Model(str(final_mdl), str(online_conf), device)
         self.graph = _lib.Graph(str(hclg), str(words_txt), device)
         self.decoder = _lib.Decoder(self.model, self.graph, **opts)
         self.lock = threading.Lock()
         self.batcher = _Batcher(self.decoder, self.lock)
 
-    def words(self, ids: Sequence[int]) -> str:
+    def refresh_graph(self):
+        """Hot graph swap.  The reference reads HCLG.fst and words.txt in every call, so the graph
+        KaldiTrainer writes (kaldi.py:409-425) is used by the next transcription; the resident engine gets the same
+        behaviour by re-binding its decoder when the files changed (rs_graph_load + rs_decoder_set_graph: the model
+        and the decoder's device workspace stay)."""
+        sig = _file_sig(self.graph_files)
+        if sig == self.graph_sig:
+            return
+        with self.lock:
+            if sig == self.graph_sig:
+                return
+            try:
+                new = _lib.Graph(str(self.graph_files[0]), str(self.graph_files[1]), self.device)
+                self.decoder.set_graph(new)
+            except _lib.RsError as e:
+                raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
+            self.graph = new            # the old graph is freed when the last result decoded on it is gone
+            self.graph_sig = sig
+
+    def words(self, ids: Sequence[int], graph=None) -> str:
         out = []
         for i in ids:
-            w = self.graph.word(i)
+            w = (graph or self.graph).word(i)
             if w is None:
                 raise RuntimeError("Unexpected error running command int2sym.pl: undefined symbol %d" % i)
             out.append(w)
         return " ".join(out)
+
+
+def _file_sig(paths) -> Tuple:
+    """(mtime, size) of each file; missing files are left to the loader's error message."""
+    out = []
+    for p in paths:
+        try:
+            st = os.stat(p)
+            out.append((st.st_mtime_ns, st.st_size))
+        except OSError:
+            out.append(None)
+    return tuple(out)
 
 
 def _engine(final_mdl: Path, online_conf: Path, graph_dir: Path, device: int, max_active: int, beam: float,
@@ -181,6 +221,10 @@ def _engine(final_mdl: Path, online_conf: Path, graph_dir: Path, device: int, ma
     key = (str(final_mdl), str(online_conf), str(graph_dir), device, max_active, float(beam), float(lattice_beam))
     with _ENGINES_LOCK:
         eng = _ENGINES.get(key)
+        if eng is not None and eng.model_sig != _file_sig((final_mdl, online_conf)):
+            eng = None                  # a new acoustic model: rebuild the engine (the old one is garbage-collected)
+        if eng is not None:
+            eng.refresh_graph()
         if eng is None:
             try:
                 eng = _Engine(final_mdl, online_conf, graph_dir / "HCLG.fst", graph_dir / "words.txt", device,
@@ -249,7 +293,8 @@ class _Base:
             raise RuntimeError("Unexpected error running command lattice-to-nbest: --n must be >= 1")
         eng.decoder.set_nbest(nbest, self.acoustic_scale)
 
-    async def _finish(self, eng: _Engine, nbest_stdout: bytes, lang_dir, max_fuzzy_cost, require_fuzzy) -> List[str]:
+    async def _finish(self, eng: _Engine, nbest_stdout: bytes, lang_dir, max_fuzzy_cost, require_fuzzy,
+                      graph=None) -> List[str]:
         lang_dir = Path(lang_dir)
         fuzzy_result = await _fuzzy(nbest_stdout, lang_dir, self.tools)
         if fuzzy_result is not None:
@@ -263,7 +308,7 @@ class _Base:
             if line.startswith("utt-"):
                 parts = line.strip().split()
                 if len(parts) > 1:      # the reference drops hypotheses without words (transcribe_wav.py:99-103)
-                    texts.append(decode_meta(eng.words([int(x) for x in parts[1:]])))
+                    texts.append(decode_meta(eng.words([int(x) for x in parts[1:]], graph)))
         return texts
 
 
@@ -272,7 +317,7 @@ class KaldiNnet3WavTranscriber(_Base):
                                require_fuzzy: bool = False) -> List[str]:
         eng = self._get_engine()
         hyp = await self._submit(eng, "wav", wav_path, nbest, "online2-wav-nnet3-latgen-faster")
-        return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)
+        return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy, hyp.graph)
 
     async def async_transcribe_many(self, wav_paths: Sequence, lang_dir, nbest: int = 1,
                                     max_fuzzy_cost: Optional[float] = None,
@@ -315,7 +360,7 @@ class KaldiNnet3StreamTranscriber(_Base):
             hyp = await self._submit(eng, "stream", stream, nbest, "online2-cli-nnet3-decode-faster")
         finally:
             stream.close()
-        return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy)
+        return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy, hyp.graph)
 
     async def async_transcribe_rescore(self, *args, **kwargs):
         raise NotImplementedError("lattice rescoring (reference transcribe_stream.py:131-243) is scope row f3")

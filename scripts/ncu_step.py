@@ -10,6 +10,8 @@ utts = synth.make_utterances(n, seed=1234)
 model = _lib.Model(p.final_mdl, p.online_conf, 0)
 graph = _lib.Graph(p.hclg, p.words_txt, 0)
 dec = _lib.Decoder(model, graph)
+if len(sys.argv) > 3:       # n-best tail: lattice recording + lattice_prune_kernel
+    dec.set_nbest(int(sys.argv[3]))
 for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     hyp = dec.decode_pcm(utts)
     print(dec.timings())

@@ -56,3 +56,46 @@ def test_concurrent_streams_and_wavs_share_device_batches(tiny_model, utterances
                                     return_exceptions=True)
     ok, err = asyncio.run(mixed())
     assert ok == want_w[0][:1] and isinstance(err, RuntimeError) and "online2-wav-nnet3-latgen-faster" in str(err)
+
+
+def test_retrained_graph_is_picked_up_without_restart(ref, synth, utterances, tmp_path):
+    """the reference reads HCLG.fst per call, so the graph KaldiTrainer rewrites is used by the next
+    transcription.  The resident engine re-binds its decoder when the files change (rs_decoder_set_graph)."""
+    import asyncio
+    import dataclasses
+    import shutil
+    import rhasspy_speech_b200 as pkg
+    a = synth.write_model(str(tmp_path / "a"), synth.TINY)
+    b = synth.write_model(str(tmp_path / "b"), dataclasses.replace(synth.TINY, graph="arpa", vocab_size=120, bigrams_per_word=6, eps_hops=2))
+    assert open(a.final_mdl, "rb").read() == open(b.final_mdl, "rb").read()       # same acoustic model, other graph
+    wav = str(tmp_path / "x.wav")
+    synth.write_wav(wav, utterances[2])
+
+    def reference(p):
+        want, _, _ = ref.transcribe_wavs(a.final_mdl, a.online_conf, p.hclg, p.words_txt, [wav])
+        words = {int(l.split()[1]): l.split()[0] for l in open(p.words_txt)}
+        return [" ".join(words[i] for i in want["utt00000-1"])] if want.get("utt00000-1") else []
+    tr = pkg.KaldiNnet3WavTranscriber(a.model_dir, a.graph_dir, None)
+    legacy = pkg.KaldiTranscriber(os.path.join(a.model_dir, "model"), a.graph_dir)
+    first = asyncio.run(tr.async_transcribe(wav, tmp_path))
+    assert first == reference(a) and first
+    eng = tr._get_engine()
+    n_states_a = eng.graph.num_states
+    # "retrain": the graph files are replaced in place
+    for f in ("HCLG.fst", "words.txt"):
+        shutil.copyfile(os.path.join(b.graph_dir, f), os.path.join(a.graph_dir, f))
+    second = asyncio.run(tr.async_transcribe(wav, tmp_path))
+    assert second == reference(b) and second and second != first
+    assert tr._get_engine() is eng and eng.graph.num_states != n_states_a          # same engine, new graph
+    assert legacy.transcribe_wav(wav) == second[0]
+    # n-best on the swapped graph
+    many = asyncio.run(tr.async_transcribe(wav, tmp_path, nbest=3))
+    assert many[:1] == second and len(many) >= 1
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_run
+    if not ref_run.available():
+        pytest.skip("oracle/_ref not built")
+    return ref_run
