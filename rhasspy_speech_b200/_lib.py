@@ -200,21 +200,32 @@ class Hypotheses:
         self.acoustic_cost = arr(r.acoustic_cost, n)
         self.num_frames = arr(r.num_frames, n)
         self.status = arr(r.status, n)
-        # every hypothesis, best first: nbest[u] = [(word ids, graph cost, acoustic cost), ...]
-        self.nbest: List[List[tuple]] = [[] for _ in range(n)]
+        # every hypothesis, best first: nbest[u] = [(word ids, graph cost, acoustic cost), ...]; built on first use
+        # (the single-best path of a 256-utterance batch should not pay for 256 tuples it never reads)
+        self._nbest: Optional[List[List[tuple]]] = None
+        self._hyp = None
         if n and self.n_hyp.max(initial=0) > 1:
             ho = arr(r.hyp_offset, n + 1)
             total = int(ho[-1])
             wo = arr(r.hyp_word_offset, total + 1)
-            wid = arr(r.hyp_word_ids, int(wo[-1]) if total else 0)
-            gc, ac = arr(r.hyp_graph_cost, total), arr(r.hyp_acoustic_cost, total)
-            for u in range(n):
-                self.nbest[u] = [([int(x) for x in wid[wo[h]:wo[h + 1]]], float(gc[h]), float(ac[h]))
-                                 for h in range(int(ho[u]), int(ho[u + 1]))]
-        else:
-            for u in range(n):
-                if self.n_hyp[u]:
-                    self.nbest[u] = [(self.words[u], float(self.graph_cost[u]), float(self.acoustic_cost[u]))]
+            self._hyp = (ho, wo, arr(r.hyp_word_ids, int(wo[-1]) if total else 0), arr(r.hyp_graph_cost, total),
+                         arr(r.hyp_acoustic_cost, total))
+
+    @property
+    def nbest(self) -> List[List[tuple]]:
+        if self._nbest is None:
+            out: List[List[tuple]] = [[] for _ in range(self.n_utts)]
+            if self._hyp is not None:
+                ho, wo, wid, gc, ac = self._hyp
+                for u in range(self.n_utts):
+                    out[u] = [([int(x) for x in wid[wo[h]:wo[h + 1]]], float(gc[h]), float(ac[h]))
+                              for h in range(int(ho[u]), int(ho[u + 1]))]
+            else:
+                for u in range(self.n_utts):
+                    if self.n_hyp[u]:
+                        out[u] = [(self.words[u], float(self.graph_cost[u]), float(self.acoustic_cost[u]))]
+            self._nbest = out
+        return self._nbest
 
 
 class Model:

@@ -338,10 +338,12 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       loff = P.lat.cost_offset + (size_t)u * (P.lat.max_t + 1);
       arena_cap = min(arena_cap, P.lat.tok_cap);
     }
-    auto add_link = [&](int src, int dst, unsigned arc) {
+    // slack = (cost through the link) - (destination's cost), the bracket of PruneForwardLinks' link_extra_cost
+    // (:330-332) in its float order; stored with the link so that the pruning sweep touches no token or arc
+    auto add_link = [&](int src, int dst, unsigned arc, float slack) {
       const int li = atomicAdd(&S.n_links, 1);
       if (li < P.lat.link_cap)
-        llink[li] = make_int4(src, dst, (int)arc, 0);
+        llink[li] = make_int4(src, dst, (int)arc, __float_as_int(slack));
       else
         S.lat_overflow = 1;
     };
@@ -492,8 +494,10 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           if (tot < cutoff) {
             const int ss = find_slot(ws.hkey[tb], arc.x, mask, identity);
             const int dpos = ss >= 0 ? ws.hidx[tb][ss] : -1;
-            if (dpos >= 0 && !(__fsub_rn(tot, ws.tok_cost[tb][dpos]) > cfg.lattice_beam))
-              add_link(base_new + pos, base_new + dpos, NE + a);
+            if (dpos >= 0) {
+              const float slack = __fsub_rn(tot, ws.tok_cost[tb][dpos]);
+              if (!(slack > cfg.lattice_beam)) add_link(base_new + pos, base_new + dpos, NE + a, slack);
+            }
           }
         }
       }
@@ -697,8 +701,10 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           if (tot < next_cutoff) {
             const int ss = find_slot(ws.hkey[nxt], arc.x, mask, identity);
             const int dpos = ss >= 0 ? ws.hidx[nxt][ss] : -1;
-            if (dpos >= 0 && !(__fsub_rn(tot, ws.tok_cost[nxt][dpos]) > cfg.lattice_beam))
-              add_link(base_cur + lo, base_new + dpos, ai);
+            if (dpos >= 0) {
+              const float slack = __fsub_rn(tot, ws.tok_cost[nxt][dpos]);
+              if (!(slack > cfg.lattice_beam)) add_link(base_cur + lo, base_new + dpos, ai, slack);
+            }
           }
         }
         __syncthreads();
@@ -839,6 +845,8 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
 // removes links this final pass removes as well (its extra costs are lower bounds of the final ones).
 // Then the survivors are renumbered and written as compact arcs (GetRawLattice :106-189: olabel, graph cost,
 // acoustic cost without the per-frame offset) behind a global cursor.
+constexpr int kPruneWin = 4096;   // tokens of one time whose extra costs fit the shared-memory window
+constexpr int kPrunePos = 2048;   // staged link-position entries (utterances up to 1022 decoded frames)
 __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_constant__ DecodeParams P, float lattice_beam,
                                                                LatticeHeader *headers, LatticeArc *arcs, int arcs_cap,
                                                                int *cursor) {
@@ -864,9 +872,22 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
   const int ntok = ltb[T + 1];
   const int nlink = lpos[2 * (T + 1)];
   for (int i = tid; i < ntok; i += NT) extra[i] = 0x7f800000u;
+  // The sweep is a chain of short, dependent steps (133 times x a few hundred links), so it is bound by latency,
+  // not by bytes: the extra costs of the two times in flight live in shared memory windows (global memory when a
+  // time holds more than kPruneWin tokens), the position tables are staged in shared memory, and every thread
+  // fetches its links of the NEXT time step before it works on the current one.
+  __shared__ unsigned win[2][kPruneWin];
+  __shared__ int s_pos[kPrunePos], s_tb[kPrunePos / 2];
+  const bool staged = 2 * T + 3 <= kPrunePos;
+  if (staged) {
+    for (int i = tid; i < 2 * T + 3; i += NT) s_pos[i] = lpos[i];
+    for (int i = tid; i < T + 2; i += NT) s_tb[i] = ltb[i];
+  }
   __syncthreads();
+  const int *pos = staged ? s_pos : lpos;
+  const int *tb = staged ? s_tb : ltb;
   // ---- last time: final costs (ComputeFinalCosts :536-577)
-  const int f0 = ltb[T], f1 = ltb[T + 1];
+  const int f0 = tb[T], f1 = tb[T + 1];
   int anyf = 0;
   for (int i = f0 + tid; i < f1; i += NT) anyf |= g.final_cost[ltok[i].x] != kInf;
   anyf = __syncthreads_or(anyf);
@@ -885,40 +906,48 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
   }
   const float final_best = S.best_cost;
   __syncthreads();
+  int wsel = 0;
+  unsigned *cur = (f1 - f0 <= kPruneWin) ? win[wsel] : extra + f0;  // extra costs of time t, indexed by token - tb[t]
+  unsigned *nxt = nullptr;                                          // ... of time t + 1
+  int b0 = f0, b1 = f1;
   for (int i = f0 + tid; i < f1; i += NT) {
     const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
     float e = __fsub_rn(__fadd_rn(__int_as_float(ltok[i].y), fc), final_best);
     if (e < 0.f) e = 0.f;
-    if (!(e > lattice_beam)) extra[i] = __float_as_uint(e);
+    cur[i - f0] = (e > lattice_beam) ? 0x7f800000u : __float_as_uint(e);
+  }
+  // link_extra_cost = extra_cost[next] + slack (:330-332); the slack was stored by decode_kernel<true>
+  auto ldx = [](const unsigned *p) { return __uint_as_float(*reinterpret_cast<const volatile unsigned *>(p)); };
+  int4 pf_e = make_int4(0, 0, 0, 0), pf_p = make_int4(0, 0, 0, 0);
+  {
+    const int p0 = pos[2 * T + 1], p1 = pos[2 * T + 2];
+    if (p0 + tid < p1) pf_p = llink[p0 + tid];
   }
   __syncthreads();
-  auto link_extra = [&](const int4 &l, float acoustic) -> float {
-    const float en = __uint_as_float(*reinterpret_cast<volatile unsigned *>(extra + l.y));
-    const int4 a = (unsigned)l.z < NE ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
-    const float through = __fadd_rn(__fadd_rn(__int_as_float(ltok[l.x].y), acoustic), __int_as_float(a.z));
-    return __fadd_rn(en, __fsub_rn(through, __int_as_float(ltok[l.y].y)));
-  };
   for (int t = T; t >= 0; t--) {
-    const int e0 = lpos[2 * t + 2], e1 = t < T ? lpos[2 * t + 3] : e0;  // emitting links t -> t + 1
-    const int p0 = lpos[2 * t + 1], p1 = lpos[2 * t + 2];              // epsilon links inside t
-    const float *ll = P.loglikes + (size_t)(P.ll_row0[u] + t) * P.ld;
-    const float off = t < T ? loff[t] : 0.f;
-    for (int i = e0 + tid; i < e1; i += NT) {
-      const int4 l = llink[i];
-      float le = link_extra(l, __fsub_rn(off, ll[g.earc[l.z].y]));
-      if (!(le > lattice_beam)) atomicMin(extra + l.x, __float_as_uint(fmaxf(le, 0.f)));
+    const int e0 = pos[2 * t + 2], e1 = t < T ? pos[2 * t + 3] : e0;  // emitting links t -> t + 1
+    const int p0 = pos[2 * t + 1], p1 = pos[2 * t + 2];              // epsilon links inside t
+    const int4 my_e = pf_e, my_p = pf_p;
+    if (t > 0) {  // links of the next step, in flight while this one is processed
+      const int ne0 = pos[2 * t], ne1 = pos[2 * t + 1], np0 = pos[2 * t - 1];
+      if (ne0 + tid < ne1) pf_e = llink[ne0 + tid];
+      if (np0 + tid < ne0) pf_p = llink[np0 + tid];
     }
+    for (int i = e0 + tid; i < e1; i += NT) {
+      const int4 l = i < e0 + NT ? my_e : llink[i];
+      const float le = __fadd_rn(ldx(nxt + (l.y - b1)), __int_as_float(l.w));
+      if (!(le > lattice_beam)) atomicMin(cur + (l.x - b0), __float_as_uint(fmaxf(le, 0.f)));
+    }
+    if (tid == 0) s_changed = 0;
     __syncthreads();
-    while (true) {
-      if (tid == 0) s_changed = 0;
-      __syncthreads();
+    while (p1 > p0) {
       int ch = 0;
       for (int i = p0 + tid; i < p1; i += NT) {
-        const int4 l = llink[i];
-        float le = link_extra(l, 0.f);
+        const int4 l = i < p0 + NT ? my_p : llink[i];
+        const float le = __fadd_rn(ldx(cur + (l.y - b0)), __int_as_float(l.w));
         if (!(le > lattice_beam)) {
           const unsigned v = __float_as_uint(fmaxf(le, 0.f));
-          if (v < atomicMin(extra + l.x, v)) ch = 1;
+          if (v < atomicMin(cur + (l.x - b0), v)) ch = 1;
         }
       }
       if (ch) s_changed = 1;
@@ -926,24 +955,29 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
       const int again = s_changed;
       __syncthreads();
       if (!again) break;
+      if (tid == 0) s_changed = 0;
+      __syncthreads();
     }
-    // extras of time t and t + 1 are final: excise / keep, and store the lattice's acoustic cost
-    // (GetRawLattice subtracts the frame's cost offset again, :158-165)
+    // extras of time t and t + 1 are final: excise the links beyond the beam, publish the extras of time t
     for (int i = e0 + tid; i < e1; i += NT) {
-      int4 l = llink[i];
-      const float ac = __fsub_rn(off, ll[g.earc[l.z].y]);
-      const float nll = __fsub_rn(ac, off);  // "l->acoustic_cost - cost_offset" (:160), rounding included
-      const float le = link_extra(l, ac);
-      if (le > lattice_beam) l.x = -1;
-      l.w = __float_as_int(nll);
-      llink[i] = l;
+      const int4 l = i < e0 + NT ? my_e : llink[i];
+      if (__fadd_rn(ldx(nxt + (l.y - b1)), __int_as_float(l.w)) > lattice_beam) llink[i].x = -1;
     }
     for (int i = p0 + tid; i < p1; i += NT) {
-      int4 l = llink[i];
-      const float le = link_extra(l, 0.f);
-      if (le > lattice_beam) l.x = -1;
-      l.w = 0;
-      llink[i] = l;
+      const int4 l = i < p0 + NT ? my_p : llink[i];
+      if (__fadd_rn(ldx(cur + (l.y - b0)), __int_as_float(l.w)) > lattice_beam) llink[i].x = -1;
+    }
+    if (cur != extra + b0)
+      for (int i = tid; i < b1 - b0; i += NT) extra[b0 + i] = cur[i];
+    __syncthreads();  // every reader of the t + 1 window is done before it is recycled
+    if (t > 0) {  // time t - 1 becomes the current one
+      nxt = cur;
+      b1 = b0;
+      b0 = tb[t - 1];
+      wsel ^= 1;
+      cur = (b1 - b0 <= kPruneWin) ? win[wsel] : extra + b0;
+      if (cur != extra + b0)
+        for (int i = tid; i < b1 - b0; i += NT) cur[i] = 0x7f800000u;
     }
     __syncthreads();
   }
@@ -986,8 +1020,22 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
     unsigned total;
     const unsigned ex = block_excl_scan(keep, S, &total);
     if (keep) {
-      const int4 a = (unsigned)l.z < NE ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
-      arcs[base + running + ex] = LatticeArc{newid[l.x], newid[l.y], a.w, __int_as_float(a.z), __int_as_float(l.w)};
+      const bool emitting = (unsigned)l.z < NE;
+      const int4 a = emitting ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
+      float acoustic = 0.f;
+      if (emitting) {
+        // the link's time: the last position entry <= i is the start of its group, entry 2t + 2 = links t -> t + 1;
+        // GetRawLattice's acoustic cost is (offset - loglike) - offset, rounding included (:158-165)
+        int lo = 0, hi = 2 * (T + 1);
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (lpos[mid] <= i) lo = mid; else hi = mid;
+        }
+        const int t = (lo - 2) >> 1;
+        const float off = loff[t];
+        acoustic = __fsub_rn(__fsub_rn(off, P.loglikes[(size_t)(P.ll_row0[u] + t) * P.ld + a.y]), off);
+      }
+      arcs[base + running + ex] = LatticeArc{newid[l.x], newid[l.y], a.w, __int_as_float(a.z), acoustic};
     }
     running += total;
   }
