@@ -169,6 +169,19 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
 int rs_debug_lattice_nbest(const int32_t *src, const int32_t *dst, const int32_t *olabel, const float *graph,
                            const float *acoustic, int32_t n_arcs, int32_t n_nodes, int32_t n, float acoustic_scale,
                            int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost);
+/* Fuzzy matcher in process (host only, no GPU): replaces the seven-process OpenFst pipeline of
+ * rhasspy_speech/transcribe_util.py:46-60 (fstcompile | fstcompose - G.fuzzy.fst | fstshortestpath | fstrmepsilon |
+ * fsttopsort | fstproject --project_type=output | fstprint).  rs_fuzzy_load reads lang_dir/G.fuzzy.fst (OpenFst vector
+ * or const FST over StdArc, embedded symbol tables skipped) and lang_dir/words.txt.  rs_fuzzy_match takes the n-best
+ * hypotheses (word ids of hypothesis k = word_ids[hyp_offset[k] .. hyp_offset[k+1]), rank k penalised 0.1 * k per
+ * word, transcribe_util.py:28-40) and returns the output word ids of the cheapest match and the cost the reference
+ * computes from fstprint's arc lines.  Returns 0 = match, 1 = no path (the reference's `None`), < 0 error. */
+typedef struct rs_fuzzy rs_fuzzy;
+rs_fuzzy *rs_fuzzy_load(const char *g_fuzzy_fst, const char *words_txt, char *err, size_t errlen);
+void rs_fuzzy_free(rs_fuzzy *f);
+int rs_fuzzy_match(const rs_fuzzy *f, const int32_t *word_ids, const int32_t *hyp_offset, int32_t n_hyp, int32_t *out_ids,
+                   int32_t max_out, int32_t *n_out, float *cost, char *err, size_t errlen);
+const char *rs_fuzzy_word(const rs_fuzzy *f, int32_t id);
 /* Text description of the compiled acoustic-model plan (one line per launch). */
 const char *rs_model_plan(const rs_model *m);
 

@@ -144,6 +144,12 @@ def main():
     n.append("build %s: cc %s" % (probe_o, os.path.join(HERE, "ref_probe.cc")))
     n.append("build %s: link %s | %s" % (probe_e, probe_o, lib))
     targets.append(probe_e)
+    # OpenFst side of the fuzzy matcher (fstcompile / fstcompose / fstshortestpath / ... through the library)
+    fz_o = os.path.join(OUT, "obj", "bin__fuzzy-probe.o")
+    fz_e = os.path.join(OUT, "bin", "fuzzy-probe")
+    n.append("build %s: cc %s" % (fz_o, os.path.join(HERE, "fuzzy_probe.cc")))
+    n.append("build %s: link %s | %s" % (fz_e, fz_o, lib))
+    targets.append(fz_e)
     n.append("default " + " ".join(targets))
     with open(os.path.join(OUT, "build.ninja"), "w") as f:
         f.write("\n".join(n) + "\n")

@@ -299,3 +299,47 @@ def decode_loglikes_lattice(final_mdl: str, hclg: str, loglikes: Sequence[np.nda
         lm = {l.split()[0]: float(l.split()[1]) for l in open(os.path.join(tmp, "lm.txt")) if l.strip()}
         ac = {l.split()[0]: float(l.split()[1]) for l in open(os.path.join(tmp, "ac.txt")) if l.strip()}
     return parse_lattice_text(raw.decode()), {k: (words[k], lm[k], ac[k]) for k in words}
+
+
+# ----------------------------------------------------------------------------------------------
+# fuzzy matcher (rhasspy_speech/transcribe_util.py:11-88) through the reference's OpenFst (oracle/fuzzy_probe.cc)
+
+
+def fuzzy_available() -> bool:
+    return os.path.isfile(os.path.join(BIN, "fuzzy-probe"))
+
+
+def fuzzy_compile(text_fst: str, words_txt: str, out_fst: str):
+    """fstcompile --isymbols=words.txt --osymbols=words.txt --keep_isymbols --keep_osymbols (kaldi.py:390-407)."""
+    run("fuzzy-probe compile %s %s %s" % (text_fst, words_txt, out_fst))
+
+
+def fuzzy_reference(nbest: Sequence[Sequence[int]], g_fuzzy_fst: str, words_txt: str) -> Optional[Tuple[str, float]]:
+    """get_fuzzy_text restated around the probe: the text FST exactly as hassil_fst.Fst.write prints it
+    (one chain per hypothesis, every arc weighted with the running penalty), then the parse of fstprint's output."""
+    lines, finals = [], []
+    penalty = 0
+    nstate = 0
+    for hyp in nbest:
+        state = 0
+        for w in hyp:
+            nstate += 1
+            lines.append("%d %d %s %s %s" % (state, nstate, w, w, penalty))
+            state = nstate
+        finals.append(state)
+        penalty += 0.1
+    for s in dict.fromkeys(finals):
+        lines.append(str(s))
+    out, _ = run("fuzzy-probe fuzzy %s %s" % (g_fuzzy_fst, words_txt), input=("\n".join(lines) + "\n").encode())
+    words: List[str] = []
+    cost = 0.0
+    for line in out.decode().splitlines():
+        parts = line.strip().split()
+        if len(parts) < 4:
+            continue
+        if len(parts) > 4:
+            cost += float(parts[4])
+        if parts[3] == "<eps>":
+            continue
+        words.append(parts[3])
+    return (" ".join(words), cost) if words else None

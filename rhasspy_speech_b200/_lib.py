@@ -61,6 +61,10 @@ SYMBOLS = [
     ("rs_graph_word", C.c_char_p, [_P, C.c_int32]),
     ("rs_decoder_create", _P, [_P, _P, C.POINTER(DecoderOpts)] + _ERR),
     ("rs_decoder_free", None, [_P]),
+    ("rs_fuzzy_load", _P, [C.c_char_p, C.c_char_p] + _ERR),
+    ("rs_fuzzy_free", None, [_P]),
+    ("rs_fuzzy_match", C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float)] + _ERR),
+    ("rs_fuzzy_word", C.c_char_p, [_P, C.c_int32]),
     ("rs_decoder_set_graph", C.c_int, [_P, _P] + _ERR),
     ("rs_decoder_set_nbest", C.c_int, [_P, C.c_int32, C.c_float] + _ERR),
     ("rs_debug_lattice_nbest", C.c_int, [_P] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, _P]),
@@ -226,6 +230,42 @@ class Hypotheses:
                         out[u] = [(self.words[u], float(self.graph_cost[u]), float(self.acoustic_cost[u]))]
             self._nbest = out
         return self._nbest
+
+
+class Fuzzy:
+    """lang_dir/G.fuzzy.fst + words.txt resident on the host (rs_fuzzy_*): rhasspy's fuzzy matcher without OpenFst tools."""
+
+    def __init__(self, g_fuzzy_fst: str, words_txt: str):
+        self.lib = load_library()
+        err = C.create_string_buffer(ERRLEN)
+        self.h = self.lib.rs_fuzzy_load(os.fsencode(g_fuzzy_fst), os.fsencode(words_txt), err, ERRLEN)
+        _check(bool(self.h), err)
+
+    def match(self, hyps: Sequence[Sequence[int]]):
+        """hyps: word ids per hypothesis, best first -> (output word ids, cost) or None when nothing matches."""
+        flat = np.array([w for h in hyps for w in h], dtype=np.int32)
+        off = np.zeros(len(hyps) + 1, np.int32)
+        off[1:] = np.cumsum([len(h) for h in hyps])
+        out = np.zeros(4096, np.int32)
+        n, cost = C.c_int32(), C.c_float()
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_fuzzy_match(self.h, flat.ctypes.data, off.ctypes.data, len(hyps), out.ctypes.data, len(out),
+                                     C.byref(n), C.byref(cost), err, ERRLEN)
+        _check(rc >= 0, err)
+        if rc == 1:
+            return None
+        return [int(x) for x in out[:n.value]], float(cost.value)
+
+    def word(self, i: int) -> Optional[str]:
+        w = self.lib.rs_fuzzy_word(self.h, i)
+        return w.decode() if w is not None else None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rs_fuzzy_free(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 class Model:

@@ -245,15 +245,50 @@ def nbest_text(hyp: "_lib.Hypotheses", utt: int) -> bytes:
                    for k, (words, _, _) in enumerate(hyp.nbest[utt])).encode()
 
 
+_FUZZY: Dict[str, Tuple[Tuple, "_lib.Fuzzy"]] = {}
+_FUZZY_LOCK = threading.Lock()
+
+
+def _fuzzy_matcher(lang_dir: Path) -> "_lib.Fuzzy":
+    """lang_dir/G.fuzzy.fst + words.txt, loaded once and reloaded when training rewrote them."""
+    files = (lang_dir / "G.fuzzy.fst", lang_dir / "words.txt")
+    sig = _file_sig(files)
+    with _FUZZY_LOCK:
+        hit = _FUZZY.get(str(lang_dir))
+        if hit is None or hit[0] != sig:
+            try:
+                hit = (sig, _lib.Fuzzy(str(files[0]), str(files[1])))
+            except _lib.RsError as e:
+                raise RuntimeError("Unexpected error running command fstcompose: %s" % e) from e
+            _FUZZY[str(lang_dir)] = hit
+        return hit[1]
+
+
 async def _fuzzy(nbest_stdout: bytes, lang_dir: Path, tools) -> Optional[Tuple[str, float]]:
-    """Out-of-vocabulary rejection (reference transcribe_util.py:11-88) is kept on the reference's own
-    OpenFst tools: a 'next' row of the scope table.  Without G.fuzzy.fst it is a no-op, as there."""
+    """Out-of-vocabulary rejection (reference transcribe_util.py:11-88) in process: the hypotheses of
+    ``nbest_stdout`` against lang_dir/G.fuzzy.fst (csrc/fuzzy.cc replaces fstcompile | fstcompose | fstshortestpath |
+    fstrmepsilon | fsttopsort | fstproject | fstprint).  Without G.fuzzy.fst it is a no-op, as there.
+    RS_B200_FUZZY=tools keeps the reference's own OpenFst pipeline (needs KaldiTools)."""
     if not (lang_dir / "G.fuzzy.fst").exists():
         return None
-    if tools is None or not hasattr(tools, "async_run_pipeline"):
-        raise RuntimeError("Unexpected error running command fstcompile: G.fuzzy.fst is present but no KaldiTools were given")
-    from rhasspy_speech.transcribe_util import get_fuzzy_text  # the unchanged reference tail
-    return await get_fuzzy_text(nbest_stdout, lang_dir, tools)
+    if os.environ.get("RS_B200_FUZZY") == "tools":
+        if tools is None or not hasattr(tools, "async_run_pipeline"):
+            raise RuntimeError("Unexpected error running command fstcompile: G.fuzzy.fst is present but no KaldiTools were given")
+        from rhasspy_speech.transcribe_util import get_fuzzy_text  # the unchanged reference tail
+        return await get_fuzzy_text(nbest_stdout, lang_dir, tools)
+    hyps = [[int(x) for x in line.split()[1:]] for line in nbest_stdout.decode("utf-8").splitlines() if line.strip()]
+    if not hyps:
+        return None
+    fz = _fuzzy_matcher(lang_dir)
+    try:
+        hit = fz.match(hyps)
+    except _lib.RsError as e:
+        raise RuntimeError("Unexpected error running command fstcompose: %s" % e) from e
+    if hit is None:
+        return None
+    words = [fz.word(i) or "" for i in hit[0]]
+    words = [w for w in words if w and w != "<eps>"]
+    return (" ".join(words), hit[1]) if words else None
 
 
 class _Base:

@@ -1,0 +1,161 @@
+"""Row f2: the in-process fuzzy matcher (csrc/fuzzy.cc) against the reference's OpenFst pipeline
+(fstcompile | fstcompose - G.fuzzy.fst | fstshortestpath | fstrmepsilon | fsttopsort | fstproject | fstprint,
+rhasspy_speech/transcribe_util.py:46-60), run through the reference's own OpenFst library by oracle/fuzzy_probe.cc.
+Host only."""
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from rhasspy_speech_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_run
+    if not ref_run.fuzzy_available():
+        pytest.skip("oracle/_ref/bin/fuzzy-probe not built")
+    return ref_run
+
+
+VOCAB = ["turn", "on", "off", "the", "light", "lights", "kitchen", "bedroom", "what", "time", "is", "it", "set", "timer",
+         "for", "five", "ten", "minutes", "please", "__output:ORSXE3Q=", "__output:NNUXIY3IMVXA====", "_meta", "<unk>"]
+
+
+def write_grammar(tmp, seed, n_sent=6):
+    """A sentence grammar as rhasspy writes it, then the self loops of kaldi.py:360-389, compiled like kaldi.py:390-407."""
+    rng = np.random.default_rng(seed)
+    words_txt = os.path.join(tmp, "words.txt")
+    with open(words_txt, "w") as f:
+        f.write("<eps> 0\n")
+        for i, w in enumerate(VOCAB):
+            f.write("%s %d\n" % (w, i + 1))
+    plain = [w for w in VOCAB if w[0] not in "<_"]
+    arcs, finals, nstate = [], [], 0
+    for _ in range(n_sent):
+        state = 0
+        if rng.random() < 0.5:                                 # a weighted <eps>:<eps> arc in front
+            nstate += 1
+            arcs.append((state, nstate, "<eps>", "<eps>", round(float(rng.uniform(0.1, 2.0)), 3)))
+            state = nstate
+        for _ in range(int(rng.integers(2, 6))):
+            w = plain[int(rng.integers(len(plain)))]
+            out = w
+            r = rng.random()
+            if r < 0.15:
+                out = "<eps>"
+            elif r < 0.3:
+                out = VOCAB[19 + int(rng.integers(2))]          # meta output word
+            nstate += 1
+            arcs.append((state, nstate, w, out, round(float(rng.uniform(0.0, 1.5)), 3)))
+            state = nstate
+            if rng.random() < 0.2:                              # <eps> input with an output word
+                nstate += 1
+                arcs.append((state, nstate, "<eps>", "_meta", 0.25))
+                state = nstate
+        if rng.random() < 0.5:
+            # trailing <eps>:<eps>: fstrmepsilon folds it into the final weight.  Weight 0, because with a weight the
+            # sum the reference reads off fstprint depends on how fstshortestpath breaks the tie between "skip the
+            # remaining words, then take the arc" and "take the arc, then skip" (equal cost, different print-out)
+            nstate += 1
+            arcs.append((state, nstate, "<eps>", "<eps>", 0.0))
+            state = nstate
+        finals.append((state, round(float(rng.uniform(0.0, 1.0)), 3)))
+    text = os.path.join(tmp, "G.fuzzy.fst.txt")
+    states = sorted({a[0] for a in arcs} | {a[1] for a in arcs})
+    with open(text, "w") as f:
+        for a in arcs:
+            f.write("%d %d %s %s %s\n" % a)
+        for s, w in finals:
+            f.write("%d %s\n" % (s, w))
+        for s in states:
+            f.write("%d %d <eps> <eps> 0.0\n" % (s, s))
+            for w in VOCAB:
+                if w[0] in "<_":
+                    continue
+                f.write("%d %d %s <eps> 1.0\n" % (s, s, w))
+    return text, words_txt, arcs
+
+
+def test_fuzzy_match_equals_reference_pipeline(lib, ref, tmp_path):
+    n_match = n_none = 0
+    for seed in range(4):
+        text, words_txt, arcs = write_grammar(str(tmp_path), seed)
+        fst = os.path.join(str(tmp_path), "G.fuzzy.%d.fst" % seed)
+        ref.fuzzy_compile(text, words_txt, fst)
+        fz = lib.Fuzzy(fst, words_txt)
+        rng = np.random.default_rng(100 + seed)
+        plain_ids = [i + 1 for i, w in enumerate(VOCAB) if w[0] not in "<_"]
+        sentences = []
+        cur = []
+        for a in arcs:                                          # the grammar's own word sequences
+            if a[0] == 0 and cur:
+                sentences.append(cur)
+                cur = []
+            if a[2] != "<eps>":
+                cur.append(VOCAB.index(a[2]) + 1)
+        sentences.append(cur)
+        for case in range(30):
+            nbest = []
+            for _ in range(int(rng.integers(1, 6))):
+                hyp = list(sentences[int(rng.integers(len(sentences)))])
+                for _ in range(int(rng.integers(0, 3))):        # insert extra words / drop words
+                    if hyp and rng.random() < 0.4:
+                        hyp.pop(int(rng.integers(len(hyp))))
+                    else:
+                        hyp.insert(int(rng.integers(len(hyp) + 1)), plain_ids[int(rng.integers(len(plain_ids)))])
+                nbest.append(hyp)
+            # fstcompose needs the arcs leaving state 0 sorted by label (one arc per hypothesis): with first words in
+            # descending id order the reference's pipeline dies with "ComposeFst: 1st argument cannot match on
+            # output labels ..." -- keep the oracle inside its working range (the product has no such restriction)
+            nbest.sort(key=lambda h: h[0] if h else 0)
+            if case == 0:
+                nbest.append([])                                # an empty hypothesis (utt-k with no words)
+            if case == 1:
+                nbest = [[22]]                                  # a meta word id: nothing can consume it
+            want = ref.fuzzy_reference(nbest, fst, words_txt)
+            got = fz.match(nbest)
+            if want is None:
+                assert got is None or not got[0], (seed, case, nbest, got)
+                n_none += 1
+                continue
+            assert got is not None, (seed, case, nbest, want)
+            text_got = " ".join(fz.word(i) for i in got[0])
+            assert abs(got[1] - want[1]) <= 1e-4 * max(1.0, abs(want[1])), (seed, case, nbest, got, want)
+            assert text_got == want[0], (seed, case, nbest, text_got, want)
+            n_match += 1
+    assert n_match >= 80 and n_none >= 1
+
+
+def test_python_tail_uses_the_in_process_matcher(lib, ref, tmp_path):
+    """transcribe._fuzzy / _finish (the mirror of transcribe_wav.py:86-105) with lang_dir/G.fuzzy.fst present:
+    same (text, cost) as get_fuzzy_text computes through the OpenFst tools; max_fuzzy_cost / require_fuzzy as there."""
+    import asyncio
+    from rhasspy_speech_b200 import transcribe as T
+    lang = tmp_path / "lang"
+    lang.mkdir()
+    text, words_txt, arcs = write_grammar(str(lang), 7)
+    ref.fuzzy_compile(text, words_txt, str(lang / "G.fuzzy.fst"))
+    sent = []
+    for i, a in enumerate(arcs):                     # the first sentence of the grammar
+        if i and a[0] == 0:
+            break
+        if a[2] != "<eps>":
+            sent.append(VOCAB.index(a[2]) + 1)
+    hyps = sorted([sent + [19], sent[:-1] + [8, 8] + sent[-1:]], key=lambda h: h[0])
+    nbest_stdout = "".join("utt-%d %s\n" % (k + 1, "".join("%d " % w for w in h)) for k, h in enumerate(hyps)).encode()
+    want = ref.fuzzy_reference(hyps, str(lang / "G.fuzzy.fst"), words_txt)
+    got = asyncio.run(T._fuzzy(nbest_stdout, lang, None))
+    assert want is not None and got is not None
+    assert got[0] == want[0] and abs(got[1] - want[1]) <= 1e-4 * max(1.0, want[1])
+    base = T._Base(tmp_path, tmp_path)
+    assert asyncio.run(base._finish(None, nbest_stdout, lang, got[1] + 0.01, False)) == [T.decode_meta(want[0])]
+    assert asyncio.run(base._finish(None, nbest_stdout, lang, got[1] - 0.5, True)) == []
+    assert asyncio.run(T._fuzzy(b"", lang, None)) is None
+    assert asyncio.run(T._fuzzy(nbest_stdout, tmp_path, None)) is None            # no G.fuzzy.fst: no-op
