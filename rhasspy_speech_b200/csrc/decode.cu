@@ -180,6 +180,7 @@ __device__ float block_select(const float *a, int n, int k, Shared &S) {
         if (lane >= o) incl += y;
       }
       const unsigned excl = incl - sum, kk = (unsigned)S.sel_k;
+      __syncwarp();  // every lane has read sel_k before the owning lane overwrites it (racecheck: WAR inside the warp)
       const bool mine = kk >= excl && kk < incl;  // exactly one lane (k < n)
       if (mine) {
         unsigned rem = kk - excl, b = 0;
