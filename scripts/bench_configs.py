@@ -30,6 +30,56 @@ def run(name, dec, fn, audio_s, reps=4):
 
 def main():
     tmp = tempfile.mkdtemp()
+    if "--mixed" in sys.argv:
+        # config 5, one GPU's share: 256 utterances of a mixed batch routed to 8 different (model, HCLG) pairs that are all
+        # resident (the reference's 8 language models differ in exactly the ways the variants below do), 32 utterances each
+        import threading
+        variants = [
+            synth.ZAMIA_LIKE,
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v1", seed=11),
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v2", seed=12, priors=True),
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v3", seed=13, lda_bias=True),
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v4", seed=14, nnet_cmvn=True),
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v5", seed=15, num_gauss=256, ivector_dim=60),
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v6", seed=16, graph="arpa", vocab_size=400, bigrams_per_word=10, eps_hops=2),
+            dataclasses.replace(synth.ZAMIA_LIKE, name="v7", seed=17, binary=False),
+        ]
+        decs = []
+        for i, spec in enumerate(variants):
+            p = synth.write_model(os.path.join(tmp, "m%d" % i), spec)
+            decs.append(_lib.Decoder(_lib.Model(p.final_mdl, p.online_conf, 0), _lib.Graph(p.hclg, p.words_txt, 0),
+                                     max_tokens_per_utt=1 << 20))
+        utts = synth.make_utterances(256, seed=1234)
+        parts = [utts[i::len(decs)] for i in range(len(decs))]
+        audio_s = sum(len(u) for u in utts) / 16000.0
+
+        def sequential():
+            return [d.decode_pcm(pt) for d, pt in zip(decs, parts)]
+
+        def threaded():
+            out = [None] * len(decs)
+            th = [threading.Thread(target=lambda i=i: out.__setitem__(i, decs[i].decode_pcm(parts[i]))) for i in range(len(decs))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            return out
+        res = {}
+        for name, fn in (("sequential", sequential), ("8 host threads", threaded)):
+            for _ in range(2):
+                hyps = fn()
+            walls = []
+            for _ in range(4):
+                t0 = time.perf_counter()
+                hyps = fn()
+                walls.append(time.perf_counter() - t0)
+            res[name] = float(np.mean(walls)) * 1e3
+            assert all(h.n_utts == len(pt) for h, pt in zip(hyps, parts))
+        dev = sum(sum(d.timings()[k] for k in ("feature_ms", "nnet_ms", "decode_ms")) for d in decs)
+        print(json.dumps({"config": "5 (one GPU's share): 256 utterances over 8 resident (model, HCLG) pairs, 32 each", "audio_s": audio_s,
+                          "wall_ms": res, "rtfx_e2e": {k: audio_s / (v / 1e3) for k, v in res.items()},
+                          "device_ms_sum_of_8_batches": dev, "decoded": int(sum(int((np.asarray(h.n_hyp) > 0).sum()) for h in hyps))}), flush=True)
+        return
     if "--surface" in sys.argv:
         # config 4 through the Python mirror: 64 concurrent KaldiNnet3StreamTranscriber.async_transcribe coroutines fed
         # 80 ms chunks; the host dynamic batcher turns them into a few device batches
