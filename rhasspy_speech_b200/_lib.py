@@ -421,12 +421,16 @@ class Stream:
         err = C.create_string_buffer(ERRLEN)
         self.h = dec.lib.rs_stream_open(dec.h, err, ERRLEN)
         _check(bool(self.h), err)
+        self._err = err         # reused by accept(): one call per 80 ms chunk and stream
 
     def accept(self, chunk: bytes):
-        n = len(chunk) // 2
-        err = C.create_string_buffer(ERRLEN)
-        buf = (C.c_char * len(chunk)).from_buffer_copy(chunk) if chunk else None
-        rc = self.dec.lib.rs_stream_accept(self.h, C.cast(buf, C.c_void_p) if buf is not None else None, n, err, ERRLEN)
+        """Raw s16le bytes (any even length); the library copies them, so the bytes object is passed as is."""
+        if not chunk:
+            return
+        if not isinstance(chunk, bytes):
+            chunk = bytes(chunk)
+        err = self._err
+        rc = self.dec.lib.rs_stream_accept(self.h, chunk, len(chunk) // 2, err, ERRLEN)
         _check(rc == 0, err)
 
     def finish(self) -> Hypotheses:

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256) splice_lda_kernel(IvecParams p) {
 // register-tiled product [frames x D] x [D x G] (the UBM tables stream through L2 once per tile,
 // not once per frame), then VectorToPosteriorEntry (hmm/posterior.cc:440-508) with one warp per
 // frame over the log-likelihood row kept in shared memory.
+// (32 frames per CTA with 8 frames per thread was measured: 169 registers, one CTA per SM, feature stage 2.31 -> 2.59 ms)
 constexpr int kUbmFrames = 16;
 __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
   extern __shared__ float sm[];

@@ -387,6 +387,9 @@ class KaldiNnet3StreamTranscriber(_Base):
             async for chunk in audio_stream:
                 if not chunk:
                     continue
+                if not pending and not (len(chunk) & 1):
+                    stream.accept(chunk)            # the common case: whole samples, no copy on this side
+                    continue
                 data = pending + chunk
                 keep = len(data) & ~1
                 pending = data[keep:]
@@ -443,6 +446,9 @@ class KaldiTranscriber:
             pending = b""
             for chunk in chunks:
                 if not chunk:
+                    continue
+                if not pending and not (len(chunk) & 1):
+                    stream.accept(chunk)            # the common case: whole samples, no copy on this side
                     continue
                 data = pending + chunk
                 keep = len(data) & ~1
