@@ -330,14 +330,16 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     int4 *llink = nullptr;
     int *ltb = nullptr, *lpos = nullptr;
     float *loff = nullptr;
-    int arena_cap = cfg.arena_cap;
+    const int arena_cap = cfg.arena_cap;
+    // lat_dead (block-uniform): the lattice of this utterance outgrew its slice; the search goes on and returns
+    // the best path, the lattice is marked unusable (tok_base[n_frames + 1] = -1 -> rs_result.status bit 5)
+    bool lat_dead = false;
     if constexpr (kLat) {
       ltok = P.lat.tok + (size_t)u * P.lat.tok_cap;
       llink = P.lat.link + (size_t)u * P.lat.link_cap;
       ltb = P.lat.tok_base + (size_t)u * (P.lat.max_t + 2);
       lpos = P.lat.link_pos + (size_t)u * (2 * P.lat.max_t + 4);
       loff = P.lat.cost_offset + (size_t)u * (P.lat.max_t + 1);
-      arena_cap = min(arena_cap, P.lat.tok_cap);
     }
     // slack = (cost through the link) - (destination's cost), the bracket of PruneForwardLinks' link_extra_cost
     // (:330-332) in its float order; stored with the link so that the pruning sweep touches no token or arc
@@ -473,8 +475,12 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           prev = ss >= 0 ? base_new + T.hidx[ss] : -1;
         }
         ws.arena[base_new + pos] = make_int2(prev, (int)arc);
-        if constexpr (kLat) ltok[base_new + pos] = make_int2(ws.tok_state[tb][pos], __float_as_int(ws.tok_cost[tb][pos]));
+        if constexpr (kLat)
+          if (!lat_dead && base_new + n_new <= P.lat.tok_cap)
+            ltok[base_new + pos] = make_int2(ws.tok_state[tb][pos], __float_as_int(ws.tok_cost[tb][pos]));
       }
+      if constexpr (kLat)
+        if (base_new + n_new > P.lat.tok_cap) lat_dead = true;
       __syncthreads();
       tick(5);
       return n_new;
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         cnt_created += r;
         if constexpr (kLat) {
           if (tid == 0) ltb[0] = lpos[0] = lpos[1] = 0;
-          eps_links(0, cfg.beam, 0, r);
+          if (!lat_dead) eps_links(0, cfg.beam, 0, r);
           if (tid == 0) lpos[2] = S.n_links;
         }
       }
@@ -686,7 +692,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         status |= (r == -1 ? 1 : 2);
         break;
       }
-      if constexpr (kLat) {
+      if constexpr (kLat) if (!lat_dead) {
         // emitting links time frame -> frame + 1: every arc whose cost passed the frame's final next_cutoff
         // (the reference's transient cutoff lets more through; those lie beyond the beam and never survive
         // the lattice-beam pruning), then the epsilon links of the new time
@@ -719,10 +725,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         __syncthreads();
         eps_links(nxt, next_cutoff, base_new, r);
         if (tid == 0) lpos[2 * (frame + 2)] = S.n_links;
-        if (S.lat_overflow) {
-          status |= 2;
-          break;
-        }
+        if (S.lat_overflow) lat_dead = true;  // every thread reads the flag behind the barrier of eps_links
       }
       clear_table(cur);
       tick(6);
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       printf("decode phases (clocks, utt %d, %d frames): cutoff %lld seed+prefix %lld expand %lld epsilon %lld compact %lld records %lld clear %lld\n", u,
              n_frames, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
     if constexpr (kLat) {
-      if (tid == 0) ltb[n_frames + 1] = arena_n;
+      if (tid == 0) ltb[n_frames + 1] = lat_dead ? -1 : arena_n;
     }
     // ---- best path (lattice-faster-online-decoder.cc:78-173)
     int n_words = -1;
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
   const int T = P.n_frames[u];
   const float kInf = __int_as_float(0x7f800000);
   const unsigned NE = g.num_earcs;
-  if (T <= 0 || P.n_words[u] < 0) {
+  if (T <= 0 || P.n_words[u] < 0 || P.lat.tok_base[(size_t)u * (P.lat.max_t + 2) + T + 1] < 0) {
     if (tid == 0) headers[u] = LatticeHeader{0, 0, 0, 0, 0, {0, 0, 0}};
     return;
   }

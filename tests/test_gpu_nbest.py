@@ -194,3 +194,28 @@ def test_nbest_on_arpa_graph_with_epsilon_chains(lib, ref, synth, utterances, tm
                 n_flagged_same += same
     print("arpa n-best: %d unflagged lists identical, %d of %d flagged lists identical" % (n_lists, n_flagged_same, n_flagged))
     assert n_lists >= 2
+
+
+def test_lattice_that_does_not_fit_falls_back_to_the_best_path(tiny, utterances, monkeypatch):
+    """An utterance whose lattice outgrows its slice of the device budget still returns its best path (status bit 5);
+    the other utterances of the call are unaffected."""
+    _, _, dec = tiny
+    batch = [utterances[i % len(utterances)] for i in range(64)]
+    dec.set_nbest(1)
+    one = dec.decode_pcm(batch)
+    monkeypatch.setenv("RS_B200_LATTICE_MB", "16")        # 16 MB / 64 utterances: 4096 tokens each
+    try:
+        dec.set_nbest(4)
+        got = dec.decode_pcm(batch)
+    finally:
+        dec.set_nbest(1)
+    assert all(s & 32 for s in got.status) and all((s & ~48) == 0 for s in got.status), list(got.status[:8])
+    assert list(got.n_hyp) == [1] * 64
+    assert got.words == one.words
+    monkeypatch.delenv("RS_B200_LATTICE_MB")
+    try:
+        dec.set_nbest(4)
+        full = dec.decode_pcm(batch[:6])
+    finally:
+        dec.set_nbest(1)
+    assert all(s in (0, 16) for s in full.status) and max(full.n_hyp) > 1
