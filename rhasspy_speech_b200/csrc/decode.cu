@@ -857,9 +857,10 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
                                                                LatticeHeader *headers, LatticeArc *arcs, int arcs_cap,
                                                                int *cursor) {
   __shared__ Shared S;
-  __shared__ int s_changed, s_base;
+  __shared__ int s_changed, s_base, s_nsurv, s_nfin;
   const int tid = threadIdx.x;
   const int u = blockIdx.x;
+  if (tid == 0) s_nsurv = 0;
   const DevGraph &g = P.g;
   const int T = P.n_frames[u];
   const float kInf = __int_as_float(0x7f800000);
@@ -872,6 +873,7 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
   unsigned *extra = reinterpret_cast<unsigned *>(P.lat.extra + (size_t)u * P.lat.tok_cap);
   int *newid = P.lat.newid + (size_t)u * P.lat.tok_cap;
   int4 *llink = P.lat.link + (size_t)u * P.lat.link_cap;
+  int4 *surv = P.lat.surv + (size_t)u * P.lat.surv_cap;
   const int *ltb = P.lat.tok_base + (size_t)u * (P.lat.max_t + 2);
   const int *lpos = P.lat.link_pos + (size_t)u * (2 * P.lat.max_t + 4);
   const float *loff = P.lat.cost_offset + (size_t)u * (P.lat.max_t + 1);
@@ -964,14 +966,22 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
       if (tid == 0) s_changed = 0;
       __syncthreads();
     }
-    // extras of time t and t + 1 are final: excise the links beyond the beam, publish the extras of time t
+    // the extras of time t and t + 1 are final: the links that stay inside the beam (2 % on a grammar graph) are
+    // copied to the utterance's survivor list, straight from the registers they were relaxed from; nothing is
+    // written back to the rest, and no later pass reads the full link array again
     for (int i = e0 + tid; i < e1; i += NT) {
       const int4 l = i < e0 + NT ? my_e : llink[i];
-      if (__fadd_rn(ldx(nxt + (l.y - b1)), __int_as_float(l.w)) > lattice_beam) llink[i].x = -1;
+      if (!(__fadd_rn(ldx(nxt + (l.y - b1)), __int_as_float(l.w)) > lattice_beam)) {
+        const int k = atomicAdd(&s_nsurv, 1);
+        if (k < P.lat.surv_cap) surv[k] = make_int4(l.x, l.y, l.z, t);
+      }
     }
     for (int i = p0 + tid; i < p1; i += NT) {
       const int4 l = i < p0 + NT ? my_p : llink[i];
-      if (__fadd_rn(ldx(cur + (l.y - b0)), __int_as_float(l.w)) > lattice_beam) llink[i].x = -1;
+      if (!(__fadd_rn(ldx(cur + (l.y - b0)), __int_as_float(l.w)) > lattice_beam)) {
+        const int k = atomicAdd(&s_nsurv, 1);
+        if (k < P.lat.surv_cap) surv[k] = make_int4(l.x, l.y, l.z, t);
+      }
     }
     if (cur != extra + b0)
       for (int i = tid; i < b1 - b0; i += NT) extra[b0 + i] = cur[i];
@@ -998,64 +1008,41 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
     n_nodes += total;
   }
   __syncthreads();
-  // ---- count, reserve, write
-  unsigned cnt = 0;
-  for (int i = tid; i < nlink; i += NT) {
-    const int4 l = llink[i];
-    cnt += (l.x >= 0 && newid[l.x] >= 0 && newid[l.y] >= 0) ? 1u : 0u;
-  }
+  // ---- reserve and write: survivors, then the final weights of the last time
+  const int n_surv = s_nsurv;
+  if (tid == 0) s_nfin = 0;
+  __syncthreads();
   for (int i = f0 + tid; i < f1; i += NT) {
     const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
-    cnt += (newid[i] >= 0 && fc != kInf) ? 1u : 0u;
+    if (newid[i] >= 0 && fc != kInf) atomicAdd(&s_nfin, 1);
   }
-  unsigned n_out;
-  block_excl_scan(cnt, S, &n_out);
-  if (tid == 0) s_base = atomicAdd(cursor, (int)n_out);
+  __syncthreads();
+  const int n_out = n_surv + s_nfin;
+  if (tid == 0) s_base = n_surv <= P.lat.surv_cap ? atomicAdd(cursor, n_out) : arcs_cap;
   __syncthreads();
   const int base = s_base;
-  if (base + (int)n_out > arcs_cap) {
+  if (n_surv > P.lat.surv_cap || base + n_out > arcs_cap) {  // survivor list or output buffer too small: best path only
     if (tid == 0) headers[u] = LatticeHeader{0, 0, 0, 0, 0, {0, 0, 0}};
     return;
   }
-  unsigned running = 0;
-  for (int b0 = 0; b0 < nlink; b0 += NT) {
-    const int i = b0 + tid;
-    int4 l = make_int4(-1, 0, 0, 0);
-    if (i < nlink) l = llink[i];
-    const unsigned keep = (l.x >= 0 && newid[l.x] >= 0 && newid[l.y] >= 0) ? 1u : 0u;
-    unsigned total;
-    const unsigned ex = block_excl_scan(keep, S, &total);
-    if (keep) {
-      const bool emitting = (unsigned)l.z < NE;
-      const int4 a = emitting ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
-      float acoustic = 0.f;
-      if (emitting) {
-        // the link's time: the last position entry <= i is the start of its group, entry 2t + 2 = links t -> t + 1;
-        // GetRawLattice's acoustic cost is (offset - loglike) - offset, rounding included (:158-165)
-        int lo = 0, hi = 2 * (T + 1);
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (lpos[mid] <= i) lo = mid; else hi = mid;
-        }
-        const int t = (lo - 2) >> 1;
-        const float off = loff[t];
-        acoustic = __fsub_rn(__fsub_rn(off, P.loglikes[(size_t)(P.ll_row0[u] + t) * P.ld + a.y]), off);
-      }
-      arcs[base + running + ex] = LatticeArc{newid[l.x], newid[l.y], a.w, __int_as_float(a.z), acoustic};
+  if (tid == 0) s_nfin = 0;
+  __syncthreads();
+  for (int k = tid; k < n_surv; k += NT) {
+    const int4 l = surv[k];
+    const bool emitting = (unsigned)l.z < NE;
+    const int4 a = emitting ? g.earc[l.z] : g.parc[(unsigned)l.z - NE];
+    float acoustic = 0.f;
+    if (emitting) {  // GetRawLattice's acoustic cost is (offset - loglike) - offset, rounding included (:158-165)
+      const float off = loff[l.w];
+      acoustic = __fsub_rn(__fsub_rn(off, P.loglikes[(size_t)(P.ll_row0[u] + l.w) * P.ld + a.y]), off);
     }
-    running += total;
+    arcs[base + k] = LatticeArc{newid[l.x], newid[l.y], a.w, __int_as_float(a.z), acoustic};
   }
-  for (int b0 = f0; b0 < f1; b0 += NT) {
-    const int i = b0 + tid;
-    float fc = kInf;
-    if (i < f1) fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
-    const unsigned keep = (i < f1 && newid[i] >= 0 && fc != kInf) ? 1u : 0u;
-    unsigned total;
-    const unsigned ex = block_excl_scan(keep, S, &total);
-    if (keep) arcs[base + running + ex] = LatticeArc{newid[i], -1, 0, fc, 0.f};
-    running += total;
+  for (int i = f0 + tid; i < f1; i += NT) {
+    const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
+    if (newid[i] >= 0 && fc != kInf) arcs[base + n_surv + atomicAdd(&s_nfin, 1)] = LatticeArc{newid[i], -1, 0, fc, 0.f};
   }
-  if (tid == 0) headers[u] = LatticeHeader{base, (int)n_out, (int)n_nodes, 1, nlink, {0, 0, 0}};
+  if (tid == 0) headers[u] = LatticeHeader{base, n_out, (int)n_nodes, 1, nlink, {0, 0, 0}};
 }
 
 void LaunchLatticePrune(const DecodeParams &p, float lattice_beam, LatticeHeader *headers, LatticeArc *arcs,

@@ -374,7 +374,7 @@ struct DecoderImpl {
   // n-best tail (rs_decoder_set_nbest): lattice recorded by decode_kernel<true>, pruned + compacted on the device
   int nbest = 1;
   float nbest_scale = 1.0f;
-  DevBuf d_lat_tok, d_lat_extra, d_lat_newid, d_lat_link, d_lat_tb, d_lat_pos, d_lat_off, d_lat_hdr, d_lat_arcs;
+  DevBuf d_lat_tok, d_lat_extra, d_lat_newid, d_lat_link, d_lat_surv, d_lat_tb, d_lat_pos, d_lat_off, d_lat_hdr, d_lat_arcs;
   PinBuf h_lat;
   std::vector<LatticeHeader> lat_hdr;  // of the last n-best call (rs_debug_fetch item 5)
   std::vector<DevBuf> slots;
@@ -966,7 +966,8 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     const char *e = getenv("RS_B200_LATTICE_MB");
     const size_t budget = (size_t)std::max(e ? atoi(e) : 8192, 16) << 20;
     const int kLinksPerToken = 3;
-    const size_t per_tok = sizeof(int2) + sizeof(float) + sizeof(int) + kLinksPerToken * sizeof(int4);
+    // tokens {state, cost}, extra cost, new id, 3 links, and a survivor list of a quarter of the links
+    const size_t per_tok = sizeof(int2) + sizeof(float) + sizeof(int) + kLinksPerToken * sizeof(int4) * 5 / 4;
     const size_t tc = std::min<size_t>((size_t)o.max_tokens_per_utt, std::max<size_t>(budget / n / per_tok, 4096));
     LatticeBuf &L = p.lat;
     L.tok_cap = (int)tc;
@@ -976,6 +977,8 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     L.extra = (float *)d->d_lat_extra.ensure(sizeof(float) * tc * n);
     L.newid = (int *)d->d_lat_newid.ensure(sizeof(int) * tc * n);
     L.link = (int4 *)d->d_lat_link.ensure(sizeof(int4) * (size_t)L.link_cap * n);
+    L.surv_cap = L.link_cap / 4;
+    L.surv = (int4 *)d->d_lat_surv.ensure(sizeof(int4) * (size_t)L.surv_cap * n);
     L.tok_base = (int *)d->d_lat_tb.ensure(sizeof(int) * (size_t)(max_t + 2) * n);
     L.link_pos = (int *)d->d_lat_pos.ensure(sizeof(int) * (size_t)(2 * max_t + 4) * n);
     L.cost_offset = (float *)d->d_lat_off.ensure(sizeof(float) * (size_t)(max_t + 1) * n);

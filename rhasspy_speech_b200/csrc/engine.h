@@ -187,11 +187,12 @@ struct LatticeBuf {
   int2 *tok;           // {state, forward cost bits} per token, in arena order (time-major)
   float *extra;        // extra_cost per token (>= 0, +inf = pruned)
   int *newid;          // compact node id of the surviving tokens
-  int4 *link;          // {source token, destination token, arc id, link_extra bits (>=0) or -1 = pruned}
+  int4 *link;          // {source token, destination token, arc id, slack bits}
+  int4 *surv;          // links inside the lattice beam: {source token, destination token, arc id, time}
   int *tok_base;       // [max_t + 2] first token of each time; [n_frames + 1] = token count
   int *link_pos;       // [2 * max_t + 4]: [2t] start of the emitting links (t-1 -> t), [2t+1] start of the epsilon links at t
   float *cost_offset;  // [max_t + 1] offset added to the acoustic costs of the frame leaving time t (:733)
-  int tok_cap, link_cap, max_t;
+  int tok_cap, link_cap, surv_cap, max_t;
 };
 
 // compact lattice as the host receives it: one header per utterance, then its arcs in `arcs`
