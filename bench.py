@@ -198,6 +198,11 @@ def run_ours(args):
     dec = _lib.Decoder(model, graph)
     audio_s = sum(len(u) for u in utts) / 16000.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # the step's inputs start in page-locked host memory (one rs_host_alloc block, utterances back to back); the same
+    # call from ordinary numpy arrays (one more host memcpy into the decoder's staging area) is timed as e2e_pageable
+    utts_pageable = utts
+    pinned = _lib.PinnedAudio.from_utterances(utts)
+    utts = pinned
 
     def barrier():
         torch.cuda.synchronize()
@@ -224,6 +229,14 @@ def run_ours(args):
         launches += t["kernel_launches"]
     barrier()
     t_all = time.perf_counter() - t_all0
+    wall_pageable = []
+    for _ in range(max(2, args.steps // 2)):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dec.decode_pcm(utts_pageable)
+        wall_pageable.append(time.perf_counter() - t0)
+    barrier()
     # the same call with two batches in flight per GPU (two decoders, two host threads): the host staging
     # and result assembly of one batch overlap the kernels of the other.  Every batch still pays its own
     # pinned staging, H2D, kernels and D2H inside the timed region.
@@ -251,12 +264,12 @@ def run_ours(args):
     dev_s = float((sm[:, 0] + sm[:, 1] + sm[:, 2]).mean() / 1e3)
     e2e_s = float(np.mean(wall_s))
     # max over ranks (device time and wall time), sum of audio
-    vec = torch.tensor([dev_s, e2e_s, pipe_s], dtype=torch.float64, device="cuda")
+    vec = torch.tensor([dev_s, e2e_s, pipe_s, float(np.mean(wall_pageable))], dtype=torch.float64, device="cuda")
     aud = torch.tensor([audio_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(aud, op=dist.ReduceOp.SUM)
-    dev_s_max, e2e_s_max, pipe_s_max = [float(x) for x in vec.tolist()]
+    dev_s_max, e2e_s_max, pipe_s_max, pageable_s_max = [float(x) for x in vec.tolist()]
     audio_total = float(aud.item())
     if rank == 0:
         pk, pk_kind = peaks()
@@ -275,7 +288,10 @@ def run_ours(args):
                        "decoder": "beam 24, max-active 7000, lattice-beam 8 (best path)", "l2": "flushed between iterations (256 MiB write)",
                        "audio_seconds_per_step": audio_total},
             "e2e": {"value": audio_total / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(t["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(t["d2h_bytes"]), "ms_per_step": e2e_s_max * 1e3},
+                    "d2h_bytes_per_step": int(t["d2h_bytes"]), "ms_per_step": e2e_s_max * 1e3,
+                    "input": "int16 PCM in one page-locked host block (rs_host_alloc), copied H2D inside the timed call"},
+            "e2e_pageable": {"value": audio_total / pageable_s_max, "unit": UNIT, "ms_per_step": pageable_s_max * 1e3,
+                             "input": "the same call from 256 ordinary numpy arrays: packed into pinned staging first"},
             "e2e_two_in_flight": {"value": audio_total / pipe_s_max, "unit": UNIT, "ms_per_batch": pipe_s_max * 1e3,
                                   "how": "two decoders per GPU driven by two host threads, same call, same per-batch copies"},
             "gpu_launches": int(launches),

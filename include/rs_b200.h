@@ -101,6 +101,12 @@ const char *rs_graph_word(const rs_graph *g, int32_t id);
 
 rs_decoder *rs_decoder_create(rs_model *m, rs_graph *g, const rs_decoder_opts *opts, char *err, size_t errlen);
 void rs_decoder_free(rs_decoder *d);
+/* Page-locked host memory for audio.  Utterances that lie back to back, in call order, inside one rs_host_alloc block are
+ * copied to the device straight from that block by rs_decode_pcm; any other buffer is first packed into the decoder's
+ * own pinned staging area (a host memcpy of the whole batch).  The reference has no counterpart: its audio travels
+ * through a pipe into the child process (transcribe_stream.py:68-82). */
+void *rs_host_alloc(size_t bytes, char *err, size_t errlen);
+void rs_host_free(void *p);
 /* Hot graph swap: binds the decoder to another HCLG without rebuilding its device workspace.  The
  * reference re-reads HCLG.fst in every call (ReadFstKaldiGeneric, online2-wav-nnet3-latgen-faster.cc:181), so a graph
  * retrained by KaldiTrainer._mkgraph (rhasspy_speech/kaldi.py:409-425) is picked up by the next transcription; a resident

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional, Sequence
+from typing import Union, List, Optional, Sequence
 
 import numpy as np
 
@@ -61,6 +61,8 @@ SYMBOLS = [
     ("rs_graph_word", C.c_char_p, [_P, C.c_int32]),
     ("rs_decoder_create", _P, [_P, _P, C.POINTER(DecoderOpts)] + _ERR),
     ("rs_decoder_free", None, [_P]),
+    ("rs_host_alloc", _P, [C.c_size_t] + _ERR),
+    ("rs_host_free", None, [_P]),
     ("rs_fuzzy_load", _P, [C.c_char_p, C.c_char_p] + _ERR),
     ("rs_fuzzy_free", None, [_P]),
     ("rs_fuzzy_match", C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float)] + _ERR),
@@ -171,6 +173,48 @@ def lattice_nbest(src, dst, olabel, graph, acoustic, n_nodes: int, n: int, acous
     if k < 0:
         raise RsError("rs_debug_lattice_nbest failed (%d)" % k)
     return [([int(x) for x in wid[woff[h]:woff[h + 1]]], float(cost[2 * h]), float(cost[2 * h + 1])) for h in range(k)]
+
+
+class PinnedAudio:
+    """A batch of utterances back to back in page-locked memory (rs_host_alloc): `views[i]` are int16 arrays the
+    caller fills (or that were filled from `utterances`); Decoder.decode_pcm(views) then copies the batch to the
+    device straight from this block, without the staging memcpy a pageable buffer needs."""
+
+    def __init__(self, lengths: Sequence[int]):
+        self.lib = load_library()
+        total = int(sum(int(x) for x in lengths))
+        err = C.create_string_buffer(ERRLEN)
+        self.ptr = self.lib.rs_host_alloc(max(total, 1) * 2, err, ERRLEN)
+        _check(bool(self.ptr), err)
+        buf = (C.c_int16 * max(total, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.int16)
+        self.views: List[np.ndarray] = []
+        o = 0
+        addrs = []
+        for n in lengths:
+            self.views.append(self.array[o:o + int(n)])
+            addrs.append(self.ptr + 2 * o)
+            o += int(n)
+        # the argument arrays of rs_decode_pcm, built once: Decoder.decode_pcm(pinned_audio) passes them as they are
+        k = len(addrs)
+        self._ptrs = (C.c_void_p * max(k, 1))(*addrs)
+        self._ns = (C.c_int32 * max(k, 1))(*[int(x) for x in lengths])
+        self._n = k
+
+    @classmethod
+    def from_utterances(cls, utterances: Sequence[np.ndarray]) -> "PinnedAudio":
+        pa = cls([len(u) for u in utterances])
+        for v, u in zip(pa.views, utterances):
+            v[:] = np.asarray(u, dtype=np.int16)
+        return pa
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.views, self.array = [], None
+            self.lib.rs_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = close
 
 
 def _address(a: np.ndarray) -> int:
@@ -348,7 +392,12 @@ class Decoder:
         finally:
             self.lib.rs_result_free(res)
 
-    def decode_pcm(self, pcm: Sequence[np.ndarray]) -> Hypotheses:
+    def decode_pcm(self, pcm: "Union[Sequence[np.ndarray], PinnedAudio]") -> Hypotheses:
+        if isinstance(pcm, PinnedAudio):        # the whole block, no per-utterance marshalling
+            res = C.POINTER(Result)()
+            err = C.create_string_buffer(ERRLEN)
+            rc = self.lib.rs_decode_pcm(self.h, pcm._ptrs, pcm._ns, pcm._n, C.byref(res), err, ERRLEN)
+            return self._take(rc, res, err)
         arrs = [np.ascontiguousarray(p, dtype=np.int16) for p in pcm]
         n = len(arrs)
         ptrs = (C.c_void_p * max(n, 1))(*[_address(a) for a in arrs])

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <atomic>
 #include <chrono>
@@ -52,6 +53,18 @@ struct DevBuf {  // grow-only device allocation
     return reinterpret_cast<T *>(p);
   }
 };
+// page-locked host ranges handed out by rs_host_alloc
+static std::mutex g_pinned_mu;
+static std::map<uintptr_t, size_t> g_pinned;
+static bool HostRangeIsPinned(const void *p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  auto it = g_pinned.upper_bound(a);
+  if (it == g_pinned.begin()) return false;
+  --it;
+  return a >= it->first && a + bytes <= it->first + it->second;
+}
+
 struct PinBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -799,6 +812,25 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
 
 void rs_decoder_free(rs_decoder *d) { delete reinterpret_cast<DecoderImpl *>(d); }
 
+void *rs_host_alloc(size_t bytes, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  void *p = nullptr;
+  CUDA_OK(cudaMallocHost(&p, std::max<size_t>(bytes, 16)));
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned[reinterpret_cast<uintptr_t>(p)] = std::max<size_t>(bytes, 16);
+  return p;
+  API_GUARD_END(nullptr)
+}
+
+void rs_host_free(void *p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned.erase(reinterpret_cast<uintptr_t>(p));
+  }
+  cudaFreeHost(p);
+}
+
 int rs_decoder_set_graph(rs_decoder *d_, rs_graph *g_, char *err, size_t errlen) {
   API_GUARD_BEGIN
   DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
@@ -1225,12 +1257,26 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   //             | v_num_frames[v_n] | v_frame_offset[v_n] | v_begin[n + 1]
   const size_t desc_ints = (size_t)2 * n + 5 * (size_t)n + axis_len + 2 * (size_t)v_n + n + 1;
   char *hin = (char *)d->h_in.ensure(pcm_bytes + 16 + desc_ints * sizeof(int));
-  int16_t *hpcm = (int16_t *)hin;
+  // Audio that already sits back to back in page-locked memory from rs_host_alloc goes to the device straight
+  // from the caller's buffer; anything else is first packed into the decoder's own pinned staging area.
+  const int16_t *direct_base = nullptr;
+  {
+    bool contiguous = total_samples > 0;
+    const int16_t *base = nullptr;
+    for (int u = 0; u < n && contiguous; u++) {
+      if (!nsamp[u]) continue;
+      if (!base) base = pcm[u] - pcm_offset[u];
+      contiguous = pcm[u] == base + pcm_offset[u];
+    }
+    if (contiguous && base && HostRangeIsPinned(base, sizeof(int16_t) * (size_t)total_samples)) direct_base = base;
+  }
+  int16_t *hpcm = direct_base ? const_cast<int16_t *>(direct_base) : (int16_t *)hin;
   // Staging is split into items of ~2 MB packed by a small persistent thread pool; each item goes to
   // the device as soon as it is complete, so the H2D copies overlap the packing of the later items.
   static const int item_shift = getenv("RS_B200_PACK_ITEM_SHIFT") ? atoi(getenv("RS_B200_PACK_ITEM_SHIFT")) : 21;
   int n_items = (int)std::min<size_t>(std::max<size_t>(pcm_bytes >> item_shift, 1), 64);
   if (n_items > n) n_items = n;
+  if (direct_base) n_items = 1;  // one copy, nothing to pack
   std::vector<int> range_begin(n_items + 1, n);
   {
     int u = 0;
@@ -1243,6 +1289,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     range_begin[n_items] = n;
   }
   auto pack = [&](int w) {
+    if (direct_base) return;
     for (int u = range_begin[w]; u < range_begin[w + 1]; u++)
       if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
   };

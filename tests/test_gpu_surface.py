@@ -99,3 +99,20 @@ def ref():
     if not ref_run.available():
         pytest.skip("oracle/_ref not built")
     return ref_run
+
+
+def test_pinned_audio_block_gives_the_same_results(tiny_model, utterances):
+    """rs_host_alloc: a batch laid out back to back in page-locked memory is copied to the device without the staging
+    memcpy; out-of-order views of the same block fall back to staging.  Results are identical either way."""
+    from rhasspy_speech_b200 import _lib
+    dec = _lib.Decoder(_lib.Model(tiny_model.final_mdl, tiny_model.online_conf, 0), _lib.Graph(tiny_model.hclg, tiny_model.words_txt, 0))
+    batch = list(utterances) + [np.zeros(0, np.int16), utterances[0][:399]]
+    want = dec.decode_pcm(batch)
+    pa = _lib.PinnedAudio.from_utterances(batch)
+    got = dec.decode_pcm(pa.views)
+    assert got.words == want.words and list(got.num_frames) == list(want.num_frames)
+    h2d_direct = dec.timings()["h2d_bytes"]
+    assert dec.decode_pcm(pa).words == want.words      # the block itself: cached argument arrays
+    rev = dec.decode_pcm(pa.views[::-1])              # not in block order: staged like any other buffer
+    assert rev.words == want.words[::-1] and dec.timings()["h2d_bytes"] == h2d_direct
+    pa.close()
