@@ -118,7 +118,11 @@ int rs_decoder_set_graph(rs_decoder *d, rs_graph *g, char *err, size_t errlen);
  * decoder.  nbest == 1 with scale 1.0 (the default) returns the device back-trace of the best path; anything
  * else records the state-level lattice on the device (GetRawLattice, lattice-faster-decoder.cc:106-189), prunes
  * it with --lattice-beam (:299-458) and returns the n cheapest distinct word sequences under
- * graph + acoustic_scale * acoustic, each with the costs of its best path. */
+ * graph + acoustic_scale * acoustic, each with the costs of its best path.
+ * The lattices of a batch share a device budget (environment RS_B200_LATTICE_MB, default 8192, split evenly over the
+ * utterances of the call: 76 bytes per token); an utterance whose lattice does not fit still returns its best path and
+ * carries status bit 5 -- raise the budget or lower the batch size for very large graphs (an ARPA-shaped HCLG at 6 k
+ * tokens per frame needs ~60 MB per 4 s utterance). */
 int rs_decoder_set_nbest(rs_decoder *d, int32_t nbest, float acoustic_scale, char *err, size_t errlen);
 
 /* Replaces one run of `online2-wav-nnet3-latgen-faster --online=false ... | lattice-to-nbest --n=1 |
