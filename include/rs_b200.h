@@ -120,9 +120,10 @@ int rs_decoder_set_graph(rs_decoder *d, rs_graph *g, char *err, size_t errlen);
  * it with --lattice-beam (:299-458) and returns the n cheapest distinct word sequences under
  * graph + acoustic_scale * acoustic, each with the costs of its best path.
  * The lattices of a batch share a device budget (environment RS_B200_LATTICE_MB, default 8192, split evenly over the
- * utterances of the call: 76 bytes per token); an utterance whose lattice does not fit still returns its best path and
- * carries status bit 5 -- raise the budget or lower the batch size for very large graphs (an ARPA-shaped HCLG at 6 k
- * tokens per frame needs ~60 MB per 4 s utterance). */
+ * utterances of the call: 76 bytes per token).  When a lattice does not fit, the decode stage is run again with four
+ * times the budget, up to RS_B200_LATTICE_MAX_MB (default 65536); the grown budget is kept for later calls (an
+ * ARPA-shaped HCLG at 6 k tokens per frame needs ~60 MB per 4 s utterance).  An utterance that still does not fit returns
+ * its best path and carries status bit 5. */
 int rs_decoder_set_nbest(rs_decoder *d, int32_t nbest, float acoustic_scale, char *err, size_t errlen);
 
 /* Replaces one run of `online2-wav-nnet3-latgen-faster --online=false ... | lattice-to-nbest --n=1 |

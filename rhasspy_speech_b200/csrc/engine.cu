@@ -387,6 +387,7 @@ struct DecoderImpl {
   // n-best tail (rs_decoder_set_nbest): lattice recorded by decode_kernel<true>, pruned + compacted on the device
   int nbest = 1;
   float nbest_scale = 1.0f;
+  size_t lattice_mb = 0;  // current lattice budget (grows when a batch did not fit)
   DevBuf d_lat_tok, d_lat_extra, d_lat_newid, d_lat_link, d_lat_surv, d_lat_tb, d_lat_pos, d_lat_off, d_lat_hdr, d_lat_arcs;
   PinBuf h_lat;
   std::vector<LatticeHeader> lat_hdr;  // of the last n-best call (rs_debug_fetch item 5)
@@ -986,17 +987,23 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   p.status = (int *)(dout + off_status);
   p.cost = (float *)(dout + off_cost);
   p.counters = (unsigned long long *)(dout + off_cnt);
-  CUDA_OK(cudaMemsetAsync(d->d_next_utt, 0, sizeof(int), d->stream));
-  // ---- n-best tail: per-utterance lattice slices inside a byte budget (RS_B200_LATTICE_MB, default 8192)
+  // ---- n-best tail: per-utterance lattice slices inside a byte budget (RS_B200_LATTICE_MB, default 8192).  When a
+  // lattice of the batch does not fit, the stage is run again with four times the budget (the log-likelihoods are
+  // still resident), up to RS_B200_LATTICE_MAX_MB (default 65536); the grown budget is kept for later calls.
   const bool lattice = d->nbest > 1 || d->nbest_scale != 1.0f;
   LatticeHeader *d_hdr = nullptr;
   LatticeArc *d_arcs = nullptr;
   int arcs_cap = 0;
+  const size_t hdr_bytes = lattice ? sizeof(LatticeHeader) * n + sizeof(int) : 0;
+  char *hout = (char *)d->h_out.ensure(out_bytes + hdr_bytes);
+  for (int attempt = 0;; attempt++) {
+  CUDA_OK(cudaMemsetAsync(d->d_next_utt, 0, sizeof(int), d->stream));
   if (lattice) {
     int max_t = 1;
     for (int u = 0; u < n; u++) max_t = std::max(max_t, d->batch.n_out[u]);
     const char *e = getenv("RS_B200_LATTICE_MB");
-    const size_t budget = (size_t)std::max(e ? atoi(e) : 8192, 16) << 20;
+    d->lattice_mb = std::max<size_t>(d->lattice_mb, (size_t)std::max(e ? atoi(e) : 8192, 16));
+    const size_t budget = d->lattice_mb << 20;
     const int kLinksPerToken = 3;
     // tokens {state, cost}, extra cost, new id, 3 links, and a survivor list of a quarter of the links
     const size_t per_tok = sizeof(int2) + sizeof(float) + sizeof(int) + kLinksPerToken * sizeof(int4) * 5 / 4;
@@ -1029,11 +1036,21 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(d->ev[4], d->stream));
-  const size_t hdr_bytes = lattice ? sizeof(LatticeHeader) * n + sizeof(int) : 0;
-  char *hout = (char *)d->h_out.ensure(out_bytes + hdr_bytes);
   CUDA_OK(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, d->stream));
   if (lattice) CUDA_OK(cudaMemcpyAsync(hout + out_bytes, d_hdr, hdr_bytes, cudaMemcpyDeviceToHost, d->stream));
   CUDA_OK(cudaStreamSynchronize(d->stream));
+  if (!lattice) break;
+  {
+    const LatticeHeader *hh = reinterpret_cast<const LatticeHeader *>(hout + out_bytes);
+    const int *decoded = reinterpret_cast<const int *>(hout + off_nw);
+    bool overflow = false;
+    for (int u = 0; u < n; u++) overflow |= !hh[u].ok && decoded[u] >= 0;
+    const char *em = getenv("RS_B200_LATTICE_MAX_MB");
+    const size_t max_mb = (size_t)std::max(em ? atoi(em) : 65536, 16);
+    if (!overflow || d->lattice_mb >= max_mb || attempt >= 3) break;
+    d->lattice_mb = std::min(d->lattice_mb * 4, max_mb);
+  }
+  }
   d->last.d2h_bytes = out_bytes + hdr_bytes;
   const LatticeHeader *hdr = reinterpret_cast<const LatticeHeader *>(hout + out_bytes);
   const LatticeArc *harcs = nullptr;

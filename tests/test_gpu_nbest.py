@@ -203,19 +203,24 @@ def test_lattice_that_does_not_fit_falls_back_to_the_best_path(tiny, utterances,
     batch = [utterances[i % len(utterances)] for i in range(64)]
     dec.set_nbest(1)
     one = dec.decode_pcm(batch)
+    from rhasspy_speech_b200 import _lib
+    model, graph, _ = tiny
+    small = _lib.Decoder(model, graph)                    # its own decoder: the lattice budget only ever grows
     monkeypatch.setenv("RS_B200_LATTICE_MB", "16")        # 16 MB / 64 utterances: 4096 tokens each
-    try:
-        dec.set_nbest(4)
-        got = dec.decode_pcm(batch)
-    finally:
-        dec.set_nbest(1)
+    monkeypatch.setenv("RS_B200_LATTICE_MAX_MB", "16")    # ... and no growth
+    small.set_nbest(4)
+    got = small.decode_pcm(batch)
     assert all(s & 32 for s in got.status) and all((s & ~48) == 0 for s in got.status), list(got.status[:8])
     assert list(got.n_hyp) == [1] * 64
     assert got.words == one.words
-    monkeypatch.delenv("RS_B200_LATTICE_MB")
+    # with room to grow, the same call re-runs the stage with a larger budget and returns the lists
+    monkeypatch.delenv("RS_B200_LATTICE_MAX_MB")
+    full = small.decode_pcm(batch)
+    assert all(s in (0, 16) for s in full.status) and max(full.n_hyp) > 1
+    assert [h[0][0] for h in full.nbest] == one.words
+    dec.set_nbest(4)
     try:
-        dec.set_nbest(4)
-        full = dec.decode_pcm(batch[:6])
+        ref_lists = dec.decode_pcm(batch[:6])
     finally:
         dec.set_nbest(1)
-    assert all(s in (0, 16) for s in full.status) and max(full.n_hyp) > 1
+    assert [x for x in full.nbest[:6]] == [x for x in ref_lists.nbest]
