@@ -365,11 +365,11 @@ class KaldiNnet3WavTranscriber(_Base):
             with eng.lock:
                 try:
                     self._set_nbest(eng, nbest)
-                    return eng.decoder.decode_wavs([str(p) for p in wav_paths])
+                    return eng.decoder.decode_wavs([str(p) for p in wav_paths]), eng.decoder.graph
                 except _lib.RsError as e:
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
-        hyp = await loop.run_in_executor(None, run)
-        return [await self._finish(eng, nbest_text(hyp, u), lang_dir, max_fuzzy_cost, require_fuzzy)
+        hyp, graph = await loop.run_in_executor(None, run)
+        return [await self._finish(eng, nbest_text(hyp, u), lang_dir, max_fuzzy_cost, require_fuzzy, graph)
                 for u in range(len(wav_paths))]
 
     async def async_transcribe_rescore(self, *args, **kwargs):
