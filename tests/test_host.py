@@ -182,3 +182,49 @@ def test_dynamic_batcher_groups_concurrent_requests():
     assert ((1, 0.5), ["ok1.wav", "bad.wav", "ok22.wav"]) in dec.calls     # the batch that failed ...
     assert ((1, 0.5), ["bad.wav"]) in dec.calls                            # ... and its per-request retry
     assert b.batches[:3] == [1, 4, 2]
+
+
+def test_transcriber_flow_with_a_fake_engine(tmp_path, monkeypatch):
+    """The Python mirror end to end on CPU with the C library replaced by a fake decoder: async_transcribe (through
+    the dynamic batcher), async_transcribe_many, the legacy class, n-best text and word mapping."""
+    import asyncio
+    import threading
+    from types import SimpleNamespace
+    from rhasspy_speech_b200 import transcribe as T
+
+    words = {1: "turn", 2: "on", 3: "off", 4: "light"}
+
+    class FakeGraph:
+        def word(self, i):
+            return words.get(i)
+
+    class FakeDecoder:
+        graph = FakeGraph()
+
+        def __init__(self):
+            self.nbest = 1
+
+        def set_nbest(self, n, scale=1.0):
+            self.nbest = n
+
+        def decode_wavs(self, paths):
+            n = len(paths)
+            lists = [[([1, 2, 4], 1.0, 2.0), ([1, 3, 4], 1.5, 2.5)][:self.nbest] for _ in paths]
+            return SimpleNamespace(n_utts=n, words=[l[0][0] for l in lists], nbest=lists, status=[0] * n, n_hyp=[len(l) for l in lists])
+
+    dec = FakeDecoder()
+    lock = threading.Lock()
+    eng = SimpleNamespace(decoder=dec, lock=lock, graph=dec.graph, batcher=T._Batcher(dec, lock),
+                          words=lambda ids, graph=None: " ".join((graph or dec.graph).word(i) for i in ids))
+    monkeypatch.setattr(T._Base, "_get_engine", lambda self: eng)
+    monkeypatch.setattr(T.KaldiTranscriber, "_get_engine", lambda self: eng)
+    tr = T.KaldiNnet3WavTranscriber(tmp_path, tmp_path, None)
+    assert asyncio.run(tr.async_transcribe("a.wav", tmp_path)) == ["turn on light"]
+    assert asyncio.run(tr.async_transcribe("a.wav", tmp_path, nbest=2)) == ["turn on light", "turn off light"]
+    many = asyncio.run(tr.async_transcribe_many(["a.wav", "b.wav"], tmp_path, nbest=2))
+    assert many == [["turn on light", "turn off light"]] * 2
+    assert T.KaldiTranscriber(tmp_path, tmp_path).transcribe_wav("a.wav") == "turn on light"
+    with pytest.raises(RuntimeError):
+        asyncio.run(tr.async_transcribe("a.wav", tmp_path, nbest=0))
+    with pytest.raises(NotImplementedError):
+        asyncio.run(tr.async_transcribe_rescore("a.wav", tmp_path, tmp_path))
