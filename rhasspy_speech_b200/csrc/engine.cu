@@ -997,59 +997,59 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   const size_t hdr_bytes = lattice ? sizeof(LatticeHeader) * n + sizeof(int) : 0;
   char *hout = (char *)d->h_out.ensure(out_bytes + hdr_bytes);
   for (int attempt = 0;; attempt++) {
-  CUDA_OK(cudaMemsetAsync(d->d_next_utt, 0, sizeof(int), d->stream));
-  if (lattice) {
-    int max_t = 1;
-    for (int u = 0; u < n; u++) max_t = std::max(max_t, d->batch.n_out[u]);
-    const char *e = getenv("RS_B200_LATTICE_MB");
-    d->lattice_mb = std::max<size_t>(d->lattice_mb, (size_t)std::max(e ? atoi(e) : 8192, 16));
-    const size_t budget = d->lattice_mb << 20;
-    const int kLinksPerToken = 3;
-    // tokens {state, cost}, extra cost, new id, 3 links, and a survivor list of a quarter of the links
-    const size_t per_tok = sizeof(int2) + sizeof(float) + sizeof(int) + kLinksPerToken * sizeof(int4) * 5 / 4;
-    const size_t tc = std::min<size_t>((size_t)o.max_tokens_per_utt, std::max<size_t>(budget / n / per_tok, 4096));
-    LatticeBuf &L = p.lat;
-    L.tok_cap = (int)tc;
-    L.link_cap = (int)std::min<size_t>(tc * kLinksPerToken, 0x7fffffff);
-    L.max_t = max_t;
-    L.tok = (int2 *)d->d_lat_tok.ensure(sizeof(int2) * tc * n);
-    L.extra = (float *)d->d_lat_extra.ensure(sizeof(float) * tc * n);
-    L.newid = (int *)d->d_lat_newid.ensure(sizeof(int) * tc * n);
-    L.link = (int4 *)d->d_lat_link.ensure(sizeof(int4) * (size_t)L.link_cap * n);
-    L.surv_cap = L.link_cap / 4;
-    L.surv = (int4 *)d->d_lat_surv.ensure(sizeof(int4) * (size_t)L.surv_cap * n);
-    L.tok_base = (int *)d->d_lat_tb.ensure(sizeof(int) * (size_t)(max_t + 2) * n);
-    L.link_pos = (int *)d->d_lat_pos.ensure(sizeof(int) * (size_t)(2 * max_t + 4) * n);
-    L.cost_offset = (float *)d->d_lat_off.ensure(sizeof(float) * (size_t)(max_t + 1) * n);
-    // headers [n] + cursor, then the compact arcs of the pruned lattices
-    d_hdr = (LatticeHeader *)d->d_lat_hdr.ensure(sizeof(LatticeHeader) * n + sizeof(int));
-    arcs_cap = (int)std::min<size_t>((size_t)L.link_cap * n / 4 + 65536, 64u << 20);
-    d_arcs = (LatticeArc *)d->d_lat_arcs.ensure(sizeof(LatticeArc) * (size_t)arcs_cap);
-  }
-  LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream, lattice);
-  launches += 1;
-  if (lattice) {
-    int *d_cursor = reinterpret_cast<int *>(d_hdr + n);
-    CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(int), d->stream));
-    LaunchLatticePrune(p, o.lattice_beam, d_hdr, d_arcs, arcs_cap, d_cursor, d->stream);
+    CUDA_OK(cudaMemsetAsync(d->d_next_utt, 0, sizeof(int), d->stream));
+    if (lattice) {
+      int max_t = 1;
+      for (int u = 0; u < n; u++) max_t = std::max(max_t, d->batch.n_out[u]);
+      const char *e = getenv("RS_B200_LATTICE_MB");
+      d->lattice_mb = std::max<size_t>(d->lattice_mb, (size_t)std::max(e ? atoi(e) : 8192, 16));
+      const size_t budget = d->lattice_mb << 20;
+      const int kLinksPerToken = 3;
+      // tokens {state, cost}, extra cost, new id, 3 links, and a survivor list of a quarter of the links
+      const size_t per_tok = sizeof(int2) + sizeof(float) + sizeof(int) + kLinksPerToken * sizeof(int4) * 5 / 4;
+      const size_t tc = std::min<size_t>((size_t)o.max_tokens_per_utt, std::max<size_t>(budget / n / per_tok, 4096));
+      LatticeBuf &L = p.lat;
+      L.tok_cap = (int)tc;
+      L.link_cap = (int)std::min<size_t>(tc * kLinksPerToken, 0x7fffffff);
+      L.max_t = max_t;
+      L.tok = (int2 *)d->d_lat_tok.ensure(sizeof(int2) * tc * n);
+      L.extra = (float *)d->d_lat_extra.ensure(sizeof(float) * tc * n);
+      L.newid = (int *)d->d_lat_newid.ensure(sizeof(int) * tc * n);
+      L.link = (int4 *)d->d_lat_link.ensure(sizeof(int4) * (size_t)L.link_cap * n);
+      L.surv_cap = L.link_cap / 4;
+      L.surv = (int4 *)d->d_lat_surv.ensure(sizeof(int4) * (size_t)L.surv_cap * n);
+      L.tok_base = (int *)d->d_lat_tb.ensure(sizeof(int) * (size_t)(max_t + 2) * n);
+      L.link_pos = (int *)d->d_lat_pos.ensure(sizeof(int) * (size_t)(2 * max_t + 4) * n);
+      L.cost_offset = (float *)d->d_lat_off.ensure(sizeof(float) * (size_t)(max_t + 1) * n);
+      // headers [n] + cursor, then the compact arcs of the pruned lattices
+      d_hdr = (LatticeHeader *)d->d_lat_hdr.ensure(sizeof(LatticeHeader) * n + sizeof(int));
+      arcs_cap = (int)std::min<size_t>((size_t)L.link_cap * n / 4 + 65536, 64u << 20);
+      d_arcs = (LatticeArc *)d->d_lat_arcs.ensure(sizeof(LatticeArc) * (size_t)arcs_cap);
+    }
+    LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream, lattice);
     launches += 1;
-  }
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaEventRecord(d->ev[4], d->stream));
-  CUDA_OK(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, d->stream));
-  if (lattice) CUDA_OK(cudaMemcpyAsync(hout + out_bytes, d_hdr, hdr_bytes, cudaMemcpyDeviceToHost, d->stream));
-  CUDA_OK(cudaStreamSynchronize(d->stream));
-  if (!lattice) break;
-  {
-    const LatticeHeader *hh = reinterpret_cast<const LatticeHeader *>(hout + out_bytes);
-    const int *decoded = reinterpret_cast<const int *>(hout + off_nw);
-    bool overflow = false;
-    for (int u = 0; u < n; u++) overflow |= !hh[u].ok && decoded[u] >= 0;
-    const char *em = getenv("RS_B200_LATTICE_MAX_MB");
-    const size_t max_mb = (size_t)std::max(em ? atoi(em) : 65536, 16);
-    if (!overflow || d->lattice_mb >= max_mb || attempt >= 3) break;
-    d->lattice_mb = std::min(d->lattice_mb * 4, max_mb);
-  }
+    if (lattice) {
+      int *d_cursor = reinterpret_cast<int *>(d_hdr + n);
+      CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(int), d->stream));
+      LaunchLatticePrune(p, o.lattice_beam, d_hdr, d_arcs, arcs_cap, d_cursor, d->stream);
+      launches += 1;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(d->ev[4], d->stream));
+    CUDA_OK(cudaMemcpyAsync(hout, dout, out_bytes, cudaMemcpyDeviceToHost, d->stream));
+    if (lattice) CUDA_OK(cudaMemcpyAsync(hout + out_bytes, d_hdr, hdr_bytes, cudaMemcpyDeviceToHost, d->stream));
+    CUDA_OK(cudaStreamSynchronize(d->stream));
+    if (!lattice) break;
+    {
+      const LatticeHeader *hh = reinterpret_cast<const LatticeHeader *>(hout + out_bytes);
+      const int *decoded = reinterpret_cast<const int *>(hout + off_nw);
+      bool overflow = false;
+      for (int u = 0; u < n; u++) overflow |= !hh[u].ok && decoded[u] >= 0;
+      const char *em = getenv("RS_B200_LATTICE_MAX_MB");
+      const size_t max_mb = (size_t)std::max(em ? atoi(em) : 65536, 16);
+      if (!overflow || d->lattice_mb >= max_mb || attempt >= 3) break;
+      d->lattice_mb = std::min(d->lattice_mb * 4, max_mb);
+    }
   }
   d->last.d2h_bytes = out_bytes + hdr_bytes;
   const LatticeHeader *hdr = reinterpret_cast<const LatticeHeader *>(hout + out_bytes);

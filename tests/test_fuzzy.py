@@ -159,3 +159,16 @@ def test_python_tail_uses_the_in_process_matcher(lib, ref, tmp_path):
     assert asyncio.run(base._finish(None, nbest_stdout, lang, got[1] - 0.5, True)) == []
     assert asyncio.run(T._fuzzy(b"", lang, None)) is None
     assert asyncio.run(T._fuzzy(nbest_stdout, tmp_path, None)) is None            # no G.fuzzy.fst: no-op
+
+
+def test_vector_fst_with_embedded_symbol_tables_loads(lib, ref, tmp_path):
+    """G.fuzzy.fst is a VectorFst written by fstcompile --keep_isymbols --keep_osymbols: the loader skips the two
+    embedded symbol tables (kaldi/openfst/src/lib/symbol-table.cc) and reads the vector body (vector-fst.h:445-484)."""
+    text, words_txt, arcs = write_grammar(str(tmp_path), 3)
+    fst = os.path.join(str(tmp_path), "G.fuzzy.fst")
+    ref.fuzzy_compile(text, words_txt, fst)
+    counts = lib.graph_check(fst, words_txt)
+    n_lines = sum(1 for l in open(text) if len(l.split()) >= 4)
+    assert counts["emitting_arcs"] + counts["epsilon_arcs"] == n_lines
+    assert counts["states"] == 1 + max(a[1] for a in arcs) and counts["start"] == 0
+    assert counts["words"] == len(VOCAB) + 1
