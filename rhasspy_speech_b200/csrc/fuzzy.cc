@@ -19,6 +19,8 @@
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <memory>
+#include <queue>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -30,6 +32,20 @@ namespace rs {
 
 struct FuzzyImpl {
   Graph g;  // G.fuzzy.fst: emitting arcs = arcs with an input word, "epsilon" arcs = <eps> input
+  // every state carries one word:<eps> loop per vocabulary word, so a state's arcs are looked up by input label:
+  // by_label[e_begin[s] .. e_begin[s+1]) = that state's emitting arcs sorted by (ilabel, original position)
+  std::vector<uint32_t> by_label;
+  bool non_negative = true;  // all arc and final weights >= 0: Dijkstra order with early termination is valid
+  void Index() {
+    by_label.resize(g.e_ilabel.size());
+    for (size_t i = 0; i < by_label.size(); i++) by_label[i] = (uint32_t)i;
+    for (int s = 0; s < g.num_states; s++)
+      std::stable_sort(by_label.begin() + g.e_begin[s], by_label.begin() + g.e_begin[s + 1],
+                       [&](uint32_t a, uint32_t b) { return g.e_ilabel[a] < g.e_ilabel[b]; });
+    for (float w : g.e_weight) non_negative &= !(w < 0.f);
+    for (float w : g.p_weight) non_negative &= !(w < 0.f);
+    for (float w : g.final_cost) non_negative &= !(w < 0.f);
+  }
 };
 
 namespace {
@@ -86,7 +102,13 @@ static bool FuzzyMatch(const FuzzyImpl &f, const int32_t *ids, const int32_t *of
     index.emplace(key, (int)node.size() - 1);
     return (int)node.size() - 1;
   };
+  // Non-negative weights (the normal case: -log probabilities, penalties): Dijkstra order, and the search stops as
+  // soon as no open node can beat the best complete match.  Otherwise: label-correcting with a FIFO queue.
+  const bool dijkstra = f.non_negative;
   std::deque<int> queue;
+  typedef std::pair<float, std::pair<long, int>> HeapItem;  // (cost, (sequence number, node)): ties in creation order
+  std::priority_queue<HeapItem, std::vector<HeapItem>, std::greater<HeapItem>> heap;
+  long seq = 0;
   auto relax = [&](int from, int to, float w, int olabel, bool both_eps) {
     const float c = node[from].cost + w;
     if (c < node[to].cost) {
@@ -95,7 +117,9 @@ static bool FuzzyMatch(const FuzzyImpl &f, const int32_t *ids, const int32_t *of
       node[to].olabel = olabel;
       node[to].weight = w;
       node[to].both_eps = both_eps;
-      if (!node[to].queued) {
+      if (dijkstra) {
+        heap.push(HeapItem(c, std::make_pair(seq++, to)));
+      } else if (!node[to].queued) {
         node[to].queued = true;
         queue.push_back(to);
       }
@@ -104,13 +128,25 @@ static bool FuzzyMatch(const FuzzyImpl &f, const int32_t *ids, const int32_t *of
   const int start = id(0, (int)g.start);
   node[start].cost = 0.f;
   node[start].queued = true;
-  queue.push_back(start);
+  if (dijkstra) heap.push(HeapItem(0.f, std::make_pair(seq++, start))); else queue.push_back(start);
   long relaxations = 0;
   const long limit = 64L * 1000 * 1000;
-  while (!queue.empty()) {
-    const int n = queue.front();
-    queue.pop_front();
-    node[n].queued = false;
+  float best_complete = std::numeric_limits<float>::infinity();
+  while (dijkstra ? !heap.empty() : !queue.empty()) {
+    int n;
+    if (dijkstra) {
+      const HeapItem top = heap.top();
+      heap.pop();
+      n = top.second.second;
+      if (top.first > node[n].cost) continue;      // a stale entry
+      if (top.first >= best_complete) break;       // nothing left that could be cheaper
+      if (pos_final[node[n].p] && !std::isinf(g.final_cost[node[n].s]))
+        best_complete = std::min(best_complete, node[n].cost + g.final_cost[node[n].s]);
+    } else {
+      n = queue.front();
+      queue.pop_front();
+      node[n].queued = false;
+    }
     const int p = node[n].p, s = node[n].s;
     // grammar arcs with <eps> input: the hypothesis does not advance
     for (uint32_t a = g.p_begin[s]; a < g.p_begin[s + 1]; a++) {
@@ -118,9 +154,12 @@ static bool FuzzyMatch(const FuzzyImpl &f, const int32_t *ids, const int32_t *of
       relax(n, id(p, g.p_next[a]), g.p_weight[a], g.p_olabel[a], g.p_olabel[a] == 0);
     }
     // a hypothesis word matched with a grammar arc of the same input label
-    for (const Out &o : out[p])
-      for (uint32_t a = g.e_begin[s]; a < g.e_begin[s + 1]; a++)
-        if (g.e_ilabel[a] == o.word) relax(n, id(o.to, g.e_next[a]), o.w + g.e_weight[a], g.e_olabel[a], false);
+    for (const Out &o : out[p]) {
+      const uint32_t *lo = f.by_label.data() + g.e_begin[s], *hi = f.by_label.data() + g.e_begin[s + 1];
+      const uint32_t *it = std::lower_bound(lo, hi, o.word, [&](uint32_t a, int w) { return g.e_ilabel[a] < w; });
+      for (; it < hi && g.e_ilabel[*it] == o.word; ++it)
+        relax(n, id(o.to, g.e_next[*it]), o.w + g.e_weight[*it], g.e_olabel[*it], false);
+    }
     if (++relaxations > limit) return false;
   }
   // best final node: hypothesis at its end, grammar state final
@@ -171,6 +210,7 @@ rs_fuzzy *rs_fuzzy_load(const char *g_fuzzy_fst, const char *words_txt, char *er
     if (!g_fuzzy_fst) RS_FAIL("rs_fuzzy_load: path required");
     std::unique_ptr<FuzzyImpl> f(new FuzzyImpl());
     LoadGraph(g_fuzzy_fst, words_txt ? words_txt : "", &f->g);
+    f->Index();
     return reinterpret_cast<rs_fuzzy *>(f.release());
   } catch (const std::exception &e) {
     FzErr(err, errlen, e.what());
