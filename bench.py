@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_workload(tmp, n_utts, seed):
-    from rhasspy_speech_b200 import synth
+    from tools import synth
     p = synth.write_model(tmp, synth.ZAMIA_LIKE)
     utts = synth.make_utterances(n_utts, seed=seed)
     return p, utts
@@ -93,7 +93,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ref_run
-    from rhasspy_speech_b200 import synth
+    from tools import synth
     if not ref_run.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (run oracle/build_ref.py)"}))
         return
@@ -145,7 +145,7 @@ def run_reference(args):
 def cpu_baseline_sample():
     """Reference timed on the host cores next to the GPU numbers (rank 0, N=1 only), ~10-30 s of CPU work."""
     from oracle import ref_run
-    from rhasspy_speech_b200 import synth
+    from tools import synth
     if not ref_run.available():
         return None
     cores = os.cpu_count() or 1

@@ -44,6 +44,10 @@ typedef struct rs_decoder_opts {
   int32_t max_words;            /* word ids returned per hypothesis (256) */
   int32_t num_lanes;            /* resident decoder CTAs; 0 = 2 per SM */
   uint32_t dither_seed;         /* only used when mfcc.conf asks for dither */
+  int32_t strict_fallback;      /* utterances whose device search was order-sensitive (status bit 4) are decoded again by
+                                 * the strict-order host decoder (csrc/strict_decode.cc) from the log-likelihoods still
+                                 * resident on the device: 1 (default) = those utterances, 0 = never (flag only),
+                                 * 2 = every utterance (test hook) */
 } rs_decoder_opts;
 
 typedef struct rs_result {
@@ -55,11 +59,14 @@ typedef struct rs_result {
   float *acoustic_cost;  /* [n_utts] of the best path */
   int32_t *num_frames;   /* [n_utts] decoded (subsampled) frames */
   int32_t *status;       /* [n_utts] 0 ok; errors: bit0 token capacity, bit1 arena capacity, bit2 no surviving tokens,
-                          * bit3 word capacity; information: bit4 (16) --max-active limited the beam on some frame:
-                          * the reference's pruning is then order-dependent (lattice-faster-decoder.cc:780-787) and the
-                          * hypothesis, although found with the same cutoff values, is not guaranteed word-identical;
+                          * bit3 word capacity; information: bit4 (16) the device search met a frame on which the
+                          * reference's order-dependent pruning (the tokens its transient next_cutoff admits,
+                          * lattice-faster-decoder.cc:780-787) could have changed a cutoff or the set of expanded tokens
+                          * (decode.cu, "safe frame" rules).  With strict_fallback != 0 (default) such an utterance has been
+                          * decoded again by the strict-order host decoder and the result returned is the reference's;
+                          * with strict_fallback == 0 it is the device result, not guaranteed word-identical;
                           * bit5 (32) n-best requested but the lattice did not fit its device buffers: only the best path
-                          * is returned */
+                          * is returned; bit6 (64) the result comes from the strict-order host decoder */
   /* every hypothesis, best first (what lattice-to-nbest | nbest-to-linear print as utt-1 .. utt-n and the two
    * cost archives of nbest-to-linear): hypothesis h of utterance u is entry hyp_offset[u] + h */
   int32_t *hyp_offset;       /* [n_utts + 1] */
@@ -80,6 +87,8 @@ typedef struct rs_timings {
   uint64_t lattice_states, lattice_arcs; /* n-best calls: states and arcs (final weights included) of the pruned
                                           * state-level lattices of the batch -- what GetRawLattice would return */
   uint64_t lattice_links_recorded;       /* forward links recorded before pruning */
+  int32_t strict_utts;                   /* utterances of the last call decoded again by the strict-order host decoder */
+  float strict_ms;                       /* wall time of that (log-likelihood D2H + host search, all threads) */
 } rs_timings;
 
 void rs_decoder_opts_default(rs_decoder_opts *opts);
@@ -180,6 +189,16 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
 int rs_debug_lattice_nbest(const int32_t *src, const int32_t *dst, const int32_t *olabel, const float *graph,
                            const float *acoustic, int32_t n_arcs, int32_t n_nodes, int32_t n, float acoustic_scale,
                            int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost);
+/* Test hook for the strict-order host decoder (csrc/strict_decode.cc; host only, no GPU): what latgen-faster-mapped
+ * (kaldi/src/bin/latgen-faster-mapped.cc) | lattice-to-nbest --n=nbest --acoustic-scale | nbest-to-linear print for
+ * one log-likelihood matrix [n_frames x num_pdfs], with the reference's order-dependent pruning reproduced
+ * (lattice-faster-decoder.cc:780-787, util/hash-list-inl.h:156-194).  tid2pdf[0 .. n_tids) maps HCLG input labels to
+ * pdfs.  Outputs as rs_debug_lattice_nbest; lattice_size (may be NULL) = {states, arcs incl. final weights} of the
+ * pruned state-level lattice when nbest > 1 or acoustic_scale != 1.  Returns the number of hypotheses, < 0 on error. */
+int rs_debug_strict_decode(const char *hclg_fst, const int32_t *tid2pdf, int32_t n_tids, const float *loglikes,
+                           int32_t n_frames, int32_t num_pdfs, const rs_decoder_opts *opts, int32_t nbest, float acoustic_scale,
+                           int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost, int32_t *lattice_size,
+                           char *err, size_t errlen);
 /* Fuzzy matcher in process (host only, no GPU): replaces the seven-process OpenFst pipeline of
  * rhasspy_speech/transcribe_util.py:46-60 (fstcompile | fstcompose - G.fuzzy.fst | fstshortestpath | fstrmepsilon |
  * fsttopsort | fstproject --project_type=output | fstprint).  rs_fuzzy_load reads lang_dir/G.fuzzy.fst (OpenFst vector

@@ -22,7 +22,7 @@ class DecoderOpts(C.Structure):
     _fields_ = [("beam", C.c_float), ("max_active", C.c_int32), ("min_active", C.c_int32), ("lattice_beam", C.c_float),
                 ("acoustic_scale", C.c_float), ("beam_delta", C.c_float), ("max_tokens_per_frame", C.c_int32),
                 ("max_tokens_per_utt", C.c_int32), ("max_words", C.c_int32), ("num_lanes", C.c_int32),
-                ("dither_seed", C.c_uint32)]
+                ("dither_seed", C.c_uint32), ("strict_fallback", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -41,7 +41,7 @@ class Timings(C.Structure):
                 ("tokens_created", C.c_uint64), ("records_written", C.c_uint64), ("nnet_flops", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_int32),
                 ("nnet_bytes", C.c_uint64), ("lattice_states", C.c_uint64), ("lattice_arcs", C.c_uint64),
-                ("lattice_links_recorded", C.c_uint64)]
+                ("lattice_links_recorded", C.c_uint64), ("strict_utts", C.c_int32), ("strict_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -70,6 +70,8 @@ SYMBOLS = [
     ("rs_decoder_set_graph", C.c_int, [_P, _P] + _ERR),
     ("rs_decoder_set_nbest", C.c_int, [_P, C.c_int32, C.c_float] + _ERR),
     ("rs_debug_lattice_nbest", C.c_int, [_P] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, _P]),
+    ("rs_debug_strict_decode", C.c_int, [C.c_char_p, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(DecoderOpts), C.c_int32,
+                                        C.c_float, _P, _P, C.c_int32, _P, _P] + _ERR),
     ("rs_decode_pcm", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
     ("rs_decode_wavs", C.c_int, [_P, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
     ("rs_decode_loglikes", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
@@ -173,6 +175,32 @@ def lattice_nbest(src, dst, olabel, graph, acoustic, n_nodes: int, n: int, acous
     if k < 0:
         raise RsError("rs_debug_lattice_nbest failed (%d)" % k)
     return [([int(x) for x in wid[woff[h]:woff[h + 1]]], float(cost[2 * h]), float(cost[2 * h + 1])) for h in range(k)]
+
+
+def strict_decode(hclg_fst: str, tid2pdf: np.ndarray, loglikes: np.ndarray, nbest: int = 1, acoustic_scale: float = 1.0, **opts):
+    """The strict-order host decoder on one log-likelihood matrix (rs_debug_strict_decode, no GPU):
+    returns ([(word ids, graph cost, acoustic cost), ...] best first, (lattice states, lattice arcs))."""
+    lib = load_library()
+    o = DecoderOpts()
+    lib.rs_decoder_opts_default(C.byref(o))
+    for k, v in opts.items():
+        if not hasattr(o, k):
+            raise TypeError("unknown decoder option " + k)
+        setattr(o, k, v)
+    ll = np.ascontiguousarray(loglikes, dtype=np.float32)
+    t2p = np.ascontiguousarray(tid2pdf, dtype=np.int32)
+    max_words = 4096 * nbest
+    woff = np.zeros(nbest + 1, np.int32)
+    wid = np.zeros(max_words, np.int32)
+    cost = np.zeros(2 * nbest, np.float32)
+    lat = np.zeros(2, np.int32)
+    err = C.create_string_buffer(ERRLEN)
+    k = lib.rs_debug_strict_decode(os.fsencode(hclg_fst), t2p.ctypes.data, len(t2p), ll.ctypes.data, ll.shape[0], ll.shape[1],
+                                   C.byref(o), nbest, acoustic_scale, woff.ctypes.data, wid.ctypes.data, max_words,
+                                   cost.ctypes.data, lat.ctypes.data, err, ERRLEN)
+    _check(k >= 0, err)
+    hyps = [([int(x) for x in wid[woff[h]:woff[h + 1]]], float(cost[2 * h]), float(cost[2 * h + 1])) for h in range(k)]
+    return hyps, (int(lat[0]), int(lat[1]))
 
 
 class PinnedAudio:

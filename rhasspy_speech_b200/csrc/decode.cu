@@ -20,10 +20,29 @@
 // Token costs use the reference's float expression order without FMA contraction, so costs, cutoffs
 // and therefore the surviving token sets are bit-identical wherever the reference itself is
 // order-independent ("decoder semantics").
+//
+// Where the reference IS order-dependent -- "safe frame" rules.  ProcessEmitting admits an arc against a transient
+// next_cutoff (:780-787), so its token list also holds "extras": tokens whose cost lies between the frame's final
+// cutoff and the cutoff seeded from the best token (:744-759), WHICH of them depends on the order of its token hash.
+// This kernel keeps the tokens inside the final cutoff (the set A, order-independent) and inserts every arc inside
+// the seed cutoff, so the entries it drops at compaction are a superset E of the reference's extras.  Extras are
+// never expanded by ProcessNonemitting (cost >= cutoff) and die after one frame; they can matter only on the next
+// frame, through GetCutoff's token count / nth_element or by being expanded.  With n = |A|, ne = |E|, me = min cost in E:
+//   * --max-active binds on A (n > max_active, its cutoff below the beam cutoff): the cutoff is the same with any
+//     subset of E added (extras cost more than every token of A), and it lies below me: safe;
+//   * otherwise unsafe if n <= max_active < n + ne and me < beam cutoff (extras could make max-active bind),
+//     or n <= min_active (the count test of :691, or an infinite cutoff under which extras would be expanded);
+//   * unsafe if me <= the frame's cutoff (an extra would be expanded);
+//   * last frame: unsafe if an extra with its final cost could be the best final token (or, n-best, lie inside the
+//     lattice beam of it).
+// An utterance with an unsafe frame carries status bit 4 (16) and is decoded again by strict_decode.cc; by induction
+// over the frames an unflagged utterance has exactly the reference's tokens inside the final cutoffs, its costs, its
+// cutoffs and its best path.  (Small graphs never get here: decode_small.cu reproduces the order itself.)
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 
+#include "decode_common.cuh"
 #include "engine.h"
 
 namespace rs {
@@ -34,9 +53,7 @@ constexpr int kMaxNT = 512;
 constexpr int kMaxNW = kMaxNT / 32;
 #define NT ((int)blockDim.x)
 #define NW ((int)(blockDim.x >> 5))
-constexpr unsigned long long kEmptyVal = ~0ULL;
 constexpr int kEmptyKey = -1;
-constexpr unsigned kArcNone = 0xffffffffu;
 
 static int g_decode_threads = 0;
 int DecodeCtaThreads() {
@@ -49,17 +66,6 @@ int DecodeCtaThreads() {
   return g_decode_threads;
 }
 
-__device__ __forceinline__ unsigned ord(float f) {
-  unsigned b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float unord(unsigned o) {
-  unsigned b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
-  return __uint_as_float(b);
-}
-__device__ __forceinline__ unsigned long long pack(float cost, unsigned arc) {
-  return ((unsigned long long)ord(cost) << 32) | arc;
-}
 __device__ __forceinline__ unsigned hash_state(int s) { return (unsigned)s * 2654435761u; }
 
 struct Shared {
@@ -80,6 +86,9 @@ struct Shared {
   int any_final;
   int n_links;       // lattice mode: links recorded so far for the utterance
   int lat_overflow;  // lattice mode: link capacity exceeded
+  unsigned seed_ord;             // next_cutoff as seeded from the best token's arcs (:744-759)
+  unsigned min_extra_ord;        // cheapest entry beyond the final cutoff of the frame being finalised (ord())
+  unsigned min_extra_final_ord;  // last frame: cheapest such entry with its final cost added
 };
 
 __device__ __forceinline__ unsigned block_excl_scan(unsigned v, Shared &S, unsigned *total) {
@@ -362,6 +371,8 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     };
     int status = 0;
     int info = 0;  // bit 16: --max-active decided the beam on some frame (see rs_result.status)
+    int n_extra = 0;       // entries the last compaction dropped: superset of the reference's extras on the current frame
+    float min_extra = kInf;
     int cur = 0;
     int n_cur = 0;        // alive tokens of the current frame
     int base_cur = 0;     // arena index of the current frame's first token
@@ -369,11 +380,14 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
 
     // One pass of: epsilon closure of table `tb` under `cutoff`, compaction of the alive entries
     // into tok_state/tok_cost[tb], traceback records.  `tprev` is the table of the previous frame.
-    auto close_and_finalize = [&](int tb, int tprev, float cutoff, int base_prev, int base_new) -> int {
+    auto close_and_finalize = [&](int tb, int tprev, float cutoff, int base_prev, int base_new, bool last) -> int {
       Table T{ws.hkey[tb], ws.hval[tb], ws.hidx[tb], ws.ins_list[tb], &S.n_ins[tb]};
       // ---- ProcessNonemitting (:820-887): frontier = alive tokens whose state has epsilon arcs
       int fcur = 0;
-      if (tid == 0) S.frontier_n[0] = S.frontier_n[1] = 0;
+      if (tid == 0) {
+        S.frontier_n[0] = S.frontier_n[1] = 0;
+        S.min_extra_ord = S.min_extra_final_ord = 0xffffffffu;
+      }
       __syncthreads();
       {
         const int n_ins = S.n_ins[tb];
@@ -443,6 +457,13 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           c = unord((unsigned)(ldv(T.hval + s) >> 32));
           alive = c < cutoff ? 1u : 0u;
           st = ldv(T.hkey + s);
+          if (!alive) {  // a possible extra of the reference (safe-frame rules)
+            atomicMin(&S.min_extra_ord, ord(c));
+            if (last) {
+              const float f = g.final_cost[st];
+              if (f != kInf) atomicMin(&S.min_extra_final_ord, ord(__fadd_rn(c, f)));
+            }
+          }
         }
         unsigned total;
         unsigned pos = running + block_excl_scan(alive, S, &total);
@@ -458,6 +479,8 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       }
       __syncthreads();
       const int n_new = (int)running;
+      n_extra = n_ins - n_new;
+      min_extra = unord(S.min_extra_ord);
       if (base_new + n_new > arena_cap) return -2;
       tick(4);
       // ---- traceback records: the arc stored with the winning cost names the predecessor state
@@ -545,7 +568,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
     }
     __syncthreads();
     {
-      int r = close_and_finalize(0, 1, cfg.beam, 0, 0);
+      int r = close_and_finalize(0, 1, cfg.beam, 0, 0, false);
       if (r < 0) {
         status |= (r == -1 ? 1 : 2);
         n_cur = 0;
@@ -592,10 +615,12 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         float max_active_cutoff = kInf, min_active_cutoff = kInf;
         if (n_cur > cfg.max_active) max_active_cutoff = block_select(cost, n_cur, cfg.max_active, S);
         if (max_active_cutoff < beam_cutoff) {
-          info |= 16;
           adaptive_beam = __fadd_rn(__fsub_rn(max_active_cutoff, best), cfg.beam_delta);
           cur_cutoff = max_active_cutoff;
         } else {
+          if (n_extra > 0 && (n_cur <= cfg.min_active ||
+                              (n_cur <= cfg.max_active && n_cur + n_extra > cfg.max_active && min_extra < beam_cutoff)))
+            info |= 16;
           if (n_cur > cfg.min_active) {
             if (cfg.min_active == 0) {
               min_active_cutoff = best;
@@ -620,6 +645,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           }
         }
       }
+      if (n_extra > 0 && min_extra <= cur_cutoff) info |= 16;
       tick(0);
       // ---- ProcessEmitting (:714-804)
       const float cost_offset = -best;
@@ -633,7 +659,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) S.nc_ord = ord(m);
+        if (lane == 0) S.nc_ord = S.seed_ord = ord(m);
       }
       // out-degree prefix over the tokens inside the cutoff
       unsigned n_arcs = 0;
@@ -654,7 +680,8 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       tick(1);
       {
         Table T{ws.hkey[nxt], ws.hval[nxt], ws.hidx[nxt], ws.ins_list[nxt], &S.n_ins[nxt]};
-        volatile unsigned *nc = &S.nc_ord;
+        const float seed_cutoff = unord(S.seed_ord);  // every arc inside the SEED cutoff is inserted: a superset of what
+                                                    // any visiting order admits, independent of thread timing
         for (unsigned a = tid; a < n_arcs; a += NT) {
           int lo = 0, hi = n_cur;
           while (hi - lo > 1) {
@@ -666,10 +693,9 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           const int4 arc = g.earc[ai];
           const float ac = __fsub_rn(cost_offset, ll[arc.y]);
           const float tot = __fadd_rn(__fadd_rn(cost[lo], ac), __int_as_float(arc.z));
-          const float ncv = unord(*nc);
-          if (tot >= ncv) continue;
+          if (tot >= seed_cutoff) continue;
           const float cand = __fadd_rn(tot, adaptive_beam);
-          if (cand < ncv) atomicMin(&S.nc_ord, ord(cand));
+          if (cand < seed_cutoff) atomicMin(&S.nc_ord, ord(cand));
           if (*(volatile int *)&S.overflow) break;
           int s2 = insert_slot(T, arc.x, mask, identity, tok_cap, &S.overflow);
           // (a plain load of the slot to skip non-improving arcs before the 64-bit atomic was measured: the extra
@@ -687,7 +713,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       cnt_tokens += n_cur;
       cnt_arcs += (tid == 0) ? n_arcs : 0;
       const int base_new = base_cur + n_cur;
-      int r = close_and_finalize(nxt, cur, next_cutoff, base_cur, base_new);
+      int r = close_and_finalize(nxt, cur, next_cutoff, base_cur, base_new, frame == n_frames - 1);
       if (r < 0) {
         status |= (r == -1 ? 1 : 2);
         break;
@@ -707,12 +733,17 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           const int4 arc = g.earc[ai];
           const float ac = __fsub_rn(cost_offset, ll[arc.y]);
           const float tot = __fadd_rn(__fadd_rn(cost[lo], ac), __int_as_float(arc.z));
-          if (tot < next_cutoff) {
+          // tot < next_cutoff: a link in any visiting order.  next_cutoff <= tot < seed cutoff: the reference holds
+          // this link only if it reached the arc before its transient cutoff had tightened -- recorded as a "maybe"
+          // link (arc id with the sign bit set); lattice_prune_kernel keeps it out of the sweep and reports the
+          // utterance as order-sensitive if the link would have survived the lattice beam
+          if (tot < unord(S.seed_ord)) {
             const int ss = find_slot(ws.hkey[nxt], arc.x, mask, identity);
             const int dpos = ss >= 0 ? ws.hidx[nxt][ss] : -1;
             if (dpos >= 0) {
               const float slack = __fsub_rn(tot, ws.tok_cost[nxt][dpos]);
-              if (!(slack > cfg.lattice_beam)) add_link(base_cur + lo, base_new + dpos, ai, slack);
+              if (!(slack > cfg.lattice_beam))
+                add_link(base_cur + lo, base_new + dpos, tot < next_cutoff ? ai : (ai | 0x80000000u), slack);
             }
           }
         }
@@ -765,6 +796,11 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
         }
       }
       block_min(bv, bi, S);
+      // safe-frame rule of the last frame: an entry beyond the final cutoff that is final and, with its final cost,
+      // as cheap as the best final token (n-best: inside the lattice beam of it) -- or final when no kept token is
+      if (S.min_extra_final_ord != 0xffffffffu &&
+          (!anyf || unord(S.min_extra_final_ord) <= __fadd_rn(S.best_cost, kLat ? cfg.lattice_beam : 0.f)))
+        info |= 16;
       if (S.best_idx == 0x7fffffff) {
         status |= 4;
       } else if (tid == 0) {
@@ -857,10 +893,10 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
                                                                LatticeHeader *headers, LatticeArc *arcs, int arcs_cap,
                                                                int *cursor) {
   __shared__ Shared S;
-  __shared__ int s_changed, s_base, s_nsurv, s_nfin;
+  __shared__ int s_changed, s_base, s_nsurv, s_nfin, s_maybe;
   const int tid = threadIdx.x;
   const int u = blockIdx.x;
-  if (tid == 0) s_nsurv = 0;
+  if (tid == 0) s_nsurv = s_maybe = 0;
   const DevGraph &g = P.g;
   const int T = P.n_frames[u];
   const float kInf = __int_as_float(0x7f800000);
@@ -944,7 +980,7 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
     for (int i = e0 + tid; i < e1; i += NT) {
       const int4 l = i < e0 + NT ? my_e : llink[i];
       const float le = __fadd_rn(ldx(nxt + (l.y - b1)), __int_as_float(l.w));
-      if (!(le > lattice_beam)) atomicMin(cur + (l.x - b0), __float_as_uint(fmaxf(le, 0.f)));
+      if (l.z >= 0 && !(le > lattice_beam)) atomicMin(cur + (l.x - b0), __float_as_uint(fmaxf(le, 0.f)));
     }
     if (tid == 0) s_changed = 0;
     __syncthreads();
@@ -972,6 +1008,10 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
     for (int i = e0 + tid; i < e1; i += NT) {
       const int4 l = i < e0 + NT ? my_e : llink[i];
       if (!(__fadd_rn(ldx(nxt + (l.y - b1)), __int_as_float(l.w)) > lattice_beam)) {
+        if (l.z < 0) {  // a "maybe" link that would survive: the lattice depends on the reference's visiting order
+          s_maybe = 1;
+          continue;
+        }
         const int k = atomicAdd(&s_nsurv, 1);
         if (k < P.lat.surv_cap) surv[k] = make_int4(l.x, l.y, l.z, t);
       }
@@ -1042,7 +1082,7 @@ __global__ void __launch_bounds__(kMaxNT) lattice_prune_kernel(const __grid_cons
     const float fc = anyf ? g.final_cost[ltok[i].x] : 0.f;
     if (newid[i] >= 0 && fc != kInf) arcs[base + n_surv + atomicAdd(&s_nfin, 1)] = LatticeArc{newid[i], -1, 0, fc, 0.f};
   }
-  if (tid == 0) headers[u] = LatticeHeader{base, n_out, (int)n_nodes, 1, nlink, {0, 0, 0}};
+  if (tid == 0) headers[u] = LatticeHeader{base, n_out, (int)n_nodes, 1, nlink, {s_maybe, 0, 0}};
 }
 
 void LaunchLatticePrune(const DecodeParams &p, float lattice_beam, LatticeHeader *headers, LatticeArc *arcs,

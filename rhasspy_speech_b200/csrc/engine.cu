@@ -19,6 +19,7 @@
 #include "model.h"
 #include "nnet_tc.h"
 #include "nbest.h"
+#include "strict_decode.h"
 
 namespace rs {
 
@@ -384,6 +385,8 @@ struct DecoderImpl {
   std::vector<void *> owned;
   DevBuf d_pcm, d_desc, d_mfcc, d_mfcc_norm, d_xraw, d_xnorm, d_post_idx, d_post_w, d_wf, d_gw, d_linear, d_quad;
   DevBuf d_out;  // decode outputs
+  DevBuf d_small_arena, d_small_off;  // decode_small.cu: batch traceback arena and its per-utterance offsets
+  PinBuf h_small;
   // n-best tail (rs_decoder_set_nbest): lattice recorded by decode_kernel<true>, pruned + compacted on the device
   int nbest = 1;
   float nbest_scale = 1.0f;
@@ -391,6 +394,7 @@ struct DecoderImpl {
   DevBuf d_lat_tok, d_lat_extra, d_lat_newid, d_lat_link, d_lat_surv, d_lat_tb, d_lat_pos, d_lat_off, d_lat_hdr, d_lat_arcs;
   PinBuf h_lat;
   std::vector<LatticeHeader> lat_hdr;  // of the last n-best call (rs_debug_fetch item 5)
+  std::map<int, std::vector<LatticeArc>> strict_lat;  // lattices of the utterances the strict-order decoder re-decoded
   std::vector<DevBuf> slots;
   DevBuf d_tid_pdf;
   DevBuf d_loglikes_ext;
@@ -402,6 +406,7 @@ struct DecoderImpl {
   std::unique_ptr<PackPool> pool;
   DevBuf d_earc_buf;                // graph arcs with ilabel mapped to pdf for this model
   const int4 *d_earc = nullptr;
+  std::vector<int32_t> h_epdf;      // the same map on the host, for the strict-order decoder (strict_decode.cc)
   rs_timings last{};
   // layout of the last batch (for rs_debug_fetch)
   struct Batch {
@@ -623,6 +628,7 @@ void rs_decoder_opts_default(rs_decoder_opts *o) {
   o->max_words = 256;
   o->num_lanes = 0;
   o->dither_seed = 0;
+  o->strict_fallback = 1;
 }
 
 rs_model *rs_model_load(const char *final_mdl, const char *online_conf, int device, char *err, size_t errlen) {
@@ -688,6 +694,9 @@ rs_graph *rs_graph_load(const char *hclg_fst, const char *words_txt, int device,
     parc[i] = make_int4(g.p_next[i], 0, wbits, g.p_olabel[i]);
   }
   d.parc = Upload(parc, &gi->owned);
+  d.eps_flat = 1;
+  for (size_t i = 0; i < g.p_next.size(); i++)
+    if (g.p_begin[g.p_next[i] + 1] > g.p_begin[g.p_next[i]]) d.eps_flat = 0;
   d.earc = nullptr;  // per decoder: ilabels are mapped through the model's tid -> pdf table
   return reinterpret_cast<rs_graph *>(gi.release());
   API_GUARD_END(nullptr)
@@ -715,6 +724,7 @@ static void BindGraph(DecoderImpl *d, GraphImpl *gi) {
   const Graph &g = gi->g;
   const auto &t2p = d->model->m.trans.tid2pdf;
   std::vector<int4> earc(g.e_next.size());
+  std::vector<int32_t> epdf(g.e_next.size());
   for (size_t i = 0; i < earc.size(); i++) {
     int il = g.e_ilabel[i];
     if (il <= 0 || il >= (int)t2p.size())
@@ -722,6 +732,7 @@ static void BindGraph(DecoderImpl *d, GraphImpl *gi) {
     int wbits;
     memcpy(&wbits, &g.e_weight[i], 4);
     earc[i] = make_int4(g.e_next[i], t2p[il], wbits, g.e_olabel[i]);
+    epdf[i] = t2p[il];
   }
   // a fresh allocation, so that a failed bind leaves the decoder on its previous graph
   DevBuf fresh;
@@ -730,6 +741,7 @@ static void BindGraph(DecoderImpl *d, GraphImpl *gi) {
   std::swap(d->d_earc_buf.p, fresh.p);
   std::swap(d->d_earc_buf.cap, fresh.cap);
   d->d_earc = d->d_earc_buf.as<int4>();
+  d->h_epdf.swap(epdf);
   d->graph = gi;
 }
 
@@ -991,6 +1003,9 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
   // lattice of the batch does not fit, the stage is run again with four times the budget (the log-likelihoods are
   // still resident), up to RS_B200_LATTICE_MAX_MB (default 65536); the grown budget is kept for later calls.
   const bool lattice = d->nbest > 1 || d->nbest_scale != 1.0f;
+  // small graphs: the kernel that reproduces the reference's token order (RS_B200_DECODE_EXACT=0 forces the general one)
+  bool small = DecodeSmallSupports(p.g);
+  if (const char *e = getenv("RS_B200_DECODE_EXACT")) small = small && e[0] != '0';
   LatticeHeader *d_hdr = nullptr;
   LatticeArc *d_arcs = nullptr;
   int arcs_cap = 0;
@@ -1026,7 +1041,20 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
       arcs_cap = (int)std::min<size_t>((size_t)L.link_cap * n / 4 + 65536, 64u << 20);
       d_arcs = (LatticeArc *)d->d_lat_arcs.ensure(sizeof(LatticeArc) * (size_t)arcs_cap);
     }
-    LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream, lattice);
+    if (small) {
+      // per-utterance slices of one traceback arena: at most one token per state and time
+      std::vector<long long> off(n + 1, 0);
+      for (int u = 0; u < n; u++) off[u + 1] = off[u] + (long long)(d->batch.n_out[u] + 1) * d->graph->g.num_states;
+      long long *h_off = (long long *)d->h_small.ensure(sizeof(long long) * (n + 1));
+      memcpy(h_off, off.data(), sizeof(long long) * (n + 1));
+      long long *d_off = (long long *)d->d_small_off.ensure(sizeof(long long) * (n + 1));
+      CUDA_OK(cudaMemcpyAsync(d_off, h_off, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, d->stream));
+      p.small_arena = (int2 *)d->d_small_arena.ensure(sizeof(int2) * (size_t)std::max<long long>(off[n], 1));
+      p.small_arena_off = d_off;
+      LaunchDecodeSmall(p, d->stream, lattice);
+    } else {
+      LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream, lattice);
+    }
     launches += 1;
     if (lattice) {
       int *d_cursor = reinterpret_cast<int *>(d_hdr + n);
@@ -1088,15 +1116,102 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     d->last.frames_decoded += d->batch.n_out[u];
   }
   r->word_offset[n] = pos;
+  // ---- order-sensitive utterances (status bit 4): decoded again by the strict-order host decoder from the
+  // log-likelihoods that are still resident on the device; its result replaces the device result
+  std::vector<int> strict_list;
+  std::vector<StrictResult> strict_res;
+  d->last.strict_utts = 0;
+  d->last.strict_ms = 0.f;
+  if (o.strict_fallback) {
+    for (int u = 0; u < n; u++)
+      if (d->batch.n_out[u] > 0 && !(status[u] & 7) &&
+          (o.strict_fallback == 2 || (status[u] & 16) || (lattice && hdr[u].ok && hdr[u].pad[0]))) {
+        r->status[u] |= 16;
+        strict_list.push_back(u);
+      }
+  }
+  if (!strict_list.empty()) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int ns = (int)strict_list.size();
+    strict_res.resize(ns);
+    std::vector<std::vector<float>> ll(ns);
+    for (int i = 0; i < ns; i++) {
+      const int u = strict_list[i];
+      ll[i].resize((size_t)d->batch.n_out[u] * ld);
+      CUDA_OK(cudaMemcpyAsync(ll[i].data(), loglikes + (size_t)d->batch.ll_row0[u] * ld, ll[i].size() * sizeof(float),
+                              cudaMemcpyDeviceToHost, d->stream));
+      d->last.d2h_bytes += ll[i].size() * sizeof(float);
+    }
+    CUDA_OK(cudaStreamSynchronize(d->stream));
+    StrictOptions so;
+    so.beam = o.beam;
+    so.beam_delta = o.beam_delta;
+    so.lattice_beam = o.lattice_beam;
+    so.max_active = o.max_active;
+    so.min_active = o.min_active;
+    so.max_words = W;
+    const int nthreads = std::max(1, std::min(ns, (int)std::thread::hardware_concurrency()));
+    std::atomic<int> next{0};
+    std::string fail;
+    std::mutex fail_mu;
+    auto work = [&]() {
+      try {
+        for (int i = next++; i < ns; i = next++)
+          StrictDecode(d->graph->g, d->h_epdf.data(), ll[i].data(), ld, d->batch.n_out[strict_list[i]], so, lattice, &strict_res[i]);
+      } catch (const std::exception &e) {
+        std::lock_guard<std::mutex> lk(fail_mu);
+        fail = e.what();
+      }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nthreads; i++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (!fail.empty()) {
+      rs_result_free(r);
+      RS_FAIL("strict-order decoder: " << fail);
+    }
+    // splice the words of the re-decoded utterances into the result
+    std::vector<int32_t> ids;
+    const std::vector<int32_t> old(r->word_offset, r->word_offset + n + 1);
+    int si = 0;
+    for (int u = 0; u < n; u++) {
+      r->word_offset[u] = (int)ids.size();
+      if (si < ns && strict_list[si] == u) {
+        const StrictResult &sr = strict_res[si++];
+        r->n_hyp[u] = sr.decoded ? 1 : 0;
+        r->graph_cost[u] = sr.decoded ? sr.graph : 0.f;
+        r->acoustic_cost[u] = sr.decoded ? sr.acoustic : 0.f;
+        r->status[u] = (r->status[u] & ~(4 | 8)) | 64 | (sr.decoded ? 0 : 4) | (sr.word_overflow ? 8 : 0);
+        ids.insert(ids.end(), sr.words.begin(), sr.words.end());
+      } else {
+        ids.insert(ids.end(), r->word_ids + old[u], r->word_ids + old[u + 1]);
+      }
+    }
+    r->word_offset[n] = (int)ids.size();
+    delete[] r->word_ids;
+    r->word_ids = new int32_t[std::max<size_t>(ids.size(), 1)];
+    std::copy(ids.begin(), ids.end(), r->word_ids);
+    d->last.strict_utts = ns;
+    d->last.strict_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   std::vector<std::vector<NbestHyp>> nb;
   if (lattice) {
     // host half of the tail: best-first search of each pruned lattice (nbest.cc), utterances across threads
     nb.resize(n);
     const int nthreads = std::max(1, std::min({n, 8, (int)std::thread::hardware_concurrency()}));
     std::atomic<int> next{0};
+    std::vector<int> strict_of(n, -1);
+    for (size_t i = 0; i < strict_list.size(); i++) strict_of[strict_list[i]] = (int)i;
     auto work = [&]() {
       for (int u = next++; u < n; u = next++) {
-        if (!hdr[u].ok || r->n_hyp[u] == 0) continue;
+        if (r->n_hyp[u] == 0) continue;
+        if (strict_of[u] >= 0) {
+          const StrictResult &sr = strict_res[strict_of[u]];
+          LatticeNbest(sr.lattice.data(), (int)sr.lattice.size(), sr.n_nodes, d->nbest, d->nbest_scale, &nb[u]);
+          continue;
+        }
+        if (!hdr[u].ok) continue;
         LatticeNbest(harcs + hdr[u].arc_begin, hdr[u].n_arcs, hdr[u].n_nodes, d->nbest, d->nbest_scale, &nb[u]);
       }
     };
@@ -1105,6 +1220,8 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     work();
     for (auto &t : th) t.join();
     d->lat_hdr.assign(hdr, hdr + n);
+    d->strict_lat.clear();
+    for (size_t i = 0; i < strict_list.size(); i++) d->strict_lat[strict_list[i]].swap(strict_res[i].lattice);
     d->last.lattice_states = d->last.lattice_arcs = d->last.lattice_links_recorded = 0;
     for (int u = 0; u < n; u++) {
       if (r->n_hyp[u] && nb[u].empty()) r->status[u] |= 32;
@@ -1115,7 +1232,10 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
       }
     }
   }
-  if (!lattice) d->lat_hdr.clear();
+  if (!lattice) {
+    d->lat_hdr.clear();
+    d->strict_lat.clear();
+  }
   if (lattice && d->nbest_scale != 1.0f) {
     // the per-utterance fields describe utt-1 of the list: under a ranking scale that need not be the
     // back-traced path of the search (which ran at scale 1)
@@ -2023,6 +2143,61 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
   API_GUARD_END(1)
 }
 
+int rs_debug_strict_decode(const char *hclg_fst, const int32_t *tid2pdf, int32_t n_tids, const float *loglikes,
+                           int32_t n_frames, int32_t num_pdfs, const rs_decoder_opts *opts, int32_t nbest, float acoustic_scale,
+                           int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost, int32_t *lattice_size,
+                           char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  if (!hclg_fst || !tid2pdf || !loglikes || !opts || !word_offset || !word_ids || !cost || nbest < 1 || n_frames < 0)
+    RS_FAIL("rs_debug_strict_decode: bad argument");
+  Graph g;
+  LoadGraph(hclg_fst, "", &g);
+  std::vector<int32_t> epdf(g.e_next.size());
+  for (size_t i = 0; i < epdf.size(); i++) {
+    const int il = g.e_ilabel[i];
+    if (il <= 0 || il >= n_tids) RS_FAIL("HCLG has input label " << il << " outside the transition-id table");
+    epdf[i] = tid2pdf[il];
+    if (epdf[i] < 0 || epdf[i] >= num_pdfs) RS_FAIL("pdf id out of range");
+  }
+  StrictOptions so;
+  so.beam = opts->beam;
+  so.beam_delta = opts->beam_delta;
+  so.lattice_beam = opts->lattice_beam;
+  so.max_active = opts->max_active;
+  so.min_active = opts->min_active;
+  so.max_words = std::max(opts->max_words, 1);
+  const bool lattice = nbest > 1 || acoustic_scale != 1.0f;
+  StrictResult sr;
+  StrictDecode(g, epdf.data(), loglikes, num_pdfs, n_frames, so, lattice, &sr);
+  if (lattice_size) {
+    lattice_size[0] = sr.n_nodes;
+    lattice_size[1] = (int32_t)sr.lattice.size();
+  }
+  std::vector<NbestHyp> hyps;
+  if (sr.decoded) {
+    if (lattice) {
+      LatticeNbest(sr.lattice.data(), (int)sr.lattice.size(), sr.n_nodes, nbest, acoustic_scale, &hyps);
+    } else {
+      NbestHyp h;
+      h.words = sr.words;
+      h.graph = sr.graph;
+      h.acoustic = sr.acoustic;
+      hyps.push_back(h);
+    }
+  }
+  int w = 0;
+  for (size_t h = 0; h < hyps.size(); h++) {
+    word_offset[h] = w;
+    if (w + (int)hyps[h].words.size() > max_words) RS_FAIL("rs_debug_strict_decode: word buffer too small");
+    for (int id : hyps[h].words) word_ids[w++] = id;
+    cost[2 * h] = hyps[h].graph;
+    cost[2 * h + 1] = hyps[h].acoustic;
+  }
+  word_offset[hyps.size()] = w;
+  return (int)hyps.size();
+  API_GUARD_END(-1)
+}
+
 int rs_decoder_timings(const rs_decoder *d_, rs_timings *t) {
   const DecoderImpl *d = reinterpret_cast<const DecoderImpl *>(d_);
   if (!d || !t) return 1;
@@ -2044,6 +2219,17 @@ int rs_debug_fetch(rs_decoder *d_, int32_t what, int32_t utt, float *dst, int32_
   if (what == 5) {
     // pruned state-level lattice of the last n-best call: rows of (src, dst, olabel, graph cost, acoustic cost)
     if ((int)d->lat_hdr.size() != B.n) RS_FAIL("rs_debug_fetch: the last call did not build lattices (rs_decoder_set_nbest)");
+    auto sl = d->strict_lat.find(utt);
+    if (sl != d->strict_lat.end()) {
+      if (rows) *rows = (int)sl->second.size();
+      if (cols) *cols = 5;
+      for (size_t i = 0; dst && i < sl->second.size(); i++) {
+        const LatticeArc &a = sl->second[i];
+        float *o = dst + i * 5;
+        o[0] = (float)a.src, o[1] = (float)a.dst, o[2] = (float)a.olabel, o[3] = a.graph, o[4] = a.acoustic;
+      }
+      return 0;
+    }
     const LatticeHeader &h = d->lat_hdr[utt];
     if (rows) *rows = h.ok ? h.n_arcs : 0;
     if (cols) *cols = 5;

@@ -151,6 +151,7 @@ struct DevGraph {
   const int4 *parc;                   // {next, 0, weight bits, olabel}
   const int *p_src;
   const float *final_cost;
+  int eps_flat;  // no epsilon arc leads to a state that has epsilon arcs itself (decode_small.cu)
 };
 
 struct DecodeConfig {
@@ -197,7 +198,8 @@ struct LatticeBuf {
 
 // compact lattice as the host receives it: one header per utterance, then its arcs in `arcs`
 struct LatticeHeader {
-  int arc_begin, n_arcs, n_nodes, ok, n_links, pad[3];
+  int arc_begin, n_arcs, n_nodes, ok, n_links;
+  int pad[3];  // pad[0]: a link the reference holds only under some visiting orders would have survived the pruning
 };
 struct LatticeArc {  // dst == -1: final weight of src (graph = final cost, acoustic = 0)
   int src, dst, olabel;
@@ -215,6 +217,9 @@ struct DecodeParams {
   int n_utts;
   LaneWorkspace *lanes;   // [gridDim.x]
   int *next_utt;          // work counter
+  // decode_small.cu: one traceback arena for the batch, utterance u owns records [small_arena_off[u], small_arena_off[u + 1])
+  int2 *small_arena;
+  const long long *small_arena_off;
   // outputs
   int *words;             // [n_utts, max_words]
   int *n_words;           // [n_utts]  (-1 = nothing decoded)
@@ -227,6 +232,11 @@ void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream, bool 
 // then renumbering + compaction of the surviving arcs into `arcs` (global cursor `cursor`), one CTA per utterance
 void LaunchLatticePrune(const DecodeParams &p, float lattice_beam, LatticeHeader *headers, LatticeArc *arcs,
                         int arcs_cap, int *cursor, cudaStream_t stream);
+// Small graphs (decode_small.cu): the reference's token order reproduced on the device -- exact unconditionally.
+// The reference's token hash never has fewer than 1000 buckets, so up to 1000 states map one state to a bucket.
+constexpr int kSmallMaxStates = 1000, kSmallMaxEarcs = 16384, kSmallMaxParcs = 4096;
+bool DecodeSmallSupports(const DevGraph &g);
+void LaunchDecodeSmall(const DecodeParams &p, cudaStream_t stream, bool lattice = false);
 int DecodeCtaThreads();
 size_t DecodeSmemBytes(int slots);
 

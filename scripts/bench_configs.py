@@ -4,7 +4,8 @@ config 3 (ARPA-shaped HCLG, batch 256, 10 % out-of-grammar audio) and config 4 (
 import dataclasses, json, os, sys, tempfile, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rhasspy_speech_b200 import synth, _lib
+from rhasspy_speech_b200 import _lib
+from tools import synth
 
 
 def run(name, dec, fn, audio_s, reps=4):

@@ -3,7 +3,8 @@ latgen-faster-mapped (with path costs) and through rs_decode_loglikes at several
 import dataclasses, os, sys, tempfile
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rhasspy_speech_b200 import synth, _lib
+from rhasspy_speech_b200 import _lib
+from tools import synth
 from oracle import ref_run
 
 which = sys.argv[1] if len(sys.argv) > 1 else "arpa"

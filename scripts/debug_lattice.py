@@ -8,7 +8,8 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref_run  # noqa: E402
-from rhasspy_speech_b200 import _lib, synth  # noqa: E402
+from rhasspy_speech_b200 import _lib  # noqa: E402
+from tools import synth  # noqa: E402
 
 tmp = tempfile.mkdtemp()
 p = synth.write_model(tmp, synth.TINY)

@@ -2,7 +2,8 @@
 import dataclasses, os, sys, tempfile
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rhasspy_speech_b200 import synth, _lib
+from rhasspy_speech_b200 import _lib
+from tools import synth
 from oracle import ref_run, kaldi_np as K
 
 which = sys.argv[1] if len(sys.argv) > 1 else "arpa"

@@ -3,7 +3,8 @@ import json, os, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from rhasspy_speech_b200 import _lib, synth
+from rhasspy_speech_b200 import _lib
+from tools import synth
 from oracle import ref_run
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64

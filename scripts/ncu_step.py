@@ -2,7 +2,8 @@
 import os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from rhasspy_speech_b200 import _lib, synth
+from rhasspy_speech_b200 import _lib
+from tools import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 tmp = tempfile.mkdtemp()
 p = synth.write_model(tmp, synth.ZAMIA_LIKE)

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def synth():
-    from rhasspy_speech_b200 import synth as s
+    from tools import synth as s
     return s
 
 

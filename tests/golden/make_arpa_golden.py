@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import kaldi_np as K  # noqa: E402
 from oracle import ref_run  # noqa: E402
-from rhasspy_speech_b200 import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 SPEC = dataclasses.replace(synth.TINY, name="tiny_arpa", seed=11, graph="arpa", vocab_size=300, bigrams_per_word=8, eps_hops=2)
 BEAM = 16.0

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import kaldi_np as K  # noqa: E402
 from oracle import ref_run  # noqa: E402
-from rhasspy_speech_b200 import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 
 def main():

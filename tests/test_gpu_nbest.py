@@ -70,7 +70,7 @@ def test_nbest_and_lattice_match_reference_on_loglikes(tiny, tiny_model, utteran
             raw, want = ref.decode_loglikes_lattice(tiny_model.final_mdl, tiny_model.hclg, mats, nbest=5, acoustic_scale=nb_scale)
             dec.set_nbest(5, nb_scale)
             got = dec.decode_loglikes(mats)
-            assert all(s in (0, 16) for s in got.status), list(got.status)
+            assert all(int(s) & 15 == 0 for s in got.status), list(got.status)
             n_multi += _compare(got, want, len(mats), (ll_scale, nb_scale))
             # a20: the pruned lattice is the reference's raw lattice, state for state and arc for arc
             t = dec.timings()
@@ -171,10 +171,10 @@ def test_nbest_on_arpa_graph_with_epsilon_chains(lib, ref, synth, utterances, tm
         wavs.append(w)
     m, g = lib.Model(p.final_mdl, p.online_conf, 0), lib.Graph(p.hclg, p.words_txt, 0)
     assert g.num_states > 1024
-    n_lists = n_flagged = n_flagged_same = 0
-    # beam 16: fewer than --max-active tokens per frame, so nothing is order-dependent and the lists must be
-    # identical.  (With beam - lattice_beam of only a few units the reference's lattice itself depends on its hash
-    # order: tokens its transient next_cutoff let through, :780-787, can then lie inside the lattice beam.)
+    n_lists = n_flagged = 0
+    # Every list must be the reference's: beam 16 keeps fewer than --max-active tokens per frame; at beam 24 the
+    # order-sensitive utterances (status bit 4: tokens or links the reference's transient next_cutoff lets through,
+    # :780-787, could matter) come from the strict-order host decoder, lattice included.
     for beam in (24.0, 16.0):
         dec = lib.Decoder(m, g, beam=beam)
         want, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, nbest=5, beam=beam)
@@ -183,16 +183,12 @@ def test_nbest_on_arpa_graph_with_epsilon_chains(lib, ref, synth, utterances, tm
         t = dec.timings()
         assert t["lattice_arcs"] > 0 and t["lattice_links_recorded"] > 0
         for u in range(len(wavs)):
-            assert got.status[u] in (0, 16), (beam, u, got.status[u])
+            assert int(got.status[u]) & 15 == 0, (beam, u, got.status[u])
             keys = sorted((k for k in want if k.startswith("utt%05d-" % u)), key=lambda k: int(k.rsplit("-", 1)[1]))
-            same = [h[0] for h in got.nbest[u]] == [want[k] for k in keys]
-            if got.status[u] == 0:
-                assert same, (beam, u, got.nbest[u], [want[k] for k in keys])
-                n_lists += len(keys) > 1
-            else:   # 16: a binding --max-active makes the reference's token set order-dependent
-                n_flagged += 1
-                n_flagged_same += same
-    print("arpa n-best: %d unflagged lists identical, %d of %d flagged lists identical" % (n_lists, n_flagged_same, n_flagged))
+            assert [h[0] for h in got.nbest[u]] == [want[k] for k in keys], (beam, u, got.status[u], got.nbest[u], [want[k] for k in keys])
+            n_lists += len(keys) > 1
+            n_flagged += bool(got.status[u] & 16)
+    print("arpa n-best: %d lists identical, %d of them from the strict-order host decoder" % (n_lists, n_flagged))
     assert n_lists >= 2
 
 
@@ -210,13 +206,13 @@ def test_lattice_that_does_not_fit_falls_back_to_the_best_path(tiny, utterances,
     monkeypatch.setenv("RS_B200_LATTICE_MAX_MB", "16")    # ... and no growth
     small.set_nbest(4)
     got = small.decode_pcm(batch)
-    assert all(s & 32 for s in got.status) and all((s & ~48) == 0 for s in got.status), list(got.status[:8])
+    assert all(s & 32 for s in got.status) and all((s & ~(48 | 64)) == 0 for s in got.status), list(got.status[:8])
     assert list(got.n_hyp) == [1] * 64
     assert got.words == one.words
     # with room to grow, the same call re-runs the stage with a larger budget and returns the lists
     monkeypatch.delenv("RS_B200_LATTICE_MAX_MB")
     full = small.decode_pcm(batch)
-    assert all(s in (0, 16) for s in full.status) and max(full.n_hyp) > 1
+    assert all(int(s) & 15 == 0 for s in full.status) and max(full.n_hyp) > 1
     assert [h[0][0] for h in full.nbest] == one.words
     dec.set_nbest(4)
     try:

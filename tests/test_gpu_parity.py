@@ -161,7 +161,7 @@ def _check_transcripts(lib, ref, synth, p, utts, tmp, **dec_opts):
     ref_kw = {k: v for k, v in dec_opts.items() if k in ("beam", "max_active")}
     want, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, **ref_kw)
     got = dec.decode_wavs(wavs)
-    assert all(st in (0, 16) for st in got.status), list(got.status)   # 16 = informational (max-active bound)
+    assert all(int(st) & 15 == 0 for st in got.status), list(got.status)   # bits 4 / 6: order-sensitive, decoded by the host
     n_words = 0
     for u in range(len(wavs)):
         w = want.get("utt%05d-1" % u)
@@ -186,25 +186,37 @@ def test_arpa_graph_with_out_of_grammar_audio(lib, ref, synth, utterances, tmp_p
     # fewer table slots than graph states: the open-addressing (hashed) path of the state tables
     dec_h, got_h, _ = _check_transcripts(lib, ref, synth, p, utts, tmp_path, beam=9.0, max_tokens_per_frame=2048)
     assert dec_h.graph.num_states > 2 * 2048 and all(st == 0 for st in got_h.status)
-    # A binding --max-active: the cutoff VALUE is reproduced (radix select == nth_element), but the
-    # reference's token list also holds the order-dependent tokens its transient next_cutoff let through
-    # (lattice-faster-decoder.cc:780-787); they change `toks.size() > max_active` and, under the then
-    # narrow adaptive beam, the search itself.  Such utterances carry status bit 16; the contract is:
-    # unflagged => word-identical, flagged => same cutoff arithmetic, agreement measured.
+    # A binding --max-active: the reference's token list then also holds the order-dependent tokens its transient
+    # next_cutoff let through (lattice-faster-decoder.cc:780-787).  The device search detects the frames on which they
+    # could matter (status bit 4) and such utterances are decoded again by the strict-order host decoder
+    # (strict_decode.cc): EVERY utterance must carry the reference's words, at every --max-active.
     m = lib.Model(p.final_mdl, p.online_conf, 0)
     g = lib.Graph(p.hclg, p.words_txt, 0)
     wavs = _write_wavs(synth, tmp_path, utts)
     flagged = 0
     for max_active in (300, 1000, 7000):
         want, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, max_active=max_active)
-        got = lib.Decoder(m, g, max_active=max_active).decode_wavs(wavs)
+        dec_m = lib.Decoder(m, g, max_active=max_active)
+        got = dec_m.decode_wavs(wavs)
         for u in range(len(wavs)):
-            assert got.status[u] in (0, 16) and got.n_hyp[u] == 1, (max_active, u, got.status[u])
-            if got.status[u] == 0:
-                assert got.words[u] == want.get("utt%05d-1" % u), (max_active, u)
-            else:
-                flagged += 1
-    assert flagged > 0          # max_active = 300 does bind on this graph
+            assert int(got.status[u]) & 15 == 0 and got.n_hyp[u] == 1, (max_active, u, got.status[u])
+            assert got.words[u] == want.get("utt%05d-1" % u), (max_active, u, got.status[u], got.words[u], want.get("utt%05d-1" % u))
+            flagged += bool(got.status[u] & 16)
+        assert dec_m.timings()["strict_utts"] == sum(1 for s_ in got.status if s_ & 64)
+        # with the host decoder switched off the flag is still raised, and unflagged utterances are still identical
+        raw = lib.Decoder(m, g, max_active=max_active, strict_fallback=0).decode_wavs(wavs)
+        for u in range(len(wavs)):
+            assert not (raw.status[u] & 64)
+            if not (raw.status[u] & 16):
+                assert raw.words[u] == want.get("utt%05d-1" % u), (max_active, u)
+        # 5-best lists under the same limits (lattice recorded on the device, or by the strict decoder when flagged)
+        dec_m.set_nbest(5)
+        got5 = dec_m.decode_wavs(wavs)
+        want5, _, _ = ref.transcribe_wavs(p.final_mdl, p.online_conf, p.hclg, p.words_txt, wavs, nbest=5, max_active=max_active)
+        for u in range(len(wavs)):
+            w5 = [want5[k] for k in sorted(want5) if k.startswith("utt%05d-" % u)]
+            assert [h[0] for h in got5.nbest[u]] == w5, (max_active, u, got5.status[u])
+    print("order-sensitive utterances over max-active 300/1000/7000:", flagged)
 
 
 @pytest.mark.parametrize("variant", ["softmax_sf1", "text_priors_ldabias", "nnet_cmvn"])

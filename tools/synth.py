@@ -996,6 +996,23 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
     raise ValueError("no data chunk in " + path)
 
 
+def load_pool(wav_dir: Optional[str] = None) -> List[np.ndarray]:
+    """The reference's tests/en_US-zamia utterances (49 WAVs, 16 kHz mono, 1-2 s; committed under
+    tests/golden/en_US-zamia): the pool BASELINE config 2 cuts its 3-5 s utterances from (make_utterances(pool=...))."""
+    import glob
+    if wav_dir is None:
+        wav_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "en_US-zamia")
+    paths = sorted(glob.glob(os.path.join(wav_dir, "*.wav")))
+    if not paths:
+        raise FileNotFoundError("no fixture WAVs under " + wav_dir)
+    pool = []
+    for f in paths:
+        pcm, rate = read_wav(f)
+        assert rate == 16000, (f, rate)
+        pool.append(pcm)
+    return pool
+
+
 def synth_speech(seconds: float, seed: int, rate: int = 16000) -> np.ndarray:
     """Speech-like test audio: voiced harmonics with moving formants + noise bursts + pauses."""
     rng = np.random.default_rng(seed)
