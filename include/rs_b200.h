@@ -66,7 +66,10 @@ typedef struct rs_result {
                           * decoded again by the strict-order host decoder and the result returned is the reference's;
                           * with strict_fallback == 0 it is the device result, not guaranteed word-identical;
                           * bit5 (32) n-best requested but the lattice did not fit its device buffers: only the best path
-                          * is returned; bit6 (64) the result comes from the strict-order host decoder */
+                          * is returned; bit6 (64) the result comes from the strict-order host decoder; bits 8-11: which safe-frame
+                          * rule raised bit 4 (min-active count, max-active count, extra inside the cutoff, last frame) and
+                          * bit 12 (4096): a forward link only some visiting orders create would have survived the lattice
+                          * pruning -- diagnostics */
   /* every hypothesis, best first (what lattice-to-nbest | nbest-to-linear print as utt-1 .. utt-n and the two
    * cost archives of nbest-to-linear): hypothesis h of utterance u is entry hyp_offset[u] + h */
   int32_t *hyp_offset;       /* [n_utts + 1] */

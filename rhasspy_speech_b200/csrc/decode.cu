@@ -618,9 +618,9 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           adaptive_beam = __fadd_rn(__fsub_rn(max_active_cutoff, best), cfg.beam_delta);
           cur_cutoff = max_active_cutoff;
         } else {
-          if (n_extra > 0 && (n_cur <= cfg.min_active ||
-                              (n_cur <= cfg.max_active && n_cur + n_extra > cfg.max_active && min_extra < beam_cutoff)))
-            info |= 16;
+          // (bits 8-11 say which rule fired: diagnostic detail of bit 4)
+          if (n_extra > 0 && n_cur <= cfg.min_active) info |= 16 | 256;
+          if (n_extra > 0 && n_cur <= cfg.max_active && n_cur + n_extra > cfg.max_active && min_extra < beam_cutoff) info |= 16 | 512;
           if (n_cur > cfg.min_active) {
             if (cfg.min_active == 0) {
               min_active_cutoff = best;
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
           }
         }
       }
-      if (n_extra > 0 && min_extra <= cur_cutoff) info |= 16;
+      if (n_extra > 0 && min_extra <= cur_cutoff) info |= 16 | 1024;
       tick(0);
       // ---- ProcessEmitting (:714-804)
       const float cost_offset = -best;
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(kMaxNT, 2) decode_kernel(const __grid_constant
       // as cheap as the best final token (n-best: inside the lattice beam of it) -- or final when no kept token is
       if (S.min_extra_final_ord != 0xffffffffu &&
           (!anyf || unord(S.min_extra_final_ord) <= __fadd_rn(S.best_cost, kLat ? cfg.lattice_beam : 0.f)))
-        info |= 16;
+        info |= 16 | 2048;
       if (S.best_idx == 0x7fffffff) {
         status |= 4;
       } else if (tid == 0) {

@@ -1126,10 +1126,13 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     for (int u = 0; u < n; u++)
       if (d->batch.n_out[u] > 0 && !(status[u] & 7) &&
           (o.strict_fallback == 2 || (status[u] & 16) || (lattice && hdr[u].ok && hdr[u].pad[0]))) {
-        r->status[u] |= 16;
+        r->status[u] |= 16 | ((lattice && hdr[u].ok && hdr[u].pad[0]) ? 4096 : 0);
         strict_list.push_back(u);
       }
   }
+  if (!o.strict_fallback && lattice)
+    for (int u = 0; u < n; u++)
+      if (hdr[u].ok && hdr[u].pad[0]) r->status[u] |= 16 | 4096;
   if (!strict_list.empty()) {
     const auto t0 = std::chrono::steady_clock::now();
     const int ns = (int)strict_list.size();

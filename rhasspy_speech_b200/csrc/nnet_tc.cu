@@ -158,6 +158,12 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
 // up to two K blocks ahead, also across the tile boundary while the epilogue warps run the bias /
 // ReLU / BatchNorm / bypass / split-store tail of the previous tile.
 constexpr int kStageABytes = kTcBM * 128;  // one plane of the activation tile: 128 rows x 128 B
+// main MMAs (K = 16 each) accumulated inside TMEM before the epilogue warps fold the sum in registers: 4 = one fold per
+// 64-wide K block, 1 = every MMA starts from zero (no in-TMEM accumulation of the main term at all)
+// Measured on the bench model (scripts/debug_ll.py, log-likelihoods against an fp64 forward; the reference's own
+// nnet3-compute is 8e-6 rms / 7e-5 max away from it): 4 -> 1.5e-5 rms / 1.4e-4 max (the truncation inside TMEM is biased
+// towards zero and the bias adds up coherently over the layers), 2 -> 9e-6 / 7e-5, 1 -> 7e-6 / 5e-5.
+constexpr int kTcFold = 2;
 
 // 12 warps = 3 per SM sub-partition (16 K registers each): 168 registers per thread at launch, then
 // re-allocated by setmaxnreg to 40 (TMA / MMA warpgroup) and 232 (epilogue warpgroups)
@@ -265,30 +271,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; physical main set = kbc & 1
       uint32_t use_par = 0;         // bit b: parity of the number of blocks committed on barrier pair b = group * 2 + set
       int last_b[2] = {-1, -1};     // barrier pair of the block that last occupied each physical set
+      constexpr int fold = kTcFold;
       uint32_t tcount = 0;  // tiles issued so far: cross accumulator = tcount & 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
         const uint32_t d_cross = tmem_base + (uint32_t)((2 + (tcount & 1)) * p.bn);
         mbar_wait(crosse_bar(tcount & 1), ((tcount >> 1) & 1u) ^ 1u);
-        for (int kb = 0; kb < total_kb; kb++, kbc++) {
-          const int set = kbc & 1, bsel = (int)(tcount & 1) * 2 + set;
-          if (last_b[set] >= 0) mbar_wait(sete_bar(last_b[set]), ((use_par >> last_b[set]) & 1u) ^ 1u);  // set drained
+        for (int kb = 0; kb < total_kb; kb++) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t d_main = tmem_base + (uint32_t)(set * p.bn);
           const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
           const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kStageABytes);
           const uint64_t b_hi = smem_desc_sw128(sa + 2 * kStageABytes), b_lo = smem_desc_sw128(sa + 2 * kStageABytes + b_bytes);
+          // fold main MMAs (16 K each) share one fresh accumulator; with fold = 1 every MMA starts from zero and the
+          // epilogue warps do ALL the accumulation in fp32 registers with round-to-nearest
 #pragma unroll
           for (int k = 0; k < kTcBK / 16; k++) {  // 16 fp16 = 32 bytes per step inside the swizzle atom
+            const int set = kbc & 1, bsel = (int)(tcount & 1) * 2 + set;
+            if (k % fold == 0 && last_b[set] >= 0)
+              mbar_wait(sete_bar(last_b[set]), ((use_par >> last_b[set]) & 1u) ^ 1u);  // set drained
+            const uint32_t d_main = tmem_base + (uint32_t)(set * p.bn);
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k != 0 ? 1u : 0u);
+            tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k % fold != 0 ? 1u : 0u);
             tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
             tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+            if (k == kTcBK / 16 - 1) tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+            if (k % fold == fold - 1) {
+              tc_commit(setf_bar(bsel));  // this partial sum (and, on the last one, the cross sum) complete
+              use_par ^= 1u << bsel;
+              last_b[set] = bsel;
+              kbc++;
+            }
           }
-          tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
-          tc_commit(setf_bar(bsel));    // this block's main sum (and, on the last block, the cross sum) complete
-          use_par ^= 1u << bsel;
-          last_b[set] = bsel;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -316,7 +329,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       if (p.ops[i].type == EpiOp::kAddScaled && p.ops[i].buf_lo) ib = i;
     for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, tcount += 2) {
       const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
-      uint32_t kbc = tcount * (uint32_t)total_kb;
+      const int total_sums = total_kb * (kTcBK / 16 / kTcFold);  // partial sums the issuer publishes per tile
+      uint32_t kbc = tcount * (uint32_t)total_sums;
       // bypass input of one 32-column chunk: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B
       // cover a row segment, 8 rows per instruction; issued early so that HBM latency is hidden
       uint4 pf_h[4], pf_l[4];
@@ -363,8 +377,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       float acc[kTcMaxBN];
 #pragma unroll
       for (int j = 0; j < kTcMaxBN; j++) acc[j] = kBiasFirst ? __shfl_sync(0xffffffffu, vr0[0][j >> 5], j & 31) : 0.f;
-      for (int kb = 0; kb < total_kb; kb++, kbc++) {
-        if (kb == total_kb - 1 && ib >= 0) prefetch(0);
+      for (int kb = 0; kb < total_sums; kb++, kbc++) {
+        if (kb == total_sums - 1 && ib >= 0) prefetch(0);
         const int set = kbc & 1, bsel = group * 2 + set;
         mbar_wait(setf_bar(bsel), (cnt_par >> set) & 1u);
         cnt_par ^= 1u << set;

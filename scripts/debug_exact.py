@@ -44,6 +44,23 @@ def compare(name, spec, n, **opts):
                     if bad <= 3:
                         print("  MISMATCH utt", u, "status", a.status[u], a.words[u], b.words[u], a.graph_cost[u], b.graph_cost[u],
                               a.acoustic_cost[u], b.acoustic_cost[u], (dev.fetch(5, u).shape, host.fetch(5, u).shape) if nb > 1 else "")
+        import collections
+        rules = collections.Counter()
+        for st in a.status:
+            for bit, nm in ((256, "min-active"), (512, "max-active count"), (1024, "extra in cutoff"), (2048, "last frame"), (4096, "maybe link")):
+                rules[nm] += bool(st & bit)
+        print("  rules:", dict(rules))
+        if nb > 1 and bad:
+            for u in range(n):
+                if a.status[u] & 16:
+                    continue
+                la, lb = dev.fetch(5, u), host.fetch(5, u)
+                if la.shape == lb.shape:
+                    continue
+                key = lambda A: collections.Counter((int(r[1] < 0), int(r[2]), round(float(r[3]), 3), round(float(r[4]), 2)) for r in A)
+                d1, d2 = key(lb) - key(la), key(la) - key(lb)
+                print("  utt", u, "frames", a.num_frames[u], "host-only arcs:", list(d1.items())[:12], "| device-only:", list(d2.items())[:6])
+                break
         print("%s nbest=%d: %d utts, %d flagged (%d of them differ), UNFLAGGED MISMATCHES %d | device decode %.2f ms wall %.1f ms | strict %d utts %.1f ms | tok/frame %.0f"
               % (name, nb, n, flagged, bad_flagged, bad, td["decode_ms"], ta * 1e3, th["strict_utts"], th["strict_ms"],
                  td["tokens_expanded"] / max(1, td["frames_decoded"])), flush=True)

@@ -185,7 +185,7 @@ def test_arpa_graph_with_out_of_grammar_audio(lib, ref, synth, utterances, tmp_p
     _check_transcripts(lib, ref, synth, p, utts, tmp_path, beam=12.0)
     # fewer table slots than graph states: the open-addressing (hashed) path of the state tables
     dec_h, got_h, _ = _check_transcripts(lib, ref, synth, p, utts, tmp_path, beam=9.0, max_tokens_per_frame=2048)
-    assert dec_h.graph.num_states > 2 * 2048 and all(st == 0 for st in got_h.status)
+    assert dec_h.graph.num_states > 2 * 2048 and all(int(st) & 15 == 0 for st in got_h.status)
     # A binding --max-active: the reference's token list then also holds the order-dependent tokens its transient
     # next_cutoff let through (lattice-faster-decoder.cc:780-787).  The device search detects the frames on which they
     # could matter (status bit 4) and such utterances are decoded again by the strict-order host decoder
