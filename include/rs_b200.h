@@ -171,7 +171,8 @@ int rs_decoder_timings(const rs_decoder *d, rs_timings *t);
  * what = 0 MFCC [T x dim], 1 iVector [solves x dim] (1 row offline, one per CG solve online), 2 log-likelihoods [T/sf x num_pdfs],
  *        3 CMVN-normalised MFCC, 4 LDA features (normalised stream),
  *        5 (after an n-best call) the pruned state-level lattice: rows of (src, dst, olabel, graph cost, acoustic cost),
- *          dst = -1 marks a final weight, state 0 is the start.
+ *          dst = -1 marks a final weight, state 0 is the start;
+ *        6 UBM posteriors (rows a9 / a10): per frame num_gselect pairs (gaussian index, weight), unused pairs (-1, 0).
  * Call with dst == NULL to query rows/cols. */
 int rs_debug_fetch(rs_decoder *d, int32_t what, int32_t utt, float *dst, int32_t *rows, int32_t *cols, char *err,
                    size_t errlen);
@@ -192,6 +193,10 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
 int rs_debug_lattice_nbest(const int32_t *src, const int32_t *dst, const int32_t *olabel, const float *graph,
                            const float *acoustic, int32_t n_arcs, int32_t n_nodes, int32_t n, float acoustic_scale,
                            int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost);
+/* Test hook for the Kaldi object reader (host only): a Matrix<float> file as Matrix::Read accepts it -- binary FM / DM,
+ * CompressedMatrix CM / CM2 / CM3 (kaldi/src/matrix/kaldi-matrix.cc:1475-1513, compressed-matrix.cc:565-660), or text.
+ * Call with dst == NULL to query the shape, then with *rows / *cols set to it. */
+int rs_debug_read_matrix(const char *path, float *dst, int32_t *rows, int32_t *cols, char *err, size_t errlen);
 /* Test hook for the strict-order host decoder (csrc/strict_decode.cc; host only, no GPU): what latgen-faster-mapped
  * (kaldi/src/bin/latgen-faster-mapped.cc) | lattice-to-nbest --n=nbest --acoustic-scale | nbest-to-linear print for
  * one log-likelihood matrix [n_frames x num_pdfs], with the reference's order-dependent pruning reproduced

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("rs_decoder_set_graph", C.c_int, [_P, _P] + _ERR),
     ("rs_decoder_set_nbest", C.c_int, [_P, C.c_int32, C.c_float] + _ERR),
     ("rs_debug_lattice_nbest", C.c_int, [_P] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, _P]),
+    ("rs_debug_read_matrix", C.c_int, [C.c_char_p, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + _ERR),
     ("rs_debug_strict_decode", C.c_int, [C.c_char_p, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(DecoderOpts), C.c_int32,
                                         C.c_float, _P, _P, C.c_int32, _P, _P] + _ERR),
     ("rs_decode_pcm", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.POINTER(Result))] + _ERR),
@@ -175,6 +176,18 @@ def lattice_nbest(src, dst, olabel, graph, acoustic, n_nodes: int, n: int, acous
     if k < 0:
         raise RsError("rs_debug_lattice_nbest failed (%d)" % k)
     return [([int(x) for x in wid[woff[h]:woff[h + 1]]], float(cost[2 * h]), float(cost[2 * h + 1])) for h in range(k)]
+
+
+def read_matrix(path: str) -> np.ndarray:
+    """A Kaldi Matrix<float> file (FM / DM / CM / CM2 / CM3 / text) through the library's reader (rs_debug_read_matrix)."""
+    lib = load_library()
+    r, c = C.c_int32(), C.c_int32()
+    err = C.create_string_buffer(ERRLEN)
+    _check(lib.rs_debug_read_matrix(os.fsencode(path), None, C.byref(r), C.byref(c), err, ERRLEN) == 0, err)
+    out = np.zeros((r.value, c.value), np.float32)
+    if out.size:
+        _check(lib.rs_debug_read_matrix(os.fsencode(path), out.ctypes.data, C.byref(r), C.byref(c), err, ERRLEN) == 0, err)
+    return out
 
 
 def strict_decode(hclg_fst: str, tid2pdf: np.ndarray, loglikes: np.ndarray, nbest: int = 1, acoustic_scale: float = 1.0, **opts):
@@ -478,6 +491,8 @@ class Decoder:
 
     def finish_streams(self, streams: Sequence["Stream"]) -> Hypotheses:
         n = len(streams)
+        if any(not getattr(s, "h", None) for s in streams):
+            raise RsError("finish_streams: a stream of the batch is closed")
         arr = (C.c_void_p * max(n, 1))(*[s.h for s in streams])
         res = C.POINTER(Result)()
         err = C.create_string_buffer(ERRLEN)

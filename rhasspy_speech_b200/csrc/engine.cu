@@ -16,6 +16,7 @@
 
 #include "../../include/rs_b200.h"
 #include "engine.h"
+#include "kaldi_io.h"
 #include "model.h"
 #include "nnet_tc.h"
 #include "nbest.h"
@@ -1942,6 +1943,8 @@ int rs_streams_finish(rs_stream *const *streams, int32_t n, rs_result **out, cha
     *out = NewResult(0);
     return 0;
   }
+  for (int i = 0; i < n; i++)
+    if (!streams[i]) RS_FAIL("rs_streams_finish: stream " << i << " is NULL (closed?)");
   DecoderImpl *d = reinterpret_cast<StreamImpl *>(streams[0])->dec;
   std::vector<const int16_t *> ptrs(n);
   std::vector<int32_t> ns(n);
@@ -2146,6 +2149,21 @@ int rs_debug_gemm(int device, const float *src, int rows, int k, const int *offs
   API_GUARD_END(1)
 }
 
+int rs_debug_read_matrix(const char *path, float *dst, int32_t *rows, int32_t *cols, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  if (!path || !rows || !cols) RS_FAIL("rs_debug_read_matrix: bad argument");
+  KaldiReader r(path);
+  MatrixF m = r.ReadMatrixF();
+  if (dst) {
+    if (*rows != m.rows || *cols != m.cols) RS_FAIL("rs_debug_read_matrix: destination is " << *rows << " x " << *cols << ", matrix " << m.rows << " x " << m.cols);
+    std::copy(m.d.begin(), m.d.end(), dst);
+  }
+  *rows = m.rows;
+  *cols = m.cols;
+  return 0;
+  API_GUARD_END(1)
+}
+
 int rs_debug_strict_decode(const char *hclg_fst, const int32_t *tid2pdf, int32_t n_tids, const float *loglikes,
                            int32_t n_frames, int32_t num_pdfs, const rs_decoder_opts *opts, int32_t nbest, float acoustic_scale,
                            int32_t *word_offset, int32_t *word_ids, int32_t max_words, float *cost, int32_t *lattice_size,
@@ -2241,6 +2259,24 @@ int rs_debug_fetch(rs_decoder *d_, int32_t what, int32_t utt, float *dst, int32_
       for (int i = 0; i < h.n_arcs; i++) {
         float *o = dst + (size_t)i * 5;
         o[0] = (float)a[i].src, o[1] = (float)a[i].dst, o[2] = (float)a[i].olabel, o[3] = a[i].graph, o[4] = a[i].acoustic;
+      }
+    }
+    return 0;
+  }
+  if (what == 6) {
+    // a9 / a10: the UBM posteriors of the last call, rows of (gaussian, weight) x num_gselect, unused entries (-1, 0)
+    if (B.from_loglikes || !m.has_ivector || !d->d_post_idx.p) RS_FAIL("rs_debug_fetch: the last call computed no posteriors");
+    const int S = m.ivec.num_gselect, T = B.num_frames[utt];
+    if (rows) *rows = T;
+    if (cols) *cols = 2 * S;
+    if (dst && T > 0) {
+      std::vector<int> idx((size_t)T * S);
+      std::vector<float> w((size_t)T * S);
+      CUDA_OK(cudaMemcpy(idx.data(), d->d_post_idx.as<int>() + (size_t)B.frame_offset[utt] * S, idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(w.data(), d->d_post_w.as<float>() + (size_t)B.frame_offset[utt] * S, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < idx.size(); i++) {
+        dst[2 * i] = (float)idx[i];
+        dst[2 * i + 1] = idx[i] >= 0 ? w[i] : 0.f;
       }
     }
     return 0;

@@ -213,8 +213,8 @@ class KaldiReader {
     MatrixD m;
     if (binary_) {
       std::string t = ReadToken();
-      if (t != "FM" && t != "DM")
-        RS_FAIL(path_ << ": expected FM/DM matrix header, got " << t << " (compressed matrices are not supported)");
+      if (t == "CM" || t == "CM2" || t == "CM3") return ReadCompressed(t);
+      if (t != "FM" && t != "DM") RS_FAIL(path_ << ": expected FM/DM/CM matrix header, got " << t);
       m.rows = ReadInt32();
       m.cols = ReadInt32();
       size_t n = (size_t)m.rows * m.cols;
@@ -251,6 +251,58 @@ class KaldiReader {
         row.push_back(TextFloat<double>());
       }
       m.cols = cols < 0 ? 0 : cols;
+    }
+    return m;
+  }
+  // CompressedMatrix (kaldi/src/matrix/compressed-matrix.cc:565-660, read through Matrix::Read,
+  // kaldi-matrix.cc:1475-1513): global header {min, range, rows, cols} without the format word, then
+  //   CM  : per-column header of four uint16 percentiles, then one byte per element, column-major;
+  //   CM2 : uint16 per element, row-major;   CM3 : uint8 per element, row-major.
+  // Expanded with the reference's float expressions (CopyToMat :600-660, CharToFloat :490-500).
+  MatrixD ReadCompressed(const std::string &tok) {
+    MatrixD m;
+    float min_value, range;
+    int32_t rows, cols;
+    Raw(&min_value, 4);
+    Raw(&range, 4);
+    Raw(&rows, 4);
+    Raw(&cols, 4);
+    if (rows < 0 || cols < 0) RS_FAIL(path_ << ": bad compressed-matrix header");
+    m.rows = rows;
+    m.cols = cols;
+    if (cols == 0) {
+      m.rows = 0;
+      return m;
+    }
+    const size_t n = (size_t)rows * cols;
+    m.d.resize(n);
+    if (tok == "CM") {
+      std::vector<uint16_t> hdr((size_t)cols * 4);
+      Raw(hdr.data(), hdr.size() * 2);
+      std::vector<uint8_t> bytes(n);
+      Raw(bytes.data(), n);
+      auto u16 = [&](uint16_t v) { return min_value + range * 1.52590218966964e-05F * v; };
+      for (int c = 0; c < cols; c++) {
+        const float p0 = u16(hdr[4 * c]), p25 = u16(hdr[4 * c + 1]), p75 = u16(hdr[4 * c + 2]), p100 = u16(hdr[4 * c + 3]);
+        for (int r = 0; r < rows; r++) {
+          const uint8_t v = bytes[(size_t)c * rows + r];
+          float f;
+          if (v <= 64) f = p0 + (p25 - p0) * v * (1 / 64.0);
+          else if (v <= 192) f = p25 + (p75 - p25) * (v - 64) * (1 / 128.0);
+          else f = p75 + (p100 - p75) * (v - 192) * (1 / 63.0);
+          m.d[(size_t)r * cols + c] = f;
+        }
+      }
+    } else if (tok == "CM2") {
+      std::vector<uint16_t> data(n);
+      Raw(data.data(), n * 2);
+      const float increment = range * (1.0 / 65535.0);
+      for (size_t i = 0; i < n; i++) m.d[i] = min_value + data[i] * increment;
+    } else {
+      std::vector<uint8_t> data(n);
+      Raw(data.data(), n);
+      const float increment = range * (1.0 / 255.0);
+      for (size_t i = 0; i < n; i++) m.d[i] = min_value + data[i] * increment;
     }
     return m;
   }

@@ -24,6 +24,7 @@ import base64
 import collections
 import concurrent.futures
 import json
+import logging
 import os
 import re
 import threading
@@ -60,6 +61,25 @@ def decode_meta(text: str) -> str:
     if match is None:
         return text
     return decode_meta_single(match.group(1)).format(**slots)
+
+
+STATUS_ERRORS = ((1, "more tokens on one frame than max_tokens_per_frame"),
+                 (2, "more tokens in the utterance than the traceback arena holds (max_tokens_per_utt)"),
+                 (8, "more words in the transcript than max_words"))
+_log = logging.getLogger(__name__)
+
+
+def check_status(status: int, command: str):
+    """rs_result.status of one utterance: capacity errors (bits 0, 1, 3) would otherwise show up as an empty or truncated
+    transcript where the reference produces one; they are raised like a failing Kaldi binary (tools.py:81-88).  Bit 2 (no
+    surviving tokens) is the reference's empty lattice: no hypothesis, not an error.  Bits 4-6 are information."""
+    for bit, what in STATUS_ERRORS:
+        if status & bit:
+            raise RuntimeError("Unexpected error running command %s: decoder capacity exceeded: %s" % (command, what))
+    if status & 32:
+        _log.warning("n-best requested but the lattice did not fit its device buffers (RS_B200_LATTICE_MAX_MB): best path only")
+    if status & 64:
+        _log.debug("utterance was order-sensitive on the device and was decoded by the strict-order host decoder")
 
 
 class _OneHyp:
@@ -135,26 +155,62 @@ class _Batcher:
             hyp.graph = getattr(self.decoder, "graph", None)
             return hyp
 
+    @staticmethod
+    def _deliver(fut: "concurrent.futures.Future", result=None, error: Optional[BaseException] = None):
+        """Resolve one request's future; a future that was cancelled meanwhile (asyncio.wait_for timeout, client gone)
+        must not take the worker thread -- and with it every other caller of the engine -- down."""
+        try:
+            if error is not None:
+                fut.set_exception(error)
+            else:
+                fut.set_result(result)
+        except concurrent.futures.InvalidStateError:
+            pass
+
+    def _release(self, kind: str, payload):
+        """The batcher owns a stream handle from submit() on: it is closed here, after the decode (or when the request was
+        cancelled before it ran), never by the awaiting coroutine -- so a cancelled caller cannot free audio in flight."""
+        if kind == "stream":
+            try:
+                payload.close()
+            except Exception:  # noqa: BLE001
+                pass
+
     def _run(self):
         while True:
             batch = self._take()
             if batch is None:
                 return
+            # a request whose caller was cancelled while it was queued is dropped here (set_running_or_notify_cancel
+            # returns False), the others are marked running and can no longer be cancelled under the decode
+            live = []
+            for b in batch:
+                if b[4].set_running_or_notify_cancel():
+                    live.append(b)
+                else:
+                    self._release(b[0], b[1])
+            batch = live
+            if not batch:
+                continue
             kind, _, nbest, scale, _ = batch[0]
             try:
-                hyp = self._decode(kind, [b[1] for b in batch], nbest, scale)
-                for u, b in enumerate(batch):
-                    b[4].set_result(_OneHyp(hyp, u, hyp.graph))
-            except Exception as first:  # noqa: BLE001 -- delivered to the caller(s) below
-                if len(batch) == 1:
-                    batch[0][4].set_exception(first)
-                    continue
-                for b in batch:             # isolate the offending request
-                    try:
-                        one = self._decode(kind, [b[1]], nbest, scale)
-                        b[4].set_result(_OneHyp(one, 0, one.graph))
-                    except Exception as e:  # noqa: BLE001
-                        b[4].set_exception(e)
+                try:
+                    hyp = self._decode(kind, [b[1] for b in batch], nbest, scale)
+                    for u, b in enumerate(batch):
+                        self._deliver(b[4], _OneHyp(hyp, u, hyp.graph))
+                except Exception as first:  # noqa: BLE001 -- delivered to the caller(s) below
+                    if len(batch) == 1:
+                        self._deliver(batch[0][4], error=first)
+                        continue
+                    for b in batch:             # isolate the offending request
+                        try:
+                            one = self._decode(kind, [b[1]], nbest, scale)
+                            self._deliver(b[4], _OneHyp(one, 0, one.graph))
+                        except Exception as e:  # noqa: BLE001
+                            self._deliver(b[4], error=e)
+            finally:
+                for b in batch:
+                    self._release(b[0], b[1])
 
 
 class _Engine:
@@ -216,11 +272,17 @@ def _file_sig(paths) -> Tuple:
     return tuple(out)
 
 
+_KEY_LOCKS: Dict[Tuple, threading.Lock] = {}
+
+
 def _engine(final_mdl: Path, online_conf: Path, graph_dir: Path, device: int, max_active: int, beam: float,
             lattice_beam: float) -> _Engine:
     key = (str(final_mdl), str(online_conf), str(graph_dir), device, max_active, float(beam), float(lattice_beam))
-    with _ENGINES_LOCK:
-        eng = _ENGINES.get(key)
+    with _ENGINES_LOCK:                 # held only for the dictionary lookups: loading one engine must not block the others
+        key_lock = _KEY_LOCKS.setdefault(key, threading.Lock())
+    with key_lock:
+        with _ENGINES_LOCK:
+            eng = _ENGINES.get(key)
         if eng is not None and eng.model_sig != _file_sig((final_mdl, online_conf)):
             eng = None                  # a new acoustic model: rebuild the engine (the old one is garbage-collected)
         if eng is not None:
@@ -231,7 +293,8 @@ def _engine(final_mdl: Path, online_conf: Path, graph_dir: Path, device: int, ma
                               max_active=max_active, beam=beam, lattice_beam=lattice_beam)
             except _lib.RsError as e:
                 raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
-            _ENGINES[key] = eng
+            with _ENGINES_LOCK:
+                _ENGINES[key] = eng
         return eng
 
 
@@ -312,14 +375,21 @@ class _Base:
         final_mdl, online_conf = self._paths()
         return _engine(final_mdl, online_conf, self.graph_dir, self.device, self.max_active, self.beam, self.lattice_beam)
 
+    async def _get_engine_async(self) -> _Engine:
+        """Engine lookup from a coroutine: the first call loads the model and the graph (disk reads, H2D upload), a later
+        one may re-bind a retrained graph -- both in a worker thread, so the event loop keeps serving the other requests."""
+        return await asyncio.get_running_loop().run_in_executor(None, self._get_engine)
+
     async def _submit(self, eng: _Engine, kind: str, payload, nbest: int, command: str):
         """One request through the engine's dynamic batcher; concurrent callers share a device batch."""
         if nbest < 1:
             raise RuntimeError("Unexpected error running command lattice-to-nbest: --n must be >= 1")
         try:
-            return await asyncio.wrap_future(eng.batcher.submit(kind, payload, nbest, self.acoustic_scale))
+            hyp = await asyncio.wrap_future(eng.batcher.submit(kind, payload, nbest, self.acoustic_scale))
         except _lib.RsError as e:
             raise RuntimeError("Unexpected error running command %s: %s" % (command, e)) from e
+        check_status(hyp.status[0], command)
+        return hyp
 
     def _set_nbest(self, eng: _Engine, nbest: int):
         """`lattice-to-nbest --n=<nbest> --acoustic-scale=<acoustic_scale>` (transcribe_wav.py:62-67); call with
@@ -350,7 +420,7 @@ class _Base:
 class KaldiNnet3WavTranscriber(_Base):
     async def async_transcribe(self, wav_path, lang_dir, nbest: int = 1, max_fuzzy_cost: Optional[float] = None,
                                require_fuzzy: bool = False) -> List[str]:
-        eng = self._get_engine()
+        eng = await self._get_engine_async()
         hyp = await self._submit(eng, "wav", wav_path, nbest, "online2-wav-nnet3-latgen-faster")
         return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy, hyp.graph)
 
@@ -358,7 +428,7 @@ class KaldiNnet3WavTranscriber(_Base):
                                     max_fuzzy_cost: Optional[float] = None,
                                     require_fuzzy: bool = False) -> List[List[str]]:
         """Batched extension: one GPU batch for all files; element i equals async_transcribe(wav_paths[i])."""
-        eng = self._get_engine()
+        eng = await self._get_engine_async()
         loop = asyncio.get_running_loop()
 
         def run():
@@ -369,6 +439,8 @@ class KaldiNnet3WavTranscriber(_Base):
                 except _lib.RsError as e:
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
         hyp, graph = await loop.run_in_executor(None, run)
+        for u in range(len(wav_paths)):
+            check_status(int(hyp.status[u]), "online2-wav-nnet3-latgen-faster")
         return [await self._finish(eng, nbest_text(hyp, u), lang_dir, max_fuzzy_cost, require_fuzzy, graph)
                 for u in range(len(wav_paths))]
 
@@ -380,7 +452,7 @@ class KaldiNnet3StreamTranscriber(_Base):
     async def async_transcribe(self, audio_stream: AsyncIterable[Optional[bytes]], lang_dir, nbest: int = 1,
                                max_fuzzy_cost: Optional[float] = None, require_fuzzy: bool = False) -> List[str]:
         """audio_stream yields raw 16 kHz mono s16le chunks of any size (reference transcribe_stream.py:38-82)."""
-        eng = self._get_engine()
+        eng = await self._get_engine_async()
         stream = eng.decoder.open_stream()
         try:
             pending = b""
@@ -395,9 +467,12 @@ class KaldiNnet3StreamTranscriber(_Base):
                 pending = data[keep:]
                 if keep:
                     stream.accept(data[:keep])
-            hyp = await self._submit(eng, "stream", stream, nbest, "online2-cli-nnet3-decode-faster")
-        finally:
-            stream.close()
+        except BaseException:
+            stream.close()                          # not submitted yet: still ours
+            raise
+        # from here on the batcher owns the stream handle and closes it after the decode, also when this coroutine is
+        # cancelled while the request is queued or in flight (a close here could free audio the GPU batch is reading)
+        hyp = await self._submit(eng, "stream", stream, nbest, "online2-cli-nnet3-decode-faster")
         return await self._finish(eng, nbest_text(hyp, 0), lang_dir, max_fuzzy_cost, require_fuzzy, hyp.graph)
 
     async def async_transcribe_rescore(self, *args, **kwargs):
@@ -430,6 +505,7 @@ class KaldiTranscriber:
                 hyp = eng.decoder.decode_wavs([str(wav_path)])
             except _lib.RsError as e:
                 raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
+        check_status(int(hyp.status[0]), "online2-wav-nnet3-latgen-faster")
         return self._text(eng, hyp, 0)
 
     def transcribe_wavs(self, wav_paths: Sequence) -> List[str]:
@@ -437,6 +513,8 @@ class KaldiTranscriber:
         with eng.lock:
             eng.decoder.set_nbest(1, 1.0)
             hyp = eng.decoder.decode_wavs([str(p) for p in wav_paths])
+        for u in range(len(wav_paths)):
+            check_status(int(hyp.status[u]), "online2-wav-nnet3-latgen-faster")
         return [self._text(eng, hyp, u) for u in range(len(wav_paths))]
 
     def transcribe_stream(self, chunks: Iterable[bytes]) -> str:
@@ -460,4 +538,5 @@ class KaldiTranscriber:
                 hyp = stream.finish()
         finally:
             stream.close()
+        check_status(int(hyp.status[0]), "online2-cli-nnet3-decode-faster")
         return self._text(eng, hyp, 0)

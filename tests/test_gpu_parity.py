@@ -76,6 +76,33 @@ def test_ivector_matches_oracle(tiny, tiny_model, utterances):
         assert np.abs(dec.fetch(4, u) - lda).max() <= 2e-4
 
 
+def test_ubm_posteriors_match_oracle(tiny, tiny_model, utterances):
+    """Rows a9 / a10 directly: DiagGmm::LogLikelihoods + VectorToPosteriorEntry (top num_gselect above min_post,
+    renormalised, x posterior_scale) on the device against the restatement (itself pinned to ivector-extract-online2):
+    the same Gaussians in the same order, weights to 1e-5."""
+    from oracle import kaldi_np as K
+    _, _, dec = tiny
+    dec.decode_pcm(utterances)
+    conf = os.path.join(tiny_model.model_dir, "model", "online", "conf")
+    s = K.IvectorSetup.from_conf(os.path.join(conf, "ivector_extractor.conf"))
+    n_frames = n_pruned = 0
+    for u in range(len(utterances)):
+        xn = dec.fetch(4, u)                       # the device's own LDA features (normalised stream)
+        want = K.gmm_posteriors(s, xn)
+        got = dec.fetch(6, u)
+        assert got.shape == (len(want), 2 * s.num_gselect)
+        for t, row in enumerate(want):
+            idx = [int(x) for x in got[t, 0::2] if x >= 0]
+            # two Gaussians whose posteriors differ in the last bit may swap places; compare as sets + weights by index
+            assert sorted(idx) == sorted(g for g, _ in row), (u, t, idx, row)
+            w = {int(g): float(x) for g, x in zip(got[t, 0::2], got[t, 1::2]) if g >= 0}
+            for g, x in row:
+                assert abs(w[g] - float(x)) <= 1e-5, (u, t, g, w[g], x)
+            n_pruned += len(row) < s.num_gselect
+        n_frames += len(want)
+    assert n_frames > 500 and n_pruned > 0          # the min_post pruning was exercised
+
+
 def test_loglikes_match_reference(tiny, tiny_model, utterances, ref, synth):
     _, _, dec = tiny
     dec.decode_pcm(utterances)

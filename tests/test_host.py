@@ -228,3 +228,112 @@ def test_transcriber_flow_with_a_fake_engine(tmp_path, monkeypatch):
         asyncio.run(tr.async_transcribe("a.wav", tmp_path, nbest=0))
     with pytest.raises(NotImplementedError):
         asyncio.run(tr.async_transcribe_rescore("a.wav", tmp_path, tmp_path))
+
+
+def test_cancelled_requests_do_not_kill_the_batcher(tmp_path):
+    """A caller that gives up (asyncio.wait_for timeout, client disconnect) cancels its future while the request is queued
+    or running.  The worker thread must survive, the co-batched callers must still get their results, and a stream handle
+    is closed by the batcher -- after the decode, never under it."""
+    import asyncio
+    import threading
+    import time
+    from types import SimpleNamespace
+    from rhasspy_speech_b200 import transcribe as T
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name, self.closed_at = name, None
+
+        def accept(self, chunk):
+            pass
+
+        def close(self):
+            self.closed_at = time.monotonic()
+
+    class FakeDecoder:
+        def __init__(self):
+            self.gate = threading.Event()
+            self.calls = []
+            self.done_at = None
+
+        def set_nbest(self, n, scale):
+            pass
+
+        def finish_streams(self, streams):
+            self.gate.wait(5)
+            assert all(s.closed_at is None for s in streams)      # nobody freed a stream that is being decoded
+            self.calls.append([s.name for s in streams])
+            self.done_at = time.monotonic()
+            n = len(streams)
+            return SimpleNamespace(words=[[len(s.name)] for s in streams], nbest=[[([len(s.name)], 0.0, 0.0)] for s in streams],
+                                   status=[0] * n, n_hyp=[1] * n)
+
+    dec = FakeDecoder()
+    b = T._Batcher(dec, threading.Lock())
+    s0, s1, s2, s3 = (FakeStream(n) for n in ("a", "bb", "ccc", "dddd"))
+    running = b.submit("stream", s0, 1, 1.0)          # picked up at once, blocks on the gate
+    time.sleep(0.05)
+    queued = [b.submit("stream", s, 1, 1.0) for s in (s1, s2, s3)]
+    assert queued[1].cancel()                          # cancelled while queued
+    assert not running.cancel()                        # already running: cannot be cancelled under the decode
+    dec.gate.set()
+    assert running.result(5).words == [[1]]
+    assert queued[0].result(5).words == [[2]] and queued[2].result(5).words == [[4]]
+    assert dec.calls == [["a"], ["bb", "dddd"]]        # the cancelled request never reached the device batch
+    assert b.thread is not None and b.thread.is_alive()
+    for s in (s0, s1, s2, s3):
+        assert s.closed_at is not None                  # every handle released by the batcher ...
+    assert s0.closed_at >= dec.done_at - 1.0
+    # ... and the worker still serves new requests
+    again = b.submit("stream", FakeStream("ee"), 1, 1.0)
+    assert again.result(5).words == [[2]]
+
+    # the coroutine-level view: wait_for times out on one of two concurrent calls, the other completes
+    dec2 = FakeDecoder()
+    lock = threading.Lock()
+    eng = SimpleNamespace(decoder=SimpleNamespace(open_stream=lambda: FakeStream("s"), graph=None), lock=lock, graph=None,
+                          batcher=T._Batcher(dec2, lock), words=lambda ids, graph=None: "w%d" % ids[0])
+    tr = T.KaldiNnet3StreamTranscriber(tmp_path, tmp_path, None)
+    tr._get_engine = lambda: eng
+
+    async def chunks():
+        yield b"\\0\\0"
+
+    async def main():
+        slow = asyncio.ensure_future(tr.async_transcribe(chunks(), tmp_path))
+        fast = asyncio.ensure_future(asyncio.wait_for(tr.async_transcribe(chunks(), tmp_path), timeout=0.2))
+        await asyncio.sleep(0.4)
+        dec2.gate.set()
+        out = await slow
+        with pytest.raises(asyncio.TimeoutError):
+            await fast
+        return out
+    assert asyncio.run(main()) == ["w1"]
+
+
+def test_capacity_status_bits_raise_like_a_failing_kaldi_binary():
+    from rhasspy_speech_b200 import transcribe as T
+    for bit in (1, 2, 8):
+        with pytest.raises(RuntimeError, match="Unexpected error running command"):
+            T.check_status(bit, "online2-wav-nnet3-latgen-faster")
+    for ok in (0, 4, 16, 16 | 64, 32, 16 | 256 | 1024):
+        T.check_status(ok, "online2-wav-nnet3-latgen-faster")
+
+
+def test_compressed_matrices_expand_as_the_reference_does(tmp_path):
+    """CM / CM2 / CM3 files written by the reference's copy-feats (tests/golden/cm_golden.npz, make_cm_golden.py) through
+    the library's reader: the values the reference itself prints for them (6 significant digits in text mode)."""
+    import __graft_entry__ as g
+    g.build()
+    from rhasspy_speech_b200 import _lib
+    from conftest import golden_dir
+    gold = np.load(os.path.join(golden_dir(), "cm_golden.npz"))
+    for tok in ("CM", "CM2", "CM3"):
+        f = tmp_path / (tok + ".mat")
+        f.write_bytes(gold[tok + "_file"].tobytes())
+        got = _lib.read_matrix(str(f))
+        want = gold[tok + "_expanded"]
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-6), (tok, np.abs(got - want).max())
+        # and the compression did lose precision against the source, i.e. the expansion was really exercised
+        assert np.abs(got - gold["source"]).max() > 1e-4
