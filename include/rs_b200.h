@@ -95,6 +95,9 @@ typedef struct rs_timings {
 } rs_timings;
 
 void rs_decoder_opts_default(rs_decoder_opts *opts);
+/* CUDA devices visible to the process (0 without a driver): the multi-device pool of the Python layer deals a request
+ * list over them; every device holds its own rs_model / rs_graph / rs_decoder replica. */
+int rs_device_count(void);
 
 /* Replaces the per-process model load of online2-wav-nnet3-latgen-faster.cc:150-181 (feature
  * pipeline info from --config=online.conf, TransitionModel + AmNnetSimple from final.mdl). */

@@ -52,6 +52,7 @@ _P = C.c_void_p
 _ERR = [C.c_char_p, C.c_size_t]
 SYMBOLS = [
     ("rs_decoder_opts_default", None, [C.POINTER(DecoderOpts)]),
+    ("rs_device_count", C.c_int, []),
     ("rs_model_load", _P, [C.c_char_p, C.c_char_p, C.c_int] + _ERR),
     ("rs_model_free", None, [_P]),
     ("rs_model_info", C.c_int, [_P] + [C.POINTER(C.c_int32)] * 6),
@@ -117,6 +118,10 @@ class RsError(RuntimeError):
 def _check(ok: bool, err):
     if not ok:
         raise RsError(err.value.decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(load_library().rs_device_count())
 
 
 def model_check(final_mdl: str, online_conf: str) -> str:

@@ -400,7 +400,9 @@ struct DecoderImpl {
   DevBuf d_tid_pdf;
   DevBuf d_loglikes_ext;
   PinBuf h_in, h_out;
-  LaneWorkspace *d_lanes = nullptr;
+  LaneWorkspace *d_lanes = nullptr;   // general decode kernel only; see EnsureLaneWorkspace
+  int lanes_allocated = 0;
+  std::vector<void *> lane_owned;
   int *d_next_utt = nullptr;
   int *d_range_flag = nullptr;  // set by a split store that had to saturate (fp16 planes)
   int *h_range_flag = nullptr;  // pinned
@@ -420,6 +422,7 @@ struct DecoderImpl {
   } batch;
   ~DecoderImpl() {
     for (void *p : owned) cudaFree(p);
+    for (void *p : lane_owned) cudaFree(p);
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -617,6 +620,11 @@ static void SetErr(char *err, size_t errlen, const std::string &msg) {
 
 extern "C" {
 
+int rs_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 void rs_decoder_opts_default(rs_decoder_opts *o) {
   o->beam = 24.0f;
   o->max_active = 7000;
@@ -746,46 +754,30 @@ static void BindGraph(DecoderImpl *d, GraphImpl *gi) {
   d->graph = gi;
 }
 
-rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts *opts, char *err, size_t errlen) {
-  API_GUARD_BEGIN
-  ModelImpl *mi = reinterpret_cast<ModelImpl *>(m_);
-  GraphImpl *gi = reinterpret_cast<GraphImpl *>(g_);
-  if (!mi || !gi) RS_FAIL("rs_decoder_create: model and graph are required");
-  if (mi->device != gi->device) RS_FAIL("model and graph live on different devices");
-  CUDA_OK(cudaSetDevice(mi->device));
-  std::unique_ptr<DecoderImpl> d(new DecoderImpl());
-  d->model = mi;
-  d->graph = gi;
-  if (opts) d->opts = *opts; else rs_decoder_opts_default(&d->opts);
-  rs_decoder_opts &o = d->opts;
-  if (o.beam <= 0 || o.max_active <= 1 || o.min_active < 0 || o.min_active >= o.max_active)
-    RS_FAIL("bad decoder options (beam/max-active/min-active)");
-  if (o.acoustic_scale != 1.0f && o.acoustic_scale != mi->m.acoustic_scale) {
-    // the scale is folded into the model's output epilogue at load time
-    RS_FAIL("acoustic_scale other than 1.0 is not supported (rhasspy always decodes with --acoustic-scale=1.0)");
-  }
-  if (o.max_tokens_per_frame < 1024) o.max_tokens_per_frame = 1024;
-  if (o.max_words < 1) o.max_words = 1;
-  CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-  for (auto &e : d->ev) CUDA_OK(cudaEventCreate(&e));
-  BindGraph(d.get(), gi);
-  // lanes
-  cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
-  d->n_lanes = o.num_lanes > 0 ? o.num_lanes : 2 * prop.multiProcessorCount;
+
+// Workspace of the general decode kernel (decode.cu): per-lane state tables and a traceback arena.  Allocated on the
+// first batch that needs it -- small graphs (decode_small.cu) never do -- and for the lanes that batch can occupy; a later,
+// larger batch grows it.  (The arena is max_tokens_per_utt records per lane: 32 MB at the default.)
+static void EnsureLaneWorkspace(DecoderImpl *d, int lanes_needed) {
+  if (d->d_lanes && d->lanes_allocated >= lanes_needed) return;
+  const rs_decoder_opts &o = d->opts;
+  CUDA_OK(cudaStreamSynchronize(d->stream));
+  for (void *p : d->lane_owned) cudaFree(p);
+  d->lane_owned.clear();
+  d->d_lanes = nullptr;
   int hash_size = 1;
   while (hash_size < 2 * o.max_tokens_per_frame) hash_size <<= 1;
   const size_t H = hash_size, C = o.max_tokens_per_frame;
-  std::vector<LaneWorkspace> lanes(d->n_lanes);
+  const int L = std::min(d->n_lanes, std::max(lanes_needed, 8));
+  std::vector<LaneWorkspace> lanes(L);
   auto dalloc = [&](size_t bytes, int fill) {
     void *p = nullptr;
     CUDA_OK(cudaMalloc(&p, bytes));
     CUDA_OK(cudaMemset(p, fill, bytes));
-    d->owned.push_back(p);
+    d->lane_owned.push_back(p);
     return p;
   };
   // one allocation per array kind, sliced per lane
-  const int L = d->n_lanes;
   int *hkey = (int *)dalloc(sizeof(int) * H * 2 * L, 0xff);
   unsigned long long *hval = (unsigned long long *)dalloc(sizeof(unsigned long long) * H * 2 * L, 0xff);
   int *hidx = (int *)dalloc(sizeof(int) * H * 2 * L, 0xff);
@@ -813,7 +805,44 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
     w.pfx = pfx + (size_t)l * (C + 1);
     w.arena = arena + (size_t)l * o.max_tokens_per_utt;
   }
-  d->d_lanes = Upload(lanes, &d->owned);
+  d->d_lanes = Upload(lanes, &d->lane_owned);
+  d->lanes_allocated = L;
+  CUDA_OK(cudaDeviceSynchronize());
+}
+
+rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts *opts, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  ModelImpl *mi = reinterpret_cast<ModelImpl *>(m_);
+  GraphImpl *gi = reinterpret_cast<GraphImpl *>(g_);
+  if (!mi || !gi) RS_FAIL("rs_decoder_create: model and graph are required");
+  if (mi->device != gi->device) RS_FAIL("model and graph live on different devices");
+  CUDA_OK(cudaSetDevice(mi->device));
+  std::unique_ptr<DecoderImpl> d(new DecoderImpl());
+  d->model = mi;
+  d->graph = gi;
+  if (opts) d->opts = *opts; else rs_decoder_opts_default(&d->opts);
+  rs_decoder_opts &o = d->opts;
+  if (o.beam <= 0 || o.max_active <= 1 || o.min_active < 0 || o.min_active >= o.max_active)
+    RS_FAIL("bad decoder options (beam/max-active/min-active)");
+  if (o.acoustic_scale != 1.0f && o.acoustic_scale != mi->m.acoustic_scale) {
+    // the scale is folded into the model's output epilogue at load time
+    RS_FAIL("acoustic_scale other than 1.0 is not supported (rhasspy always decodes with --acoustic-scale=1.0)");
+  }
+  if (o.max_tokens_per_frame < 1024) o.max_tokens_per_frame = 1024;
+  if (o.max_words < 1) o.max_words = 1;
+  CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  for (auto &e : d->ev) CUDA_OK(cudaEventCreate(&e));
+  BindGraph(d.get(), gi);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
+  d->n_lanes = o.num_lanes > 0 ? o.num_lanes : 2 * prop.multiProcessorCount;
+  auto dalloc = [&](size_t bytes, int fill) {
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    CUDA_OK(cudaMemset(p, fill, bytes));
+    d->owned.push_back(p);
+    return p;
+  };
   d->d_next_utt = (int *)dalloc(sizeof(int), 0);
   d->d_range_flag = (int *)dalloc(sizeof(int), 0);
   CUDA_OK(cudaMallocHost(&d->h_range_flag, sizeof(int)));
@@ -1054,7 +1083,9 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
       p.small_arena_off = d_off;
       LaunchDecodeSmall(p, d->stream, lattice);
     } else {
-      LaunchDecode(p, std::min(d->n_lanes, std::max(n, 1)), d->stream, lattice);
+      EnsureLaneWorkspace(d, std::min(d->n_lanes, std::max(n, 1)));
+      p.lanes = d->d_lanes;
+      LaunchDecode(p, std::min(d->lanes_allocated, std::max(n, 1)), d->stream, lattice);
     }
     launches += 1;
     if (lattice) {

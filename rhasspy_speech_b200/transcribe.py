@@ -110,6 +110,7 @@ class _Batcher:
         self.cv = threading.Condition()
         self.pending: "collections.deque" = collections.deque()
         self.batches: List[int] = []          # size of every device batch so far (instrumentation)
+        self.running = 0                      # requests of the batch that is on the device right now
         self.thread: Optional[threading.Thread] = None
 
     def submit(self, kind: str, payload, nbest: int, scale: float) -> "concurrent.futures.Future":
@@ -193,6 +194,7 @@ class _Batcher:
             if not batch:
                 continue
             kind, _, nbest, scale, _ = batch[0]
+            self.running = len(batch)
             try:
                 try:
                     hyp = self._decode(kind, [b[1] for b in batch], nbest, scale)
@@ -209,6 +211,7 @@ class _Batcher:
                         except Exception as e:  # noqa: BLE001
                             self._deliver(b[4], error=e)
             finally:
+                self.running = 0
                 for b in batch:
                     self._release(b[0], b[1])
 
@@ -230,6 +233,7 @@ class _Engine:
         self.decoder = _lib.Decoder(self.model, self.graph, **opts)
         self.lock = threading.Lock()
         self.batcher = _Batcher(self.decoder, self.lock)
+        self.open_streams = 0           # streams bound to this engine (sticky stream -> GPU assignment)
 
     def refresh_graph(self):
         """Hot graph swap.  The reference reads HCLG.fst and words.txt in every call, so the graph
@@ -260,6 +264,11 @@ class _Engine:
         return " ".join(out)
 
 
+def _load(eng) -> int:
+    b = getattr(eng, "batcher", None)
+    return (len(b.pending) + getattr(b, "running", 0) if b is not None else 0) + getattr(eng, "open_streams", 0)
+
+
 def _file_sig(paths) -> Tuple:
     """(mtime, size) of each file; missing files are left to the loader's error message."""
     out = []
@@ -276,8 +285,8 @@ _KEY_LOCKS: Dict[Tuple, threading.Lock] = {}
 
 
 def _engine(final_mdl: Path, online_conf: Path, graph_dir: Path, device: int, max_active: int, beam: float,
-            lattice_beam: float) -> _Engine:
-    key = (str(final_mdl), str(online_conf), str(graph_dir), device, max_active, float(beam), float(lattice_beam))
+            lattice_beam: float, replica: int = 0) -> _Engine:
+    key = (str(final_mdl), str(online_conf), str(graph_dir), device, max_active, float(beam), float(lattice_beam), replica)
     with _ENGINES_LOCK:                 # held only for the dictionary lookups: loading one engine must not block the others
         key_lock = _KEY_LOCKS.setdefault(key, threading.Lock())
     with key_lock:
@@ -354,9 +363,27 @@ async def _fuzzy(nbest_stdout: bytes, lang_dir: Path, tools) -> Optional[Tuple[s
     return (" ".join(words), hit[1]) if words else None
 
 
+def resolve_devices(device) -> List[int]:
+    """`device` of the transcriber classes: one CUDA device index, a sequence of indices (a device may be listed more
+    than once: that many engines on it), or "all"."""
+    if isinstance(device, str):
+        if device != "all":
+            raise ValueError("device must be an index, a sequence of indices or 'all'")
+        n = _lib.device_count()
+        if n < 1:
+            raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: no CUDA device available")
+        return list(range(n))
+    if isinstance(device, int):
+        return [device]
+    devs = [int(d) for d in device]
+    if not devs:
+        raise ValueError("empty device list")
+    return devs
+
+
 class _Base:
     def __init__(self, model_dir, graph_dir, tools=None, max_active: int = 7000, lattice_beam: float = 8.0,
-                 acoustic_scale: float = 1.0, beam: float = 24.0, device: int = 0):
+                 acoustic_scale: float = 1.0, beam: float = 24.0, device: Union[int, Sequence[int], str] = 0):
         self.model_dir = Path(model_dir)
         self.graph_dir = Path(graph_dir)
         self.tools = tools
@@ -366,14 +393,38 @@ class _Base:
         # --acoustic-scale, transcribe_wav.py:65); the search always runs at 1.0 (:54)
         self.acoustic_scale = acoustic_scale
         self.beam = beam
+        # Multi-GPU: utterances are independent, so a transcriber given several devices keeps one engine
+        # (model + graph replica, decoder, dynamic batcher) per device; a request list is dealt longest-first over them
+        # (shard.shard_utterances), a single request or a stream goes to the least-loaded engine and stays there.
         self.device = device
+        self._rr = 0
 
     def _paths(self) -> Tuple[Path, Path]:
         return (self.model_dir / "model" / "model" / "final.mdl", self.model_dir / "model" / "online" / "conf" / "online.conf")
 
-    def _get_engine(self) -> _Engine:
+    def _get_engines(self) -> List[_Engine]:
         final_mdl, online_conf = self._paths()
-        return _engine(final_mdl, online_conf, self.graph_dir, self.device, self.max_active, self.beam, self.lattice_beam)
+        devs = resolve_devices(self.device)
+        seen: Dict[int, int] = {}
+        jobs = []
+        for d in devs:
+            jobs.append((d, seen.get(d, 0)))
+            seen[d] = seen.get(d, 0) + 1
+
+        def make(job):
+            return _engine(final_mdl, online_conf, self.graph_dir, job[0], self.max_active, self.beam, self.lattice_beam, job[1])
+        if len(jobs) == 1:
+            return [make(jobs[0])]
+        with concurrent.futures.ThreadPoolExecutor(max_workers=len(jobs)) as ex:     # replicas load side by side
+            return list(ex.map(make, jobs))
+
+    def _get_engine(self) -> _Engine:
+        """The engine for ONE request: the least-loaded of the pool (queued + running requests, then open streams)."""
+        engines = self._get_engines()
+        if len(engines) == 1:
+            return engines[0]
+        self._rr += 1
+        return min(enumerate(engines), key=lambda ie: (_load(ie[1]), (ie[0] - self._rr) % len(engines)))[1]
 
     async def _get_engine_async(self) -> _Engine:
         """Engine lookup from a coroutine: the first call loads the model and the graph (disk reads, H2D upload), a later
@@ -427,22 +478,40 @@ class KaldiNnet3WavTranscriber(_Base):
     async def async_transcribe_many(self, wav_paths: Sequence, lang_dir, nbest: int = 1,
                                     max_fuzzy_cost: Optional[float] = None,
                                     require_fuzzy: bool = False) -> List[List[str]]:
-        """Batched extension: one GPU batch for all files; element i equals async_transcribe(wav_paths[i])."""
-        eng = await self._get_engine_async()
+        """Batched extension: element i equals async_transcribe(wav_paths[i]).  One device batch per engine: with several
+        devices the list is dealt longest-first (file size = duration) so that every GPU gets the same audio seconds, and
+        the shares run concurrently (no collective -- the results are word ids gathered by this thread)."""
+        from .shard import shard_utterances
         loop = asyncio.get_running_loop()
+        engines = await loop.run_in_executor(None, self._get_engines)
+        paths = [str(p) for p in wav_paths]
+        if len(engines) > 1:
+            sizes = []
+            for p in paths:
+                try:
+                    sizes.append(float(os.path.getsize(p)))
+                except OSError:
+                    sizes.append(0.0)           # a missing file fails in its own share with the loader's message
+            shares = shard_utterances(sizes, len(engines))
+        else:
+            shares = [list(range(len(paths)))]
 
-        def run():
+        def run(eng, idx):
+            if not idx:
+                return None, None
             with eng.lock:
                 try:
                     self._set_nbest(eng, nbest)
-                    return eng.decoder.decode_wavs([str(p) for p in wav_paths]), eng.decoder.graph
+                    return eng.decoder.decode_wavs([paths[i] for i in idx]), eng.decoder.graph
                 except _lib.RsError as e:
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
-        hyp, graph = await loop.run_in_executor(None, run)
-        for u in range(len(wav_paths)):
-            check_status(int(hyp.status[u]), "online2-wav-nnet3-latgen-faster")
-        return [await self._finish(eng, nbest_text(hyp, u), lang_dir, max_fuzzy_cost, require_fuzzy, graph)
-                for u in range(len(wav_paths))]
+        parts = await asyncio.gather(*[loop.run_in_executor(None, run, eng, idx) for eng, idx in zip(engines, shares)])
+        out: List[Optional[List[str]]] = [None] * len(paths)
+        for eng, idx, (hyp, graph) in zip(engines, shares, parts):
+            for k, i in enumerate(idx):
+                check_status(int(hyp.status[k]), "online2-wav-nnet3-latgen-faster")
+                out[i] = await self._finish(eng, nbest_text(hyp, k), lang_dir, max_fuzzy_cost, require_fuzzy, graph)
+        return out  # type: ignore[return-value]
 
     async def async_transcribe_rescore(self, *args, **kwargs):
         raise NotImplementedError("lattice rescoring (reference transcribe_wav.py:107-232) is scope row f3")
@@ -452,8 +521,15 @@ class KaldiNnet3StreamTranscriber(_Base):
     async def async_transcribe(self, audio_stream: AsyncIterable[Optional[bytes]], lang_dir, nbest: int = 1,
                                max_fuzzy_cost: Optional[float] = None, require_fuzzy: bool = False) -> List[str]:
         """audio_stream yields raw 16 kHz mono s16le chunks of any size (reference transcribe_stream.py:38-82)."""
-        eng = await self._get_engine_async()
+        eng = await self._get_engine_async()        # least-loaded engine; the stream stays on it (sticky)
         stream = eng.decoder.open_stream()
+        eng.open_streams = getattr(eng, "open_streams", 0) + 1
+        try:
+            return await self._transcribe_on(eng, stream, audio_stream, lang_dir, nbest, max_fuzzy_cost, require_fuzzy)
+        finally:
+            eng.open_streams -= 1
+
+    async def _transcribe_on(self, eng, stream, audio_stream, lang_dir, nbest, max_fuzzy_cost, require_fuzzy) -> List[str]:
         try:
             pending = b""
             async for chunk in audio_stream:

@@ -116,3 +116,48 @@ def test_pinned_audio_block_gives_the_same_results(tiny_model, utterances):
     rev = dec.decode_pcm(pa.views[::-1])              # not in block order: staged like any other buffer
     assert rev.words == want.words[::-1] and dec.timings()["h2d_bytes"] == h2d_direct
     pa.close()
+
+
+def test_device_pool_gives_the_single_device_results(tiny_model, utterances, synth, tmp_path):
+    """SURVEY 8e on the product path: a transcriber over several engines (here two on device 0 -- and every visible device
+    when the box has more) deals a request list longest-first, runs the shares concurrently and returns what one device
+    returns; concurrent single requests and streams spread over the engines."""
+    import rhasspy_speech_b200 as pkg
+    from rhasspy_speech_b200 import _lib
+    graph_dir = os.path.dirname(tiny_model.hclg)
+    wavs = []
+    for i in range(24):
+        w = os.path.join(str(tmp_path), "p%03d.wav" % i)
+        synth.write_wav(w, utterances[i % len(utterances)][:16000 + 997 * i])
+        wavs.append(w)
+    one = pkg.KaldiNnet3WavTranscriber(tiny_model.model_dir, graph_dir, None)
+    want = asyncio.run(one.async_transcribe_many(wavs, tmp_path, nbest=2))
+    devices = [0, 0] if _lib.device_count() < 2 else list(range(_lib.device_count()))
+    pool = pkg.KaldiNnet3WavTranscriber(tiny_model.model_dir, graph_dir, None, device=devices)
+    engines = pool._get_engines()
+    assert len(engines) == len(devices) and len({id(e) for e in engines}) == len(devices)
+    assert asyncio.run(pool.async_transcribe_many(wavs, tmp_path, nbest=2)) == want
+
+    async def burst():
+        return await asyncio.gather(*[pool.async_transcribe(w, tmp_path, nbest=2) for w in wavs])
+    before = [len(e.batcher.batches) for e in engines]
+    assert asyncio.run(burst()) == want
+    assert sum(1 for e, b in zip(engines, before) if len(e.batcher.batches) > b) >= 2      # more than one engine took work
+    # streams: sticky to the least-loaded engine
+    sp = pkg.KaldiNnet3StreamTranscriber(tiny_model.model_dir, graph_dir, None, device=devices)
+
+    async def chunks(pcm):
+        raw = np.asarray(pcm, dtype="<i2").tobytes()
+        for o in range(0, len(raw), 2560):
+            yield raw[o:o + 2560]
+            await asyncio.sleep(0)
+
+    async def streams():
+        return await asyncio.gather(*[sp.async_transcribe(chunks(utterances[i % len(utterances)]), tmp_path) for i in range(12)])
+    s1 = pkg.KaldiNnet3StreamTranscriber(tiny_model.model_dir, graph_dir, None)
+
+    async def lone():
+        return [await s1.async_transcribe(chunks(utterances[i % len(utterances)]), tmp_path) for i in range(len(utterances))]
+    got, ref = asyncio.run(streams()), asyncio.run(lone())
+    assert got == [ref[i % len(utterances)] for i in range(12)]
+    assert all(e.open_streams == 0 for e in sp._get_engines())

@@ -216,7 +216,7 @@ def test_transcriber_flow_with_a_fake_engine(tmp_path, monkeypatch):
     lock = threading.Lock()
     eng = SimpleNamespace(decoder=dec, lock=lock, graph=dec.graph, batcher=T._Batcher(dec, lock),
                           words=lambda ids, graph=None: " ".join((graph or dec.graph).word(i) for i in ids))
-    monkeypatch.setattr(T._Base, "_get_engine", lambda self: eng)
+    monkeypatch.setattr(T._Base, "_get_engines", lambda self: [eng])
     monkeypatch.setattr(T.KaldiTranscriber, "_get_engine", lambda self: eng)
     tr = T.KaldiNnet3WavTranscriber(tmp_path, tmp_path, None)
     assert asyncio.run(tr.async_transcribe("a.wav", tmp_path)) == ["turn on light"]
@@ -337,3 +337,64 @@ def test_compressed_matrices_expand_as_the_reference_does(tmp_path):
         assert np.allclose(got, want, rtol=2e-6, atol=1e-6), (tok, np.abs(got - want).max())
         # and the compression did lose precision against the source, i.e. the expansion was really exercised
         assert np.abs(got - gold["source"]).max() > 1e-4
+
+
+def test_multi_device_pool_deals_requests_over_engines(tmp_path, monkeypatch):
+    """SURVEY 8e on the product path: a transcriber given several devices keeps one engine per device; a request list is
+    dealt longest-first (shard.shard_utterances) and the shares run concurrently; single requests and streams go to the
+    least-loaded engine.  Fake engines on CPU; tests/test_gpu_surface.py runs the same path on real devices."""
+    import asyncio
+    import threading
+    import time
+    from types import SimpleNamespace
+    from rhasspy_speech_b200 import transcribe as T
+
+    class FakeGraph:
+        def word(self, i):
+            return "w%d" % i
+
+    class FakeDecoder:
+        def __init__(self, name):
+            self.name, self.graph, self.calls, self.busy = name, FakeGraph(), [], threading.Event()
+
+        def set_nbest(self, n, scale=1.0):
+            pass
+
+        def decode_wavs(self, paths):
+            self.calls.append(list(paths))
+            time.sleep(0.05)
+            n = len(paths)
+            ids = [[int(os.path.basename(p)[1:4])] for p in paths]
+            return SimpleNamespace(n_utts=n, words=ids, nbest=[[(w, 0.0, 0.0)] for w in ids], status=[0] * n, n_hyp=[1] * n)
+
+    engines = []
+    for k in range(3):
+        dec = FakeDecoder("gpu%d" % k)
+        lock = threading.Lock()
+        engines.append(SimpleNamespace(decoder=dec, lock=lock, graph=dec.graph, batcher=T._Batcher(dec, lock), open_streams=0,
+                                       words=lambda ids, graph=None: " ".join("w%d" % i for i in ids)))
+    monkeypatch.setattr(T._Base, "_get_engines", lambda self: engines)
+    tr = T.KaldiNnet3WavTranscriber(tmp_path, tmp_path, None, device=[0, 1, 2])
+    paths = []
+    for i in range(20):
+        p = tmp_path / ("u%03d.wav" % i)
+        p.write_bytes(b"x" * (1000 + 977 * ((i * 7) % 11)))
+        paths.append(str(p))
+    t0 = time.monotonic()
+    out = asyncio.run(tr.async_transcribe_many(paths, tmp_path))
+    assert out == [["w%d" % i] for i in range(20)]                       # original order restored
+    shares = [e.decoder.calls[0] for e in engines]
+    assert sorted(p for s in shares for p in s) == sorted(paths) and all(len(s) >= 5 for s in shares)
+    loads = [sum(os.path.getsize(p) for p in s) for s in shares]
+    assert max(loads) - min(loads) <= 11 * 977                           # equal audio per device (longest-first deal)
+    assert time.monotonic() - t0 < 0.14                                  # the three shares ran side by side, not 3 x 50 ms
+    # single requests spread over the pool
+    async def burst():
+        return await asyncio.gather(*[tr.async_transcribe(paths[i], tmp_path) for i in range(9)])
+    for e in engines:
+        e.decoder.calls.clear()
+    assert asyncio.run(burst()) == [["w%d" % i] for i in range(9)]
+    assert all(e.decoder.calls for e in engines)
+    assert T.resolve_devices(3) == [3] and T.resolve_devices([1, 1, 0]) == [1, 1, 0]
+    with pytest.raises(ValueError):
+        T.resolve_devices("some")
