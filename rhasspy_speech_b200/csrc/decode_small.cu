@@ -15,7 +15,10 @@
 //     GetCutoff (:644-711), are skipped by ProcessNonemitting, and may be final on the last frame.
 // Every per-frame table is addressed by state id and lives in shared memory; one CTA walks one utterance.
 // Larger graphs use decode.cu (same cutoff values, extras dropped, order-sensitive frames detected and flagged).
+#include <cuda_pipeline.h>
+
 #include <cfloat>
+#include <cstdio>
 
 #include "decode_common.cuh"
 #include "engine.h"
@@ -24,7 +27,7 @@ namespace rs {
 
 namespace {
 
-constexpr int kNT = 256;
+constexpr int kNT = 512;
 constexpr int kNW = kNT / 32;
 constexpr int kSlots = 1024;         // >= kSmallMaxStates
 constexpr int kItems = kSlots / kNT; // list items per thread in the blocked scans
@@ -172,6 +175,51 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
     S.nval[i] = kEmptyVal;
     S.first[i] = kNoFirst;
   }
+  // Dynamic shared memory (layout fixed by SmallSmemPlan on the host): the graph's CSR offsets, its arcs when they fit,
+  // the destination state of every flat arc of the frame, and two staged log-likelihood rows (the row of frame f + 1 is
+  // copied asynchronously while frame f is processed).  Every per-arc access of the frame loop is then shared memory.
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int S1 = g.num_states + 1;
+  unsigned *ebeg = reinterpret_cast<unsigned *>(dsm), *pbeg = ebeg + S1;
+  unsigned char *q = dsm + (((size_t)2 * S1 * 4 + 15) & ~(size_t)15);
+  const int4 *earc = g.earc, *parc = g.parc;
+  const int *psrc = g.p_src;
+  for (int i = tid; i < S1; i += kNT) {
+    ebeg[i] = g.e_begin[i];
+    pbeg[i] = g.p_begin[i];
+  }
+  if (cfg.small_cache_arcs) {
+    int4 *e_s = reinterpret_cast<int4 *>(q);
+    q += (size_t)NE * 16;
+    int4 *p_s = reinterpret_cast<int4 *>(q);
+    q += (size_t)g.num_parcs * 16;
+    int *ps_s = reinterpret_cast<int *>(q);
+    q += ((size_t)g.num_parcs * 4 + 15) & ~(size_t)15;
+    for (unsigned i = tid; i < NE; i += kNT) e_s[i] = g.earc[i];
+    for (unsigned i = tid; i < g.num_parcs; i += kNT) {
+      p_s[i] = g.parc[i];
+      ps_s[i] = g.p_src[i];
+    }
+    earc = e_s;
+    parc = p_s;
+    psrc = ps_s;
+  }
+  unsigned short *adst = reinterpret_cast<unsigned short *>(q);
+  q += ((size_t)NE * 2 + 15) & ~(size_t)15;
+  float *llbuf[2] = {nullptr, nullptr};
+  if (cfg.small_ll_stage) {
+    llbuf[0] = reinterpret_cast<float *>(q);
+    llbuf[1] = llbuf[0] + P.ld;
+  }
+  const float *ll_rows = P.loglikes + (size_t)P.ll_row0[u] * P.ld;
+  auto stage_row = [&](int frame) {  // asynchronous copy of one log-likelihood row (ld is a multiple of 4 floats)
+    if (!cfg.small_ll_stage || frame >= n_frames) return;
+    const float4 *src = reinterpret_cast<const float4 *>(ll_rows + (size_t)frame * P.ld);
+    float4 *dst = reinterpret_cast<float4 *>(llbuf[frame & 1]);
+    for (int i = tid; i < P.ld / 4; i += kNT) __pipeline_memcpy_async(dst + i, src + i, 16);
+    __pipeline_commit();
+  };
+  stage_row(0);
   if (tid == 0) {
     S.n_links = 0;
     S.lat_overflow = 0;
@@ -199,6 +247,15 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       S.lat_overflow = 1;
   };
   unsigned long long cnt_tokens = 0, cnt_arcs = 0, cnt_created = 0;  // block-uniform
+  // optional phase timing (RS_B200_DECODE_PROFILE=1): thread 0 of block 0 accumulates SM clocks per phase
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_last = clock64();
+  auto tick = [&](int k) {
+    if (cfg.profile && tid == 0 && blockIdx.x == 0) {
+      const long long now = clock64();
+      ph[k] += now - ph_last;
+      ph_last = now;
+    }
+  };
   int status = 0;
   int cur = 0;          // which list is the current one
   int n_cur = 0;
@@ -225,7 +282,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
           if (r < n_emit) {
             const int st = ls[n_emit - 1 - r];
             const float c = unord((unsigned)(S.nval[st] >> 32));
-            if (c < cutoff) deg[k] = g.p_begin[st + 1] - g.p_begin[st];
+            if (c < cutoff) deg[k] = pbeg[st + 1] - pbeg[st];
           }
           sum += deg[k];
         }
@@ -245,8 +302,8 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
           if (e < n_eps) {
             const int r = locate(S.pfx2, n_emit, e);
             const int st = ls[n_emit - 1 - r];
-            const unsigned pa = g.p_begin[st] + (e - S.pfx2[r]);
-            const int4 arc = g.parc[pa];
+            const unsigned pa = pbeg[st] + (e - S.pfx2[r]);
+            const int4 arc = parc[pa];
             const float c = unord((unsigned)(S.nval[st] >> 32));
             const float tot = __fadd_rn(c, __int_as_float(arc.z));
             if (tot < cutoff) {
@@ -265,7 +322,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
           if (e < n_eps && ((S.adm2[e >> 5] >> (e & 31)) & 1u)) {
             const int r = locate(S.pfx2, n_emit, e);
             const int st = ls[n_emit - 1 - r];
-            const int4 arc = g.parc[g.p_begin[st] + (e - S.pfx2[r])];
+            const int4 arc = parc[pbeg[st] + (e - S.pfx2[r])];
             if (S.first[arc.x] == kEpsBase + e) ns = arc.x;
           }
           unsigned total;
@@ -281,14 +338,14 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
           const int qcap = kSlots + 1;
           int nq = 0, nn = n_emit;
           for (int j = 0; j < n_emit; j++)
-            if (g.p_begin[ls[j] + 1] > g.p_begin[ls[j]]) q[nq++] = ls[j];
+            if (pbeg[ls[j] + 1] > pbeg[ls[j]]) q[nq++] = ls[j];
           unsigned visited = 0;
           while (nq > 0) {
             const int st = q[--nq];
             const float c = unord((unsigned)(S.nval[st] >> 32));
             if (c >= cutoff) continue;
-            for (unsigned pa = g.p_begin[st]; pa < g.p_begin[st + 1]; pa++) {
-              const int4 arc = g.parc[pa];
+            for (unsigned pa = pbeg[st]; pa < pbeg[st + 1]; pa++) {
+              const int4 arc = parc[pa];
               visited++;
               const float tot = __fadd_rn(c, __int_as_float(arc.z));
               if (tot < cutoff) {
@@ -303,7 +360,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
                   S.nval[arc.x] = pack(tot, kEpsTag | pa);
                   changed = true;
                 }
-                if (changed && g.p_begin[arc.x + 1] > g.p_begin[arc.x]) {
+                if (changed && pbeg[arc.x + 1] > pbeg[arc.x]) {
                   if (nq < qcap) q[nq++] = arc.x; else S.flag = 1;
                 }
               }
@@ -319,6 +376,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       }
     }
     cnt_arcs += n_eps;
+    tick(4);
     if ((long long)base_new + n_new > arena_cap) return -2;
     for (int i = tid; i < n_new; i += kNT) S.nidx[ls[i]] = i;
     __syncthreads();
@@ -334,12 +392,12 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       if (low == kArcNone) {
       } else if (low & kEpsTag) {
         const unsigned pa = low & ~kEpsTag;
-        prev = base_new + S.nidx[g.p_src[pa]];
+        prev = base_new + S.nidx[psrc[pa]];
         arc = NE + pa;
       } else {
         const int lo = locate(S.pfx, n_cur, low);
         prev = base_cur + lo;
-        arc = g.e_begin[lp[lo]] + (low - S.pfx[lo]);
+        arc = ebeg[lp[lo]] + (low - S.pfx[lo]);
       }
       arena[base_new + i] = make_int2(prev, (int)arc);
       if constexpr (kLat)
@@ -359,8 +417,8 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       const int st = S.lstate[nx][i];
       const float c = S.lcost[nx][i];
       if (!(c < cutoff)) continue;
-      for (unsigned a = g.p_begin[st]; a < g.p_begin[st + 1]; a++) {
-        const int4 arc = g.parc[a];
+      for (unsigned a = pbeg[st]; a < pbeg[st + 1]; a++) {
+        const int4 arc = parc[a];
         const float tot = __fadd_rn(c, __int_as_float(arc.z));
         if (tot < cutoff) {
           const int d = S.nidx[arc.x];
@@ -403,7 +461,14 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
     const int nx = cur ^ 1;
     const int *state = S.lstate[cur];
     const float *cost = S.lcost[cur];
-    const float *ll = P.loglikes + (size_t)(P.ll_row0[u] + frame) * P.ld;
+    // this frame's row was staged during the previous frame (or before the loop); start on the next one
+    const float *ll = ll_rows + (size_t)frame * P.ld;
+    if (cfg.small_ll_stage) {
+      __pipeline_wait_prior(0);
+      __syncthreads();
+      ll = llbuf[frame & 1];
+      stage_row(frame + 1);
+    }
     // ---- GetCutoff (:644-711) over the whole list, extras included
     float best;
     int best_idx;
@@ -451,7 +516,40 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
             unsigned inside = 0, total;
             for (int i = tid; i < n_cur; i += kNT) inside += cost[i] <= beam_cutoff ? 1u : 0u;
             X.scan_sum(inside, &total);
-            min_active_cutoff = (int)total > cfg.min_active ? beam_cutoff : kth(cfg.min_active);
+            if ((int)total > cfg.min_active) {
+              min_active_cutoff = beam_cutoff;
+            } else {
+              // the min_active-th smallest cost lies among the few tokens beyond the beam: rank (min_active - inside)
+              // among those, ordered by (cost, index) -- the ranking kth() computes, over a compacted list
+              float *oc = reinterpret_cast<float *>(S.pfx2);
+              int *oi = reinterpret_cast<int *>(S.pfx2) + 512;
+              if (tid == 0) S.n_new = 0;
+              __syncthreads();
+              for (int i = tid; i < n_cur; i += kNT)
+                if (cost[i] > beam_cutoff) {
+                  const int j = atomicAdd(&S.n_new, 1);
+                  if (j < 512) {
+                    oc[j] = cost[i];
+                    oi[j] = i;
+                  }
+                }
+              __syncthreads();
+              const int m = S.n_new, target = cfg.min_active - (int)total;
+              if (m > 512) {
+                min_active_cutoff = kth(cfg.min_active);
+              } else {
+                for (int j = tid; j < m; j += kNT) {
+                  const float c = oc[j];
+                  const int ci = oi[j];
+                  int r = 0;
+                  for (int l = 0; l < m; l++) r += (oc[l] < c || (oc[l] == c && oi[l] < ci)) ? 1 : 0;
+                  if (r == target) S.kth = c;
+                }
+                __syncthreads();
+                min_active_cutoff = S.kth;
+                __syncthreads();
+              }
+            }
           }
         }
         if (min_active_cutoff > beam_cutoff) {
@@ -463,13 +561,14 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
         }
       }
     }
+    tick(0);
     // ---- ProcessEmitting (:714-804)
     const float cost_offset = -best;
     if (warp == 0) {  // next_cutoff seeded from the best token's arcs (:744-759)
       const int st = state[best_idx];
       float m = kInf;
-      for (unsigned a = g.e_begin[st] + lane; a < g.e_begin[st + 1]; a += 32) {
-        const int4 arc = g.earc[a];
+      for (unsigned a = ebeg[st] + lane; a < ebeg[st + 1]; a += 32) {
+        const int4 arc = earc[a];
         const float nw = __fadd_rn(__fsub_rn(__fadd_rn(__int_as_float(arc.z), cost_offset), ll[arc.y]), best);
         m = fminf(m, __fadd_rn(nw, adaptive_beam));
       }
@@ -486,7 +585,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
         deg[k] = 0;
         if (i < n_cur && cost[i] <= cur_cutoff) {
           const int st = state[i];
-          deg[k] = g.e_begin[st + 1] - g.e_begin[st];
+          deg[k] = ebeg[st + 1] - ebeg[st];
         }
         sum += deg[k];
       }
@@ -500,6 +599,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       if (tid == 0) S.pfx[n_cur] = n_arcs;
     }
     __syncthreads();
+    tick(1);
     // pass 1: every flat arc against the cutoff it meets in list order; winners by (cost, flat position)
     float run = S.seed;
     for (unsigned a0 = 0; a0 < n_arcs; a0 += kNT) {
@@ -508,11 +608,12 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       int ns = 0;
       if (a < n_arcs) {
         const int lo = locate(S.pfx, n_cur, a);
-        const int4 arc = g.earc[g.e_begin[state[lo]] + (a - S.pfx[lo])];
+        const int4 arc = earc[ebeg[state[lo]] + (a - S.pfx[lo])];
         const float ac = __fsub_rn(cost_offset, ll[arc.y]);
         tot = __fadd_rn(__fadd_rn(cost[lo], ac), __int_as_float(arc.z));
         cand = __fadd_rn(tot, adaptive_beam);
         ns = arc.x;
+        adst[a] = (unsigned short)ns;
       }
       float chunk_min;
       const float met = fminf(run, X.scan_min(cand, &chunk_min));
@@ -527,15 +628,15 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
     }
     const float next_cutoff = run;
     __syncthreads();
+    tick(2);
     // pass 2: the states in the order of their first insertion
     int n_emit = 0;
     for (unsigned a0 = 0; a0 < n_arcs; a0 += kNT) {
       const unsigned a = a0 + tid;
       int ns = -1;
       if (a < n_arcs && ((S.adm[a >> 5] >> (a & 31)) & 1u)) {
-        const int lo = locate(S.pfx, n_cur, a);
-        const int4 arc = g.earc[g.e_begin[state[lo]] + (a - S.pfx[lo])];
-        if (S.first[arc.x] == a) ns = arc.x;
+        const int d = adst[a];
+        if (S.first[d] == a) ns = d;
       }
       unsigned total;
       const unsigned pos = X.scan_sum(ns >= 0 ? 1u : 0u, &total);
@@ -543,10 +644,12 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       n_emit += (int)total;
     }
     __syncthreads();
+    tick(3);
     cnt_tokens += n_cur;
     cnt_arcs += n_arcs;
     const int base_new = base_cur + n_cur;
     const int r = close_and_finalize(nx, n_emit, next_cutoff, base_new);
+    tick(5);
     if (r < 0) {
       status |= 2;
       break;
@@ -558,8 +661,8 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
       for (unsigned a = tid; a < n_arcs; a += kNT) {
         if (!((S.adm[a >> 5] >> (a & 31)) & 1u)) continue;
         const int lo = locate(S.pfx, n_cur, a);
-        const unsigned ai = g.e_begin[state[lo]] + (a - S.pfx[lo]);
-        const int4 arc = g.earc[ai];
+        const unsigned ai = ebeg[state[lo]] + (a - S.pfx[lo]);
+        const int4 arc = earc[ai];
         const float ac = __fsub_rn(cost_offset, ll[arc.y]);
         const float tot = __fadd_rn(__fadd_rn(cost[lo], ac), __int_as_float(arc.z));
         const int d = S.nidx[arc.x];
@@ -583,9 +686,13 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
     cnt_created += r;
     cur = nx;
   }
+  if (cfg.small_ll_stage) __pipeline_wait_prior(0);
   if constexpr (kLat) {
     if (tid == 0) ltb[n_frames + 1] = lat_dead ? -1 : arena_n;
   }
+  if (cfg.profile && tid == 0 && blockIdx.x == 0)
+    printf("decode_small phases (clocks, utt %d, %d frames): cutoff %lld seed+prefix %lld pass1 %lld pass2 %lld epsilon %lld finalize %lld\n", u,
+           n_frames, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
   // ---- best path (lattice-faster-online-decoder.cc:78-173)
   int n_words = -1;
   if (status == 0 && n_cur == 0) status |= 4;
@@ -625,7 +732,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
           const int2 rec = arena[gid];
           const unsigned arc = (unsigned)rec.y;
           if (arc != kArcNone) {
-            const int4 a = arc < NE ? g.earc[arc] : g.parc[arc - NE];
+            const int4 a = arc < NE ? earc[arc] : parc[arc - NE];
             graph += __int_as_float(a.z);
             if (arc < NE) {
               acoustic -= P.loglikes[(size_t)(P.ll_row0[u] + f) * P.ld + a.y];
@@ -673,12 +780,35 @@ bool DecodeSmallSupports(const DevGraph &g) {
   return g.num_states <= kSmallMaxStates && g.num_earcs <= (unsigned)kSmallMaxEarcs && g.num_parcs <= (unsigned)kSmallMaxParcs;
 }
 
-void LaunchDecodeSmall(const DecodeParams &p, cudaStream_t stream, bool lattice) {
-  if (p.n_utts == 0) return;
+// dynamic shared memory of decode_small_kernel: CSR offsets | [arcs] | flat-arc destinations | [two log-likelihood rows];
+// the optional parts are dropped (arcs first) when they do not fit next to the static tables
+static size_t SmallSmemPlan(const DecodeParams &p, int *cache_arcs, int *ll_stage) {
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t base = up16((size_t)2 * (p.g.num_states + 1) * 4) + up16((size_t)p.g.num_earcs * 2);
+  const size_t arcs = (size_t)p.g.num_earcs * 16 + (size_t)p.g.num_parcs * 16 + up16((size_t)p.g.num_parcs * 4);
+  const size_t rows = (size_t)2 * p.ld * 4;
+  const size_t budget = 150 * 1024;  // next to ~43 KB of static tables; leaves room for a second CTA on small graphs
+  *ll_stage = (p.ld % 4 == 0 && base + rows <= budget) ? 1 : 0;
+  *cache_arcs = base + (*ll_stage ? rows : 0) + arcs <= budget ? 1 : 0;
+  return base + (*ll_stage ? rows : 0) + (*cache_arcs ? arcs : 0) + 16;
+}
+
+void LaunchDecodeSmall(const DecodeParams &p_in, cudaStream_t stream, bool lattice) {
+  if (p_in.n_utts == 0) return;
+  DecodeParams p = p_in;
+  const size_t smem = SmallSmemPlan(p, &p.cfg.small_cache_arcs, &p.cfg.small_ll_stage);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[lattice]) {
+    if (lattice)
+      cudaFuncSetAttribute(decode_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else
+      cudaFuncSetAttribute(decode_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured[lattice] = smem;
+  }
   if (lattice)
-    decode_small_kernel<true><<<p.n_utts, kNT, 0, stream>>>(p);
+    decode_small_kernel<true><<<p.n_utts, kNT, smem, stream>>>(p);
   else
-    decode_small_kernel<false><<<p.n_utts, kNT, 0, stream>>>(p);
+    decode_small_kernel<false><<<p.n_utts, kNT, smem, stream>>>(p);
 }
 
 }  // namespace rs

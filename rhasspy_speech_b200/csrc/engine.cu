@@ -1,6 +1,10 @@
 // Host engine + C ABI (include/rs_b200.h): uploads the model tables, lays a batch of utterances out
 // on the global time axis, launches the three stages on one CUDA stream and returns word ids.
 // There is no CPU fallback: every entry point fails loudly if CUDA is unavailable.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -1352,7 +1356,11 @@ static OnlineSchedule ComputeOnlineSchedule(int nsamp, int T, int length, int sh
   return s;
 }
 
-static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int32_t *nsamp, int n, bool online = false) {
+// `fill`, when given, writes utterance u's samples straight into the pinned staging area (rs_decode_wavs reads the files
+// there: no intermediate copy); pcm[] is then unused.
+using FillFn = std::function<void(int, int16_t *)>;
+static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int32_t *nsamp, int n, bool online = false,
+                            const FillFn *fill = nullptr) {
   ModelImpl *mi = d->model;
   const Model &m = mi->m;
   const Plan &pl = m.plan;
@@ -1364,7 +1372,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double hp0 = now_ms();
   for (int i = 0; i < n; i++)
-    if (nsamp[i] < 0 || (nsamp[i] > 0 && !pcm[i])) RS_FAIL("utterance " << i << ": bad sample buffer");
+    if (nsamp[i] < 0 || (nsamp[i] > 0 && !fill && !pcm[i])) RS_FAIL("utterance " << i << ": bad sample buffer");
   const int sf = m.frame_subsampling_factor, D = m.mfcc.num_ceps;
   const int shift = m.mfcc.WindowShift(), length = m.mfcc.WindowSize();
   auto &B = d->batch;
@@ -1433,7 +1441,7 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   // from the caller's buffer; anything else is first packed into the decoder's own pinned staging area.
   const int16_t *direct_base = nullptr;
   {
-    bool contiguous = total_samples > 0;
+    bool contiguous = total_samples > 0 && !fill;
     const int16_t *base = nullptr;
     for (int u = 0; u < n && contiguous; u++) {
       if (!nsamp[u]) continue;
@@ -1460,10 +1468,20 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     }
     range_begin[n_items] = n;
   }
+  std::string pack_err;  // a failing file read must not escape a staging thread
+  std::mutex pack_err_mu;
   auto pack = [&](int w) {
     if (direct_base) return;
-    for (int u = range_begin[w]; u < range_begin[w + 1]; u++)
-      if (nsamp[u]) memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
+    try {
+      for (int u = range_begin[w]; u < range_begin[w + 1]; u++)
+        if (nsamp[u]) {
+          if (fill) (*fill)(u, hpcm + pcm_offset[u]);
+          else memcpy(hpcm + pcm_offset[u], pcm[u], sizeof(int16_t) * (size_t)nsamp[u]);
+        }
+    } catch (const std::exception &e) {
+      std::lock_guard<std::mutex> lk(pack_err_mu);
+      if (pack_err.empty()) pack_err = e.what();
+    }
   };
   const bool pooled = n_items > 1;
   if (pooled && !d->pool) {
@@ -1548,6 +1566,13 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     }
   }
   CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  {
+    std::lock_guard<std::mutex> lk(pack_err_mu);
+    if (!pack_err.empty()) {
+      CUDA_OK(cudaStreamSynchronize(d->stream));
+      RS_FAIL(pack_err);
+    }
+  }
   const double hp1 = now_ms();
   d->last.h2d_bytes = pcm_bytes + desc_ints * sizeof(int);
   // ---- stage (i)
@@ -1845,47 +1870,75 @@ static rs_result *DecodeLoglikes(DecoderImpl *d, const float *const *ll, const i
   return r;
 }
 
-// RIFF/WAVE PCM16 reader (kaldi/src/feat/wave-reader.cc:153-320): mono, 16-bit, no scaling.
-static void ReadWav(const std::string &path, float expect_rate, std::vector<int16_t> *out) {
-  std::ifstream f(path, std::ios::binary);
-  if (!f) RS_FAIL("cannot open " << path);
-  std::stringstream ss;
-  ss << f.rdbuf();
-  const std::string b = ss.str();
-  if (b.size() < 12 || b.compare(0, 4, "RIFF") || b.compare(8, 4, "WAVE")) RS_FAIL(path << ": not a RIFF/WAVE file");
-  size_t p = 12;
+// RIFF/WAVE PCM16 reader (kaldi/src/feat/wave-reader.cc:153-320): mono, 16-bit, no scaling.  Two steps so that a batch of
+// files is read by several threads straight into the pinned staging area: WavOpen walks the chunk headers and validates
+// the format, WavFile::Read copies the samples.
+struct WavFile {
+  int fd = -1;
+  long long data_off = 0;
+  int n_samples = 0;
+  WavFile() = default;
+  WavFile(const WavFile &) = delete;
+  WavFile(WavFile &&o) noexcept : fd(o.fd), data_off(o.data_off), n_samples(o.n_samples) { o.fd = -1; }
+  ~WavFile() {
+    if (fd >= 0) close(fd);
+  }
+  void Read(const std::string &path, int16_t *dst) const {
+    size_t want = sizeof(int16_t) * (size_t)n_samples, got = 0;
+    while (got < want) {
+      const ssize_t k = pread(fd, reinterpret_cast<char *>(dst) + got, want - got, data_off + (long long)got);
+      if (k <= 0) RS_FAIL(path << ": read error");
+      got += (size_t)k;
+    }
+  }
+};
+
+static WavFile WavOpen(const std::string &path, float expect_rate) {
+  WavFile w;
+  w.fd = open(path.c_str(), O_RDONLY);
+  if (w.fd < 0) RS_FAIL("cannot open " << path);
+  struct stat st;
+  if (fstat(w.fd, &st) != 0) RS_FAIL("cannot stat " << path);
+  const long long size = st.st_size;
+  unsigned char hdr[12];
+  if (size < 12 || pread(w.fd, hdr, 12, 0) != 12 || memcmp(hdr, "RIFF", 4) || memcmp(hdr + 8, "WAVE", 4))
+    RS_FAIL(path << ": not a RIFF/WAVE file");
+  long long p = 12;
   int channels = 0, bits = 0, fmt = 0;
   uint32_t rate = 0;
   bool have_fmt = false;
-  while (p + 8 <= b.size()) {
-    std::string id = b.substr(p, 4);
+  while (p + 8 <= size) {
+    unsigned char ch[8];
+    if (pread(w.fd, ch, 8, p) != 8) RS_FAIL(path << ": read error");
     uint32_t sz;
-    memcpy(&sz, b.data() + p + 4, 4);
+    memcpy(&sz, ch + 4, 4);
     p += 8;
-    if (id == "fmt ") {
-      if (p + 16 > b.size()) RS_FAIL(path << ": truncated fmt chunk");
+    if (!memcmp(ch, "fmt ", 4)) {
+      unsigned char f[16];
+      if (p + 16 > size || pread(w.fd, f, 16, p) != 16) RS_FAIL(path << ": truncated fmt chunk");
       uint16_t v16;
-      memcpy(&v16, b.data() + p, 2);
+      memcpy(&v16, f, 2);
       fmt = v16;
-      memcpy(&v16, b.data() + p + 2, 2);
+      memcpy(&v16, f + 2, 2);
       channels = v16;
-      memcpy(&rate, b.data() + p + 4, 4);
-      memcpy(&v16, b.data() + p + 14, 2);
+      memcpy(&rate, f + 4, 4);
+      memcpy(&v16, f + 14, 2);
       bits = v16;
       have_fmt = true;
-    } else if (id == "data") {
+    } else if (!memcmp(ch, "data", 4)) {
       if (!have_fmt) RS_FAIL(path << ": data chunk before fmt chunk");
       if (fmt != 1 || bits != 16) RS_FAIL(path << ": only 16-bit PCM WAVE files are supported");
       if (channels != 1) RS_FAIL(path << ": only mono WAVE files are supported (got " << channels << " channels)");
       if ((float)rate != expect_rate)
         RS_FAIL(path << ": sampling frequency mismatch, expected " << expect_rate << ", got " << rate);
-      size_t n = std::min<size_t>(sz, b.size() - p);
-      if (sz == 0xffffffffu || sz == 0) n = b.size() - p;  // streamed headers
-      out->resize(n / 2);
-      if (n / 2) memcpy(out->data(), b.data() + p, (n / 2) * 2);
-      return;
+      long long n = std::min<long long>(sz, size - p);
+      if (sz == 0xffffffffu || sz == 0) n = size - p;  // streamed headers
+      if (n / 2 > 0x7fffffff) RS_FAIL(path << ": too long");
+      w.data_off = p;
+      w.n_samples = (int)(n / 2);
+      return w;
     }
-    p += sz + (sz & 1);
+    p += (long long)sz + (sz & 1);
   }
   RS_FAIL(path << ": no data chunk");
 }
@@ -1908,15 +1961,19 @@ int rs_decode_wavs(rs_decoder *d_, const char *const *paths, int32_t n, rs_resul
   API_GUARD_BEGIN
   DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
   if (!d || !out) RS_FAIL("rs_decode_wavs: null argument");
-  std::vector<std::vector<int16_t>> data(n);
-  std::vector<const int16_t *> ptrs(n);
+  if (n < 0 || (n && !paths)) RS_FAIL("rs_decode_wavs: bad argument");
+  // headers first (sizes fix the batch layout), then the staging threads read the samples into pinned memory
+  std::vector<WavFile> files;
+  files.reserve(n);
+  std::vector<const int16_t *> ptrs(n, nullptr);
   std::vector<int32_t> ns(n);
   for (int i = 0; i < n; i++) {
-    ReadWav(paths[i], d->model->m.mfcc.samp_freq, &data[i]);
-    ptrs[i] = data[i].data();
-    ns[i] = (int32_t)data[i].size();
+    if (!paths[i]) RS_FAIL("rs_decode_wavs: path " << i << " is NULL");
+    files.push_back(WavOpen(paths[i], d->model->m.mfcc.samp_freq));
+    ns[i] = files[i].n_samples;
   }
-  *out = DecodePcm(d, ptrs.data(), ns.data(), n);
+  const FillFn fill = [&](int u, int16_t *dst) { files[u].Read(paths[u], dst); };
+  *out = DecodePcm(d, ptrs.data(), ns.data(), n, false, &fill);
   return 0;
   API_GUARD_END(1)
 }

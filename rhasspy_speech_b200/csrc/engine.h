@@ -164,6 +164,7 @@ struct DecodeConfig {
   int profile;      // debug: block 0 prints its per-phase clock counts (RS_B200_DECODE_PROFILE=1)
   int smem_slots;   // > 0: state tables in shared memory, addressed by state id (power of two >= num_states)
   float lattice_beam;  // lattice mode: links worse than their destination by more than this are not recorded
+  int small_cache_arcs, small_ll_stage;  // decode_small.cu: arcs / log-likelihood rows staged in shared memory
 };
 
 struct LaneWorkspace {  // one per resident CTA; all pointers are device memory

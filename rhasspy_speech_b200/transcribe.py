@@ -507,10 +507,15 @@ class KaldiNnet3WavTranscriber(_Base):
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
         parts = await asyncio.gather(*[loop.run_in_executor(None, run, eng, idx) for eng, idx in zip(engines, shares)])
         out: List[Optional[List[str]]] = [None] * len(paths)
+        fuzzy = (Path(lang_dir) / "G.fuzzy.fst").exists()       # one stat for the whole list
         for eng, idx, (hyp, graph) in zip(engines, shares, parts):
             for k, i in enumerate(idx):
                 check_status(int(hyp.status[k]), "online2-wav-nnet3-latgen-faster")
-                out[i] = await self._finish(eng, nbest_text(hyp, k), lang_dir, max_fuzzy_cost, require_fuzzy, graph)
+                if fuzzy or require_fuzzy:
+                    out[i] = await self._finish(eng, nbest_text(hyp, k), lang_dir, max_fuzzy_cost, require_fuzzy, graph)
+                else:       # no fuzzy matcher in play: word ids -> text without the detour over the text archive
+                    out[i] = [decode_meta(eng.words(words, graph)) for words, _, _ in (hyp.nbest[k] if hyp.words[k] is not None else [])
+                              if words]
         return out  # type: ignore[return-value]
 
     async def async_transcribe_rescore(self, *args, **kwargs):
