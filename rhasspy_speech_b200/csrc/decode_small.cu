@@ -27,7 +27,7 @@ namespace rs {
 
 namespace {
 
-constexpr int kNT = 512;
+constexpr int kNT = 256;
 constexpr int kNW = kNT / 32;
 constexpr int kSlots = 1024;         // >= kSmallMaxStates
 constexpr int kItems = kSlots / kNT; // list items per thread in the blocked scans
@@ -516,40 +516,7 @@ __global__ void __launch_bounds__(kNT) decode_small_kernel(const __grid_constant
             unsigned inside = 0, total;
             for (int i = tid; i < n_cur; i += kNT) inside += cost[i] <= beam_cutoff ? 1u : 0u;
             X.scan_sum(inside, &total);
-            if ((int)total > cfg.min_active) {
-              min_active_cutoff = beam_cutoff;
-            } else {
-              // the min_active-th smallest cost lies among the few tokens beyond the beam: rank (min_active - inside)
-              // among those, ordered by (cost, index) -- the ranking kth() computes, over a compacted list
-              float *oc = reinterpret_cast<float *>(S.pfx2);
-              int *oi = reinterpret_cast<int *>(S.pfx2) + 512;
-              if (tid == 0) S.n_new = 0;
-              __syncthreads();
-              for (int i = tid; i < n_cur; i += kNT)
-                if (cost[i] > beam_cutoff) {
-                  const int j = atomicAdd(&S.n_new, 1);
-                  if (j < 512) {
-                    oc[j] = cost[i];
-                    oi[j] = i;
-                  }
-                }
-              __syncthreads();
-              const int m = S.n_new, target = cfg.min_active - (int)total;
-              if (m > 512) {
-                min_active_cutoff = kth(cfg.min_active);
-              } else {
-                for (int j = tid; j < m; j += kNT) {
-                  const float c = oc[j];
-                  const int ci = oi[j];
-                  int r = 0;
-                  for (int l = 0; l < m; l++) r += (oc[l] < c || (oc[l] == c && oi[l] < ci)) ? 1 : 0;
-                  if (r == target) S.kth = c;
-                }
-                __syncthreads();
-                min_active_cutoff = S.kth;
-                __syncthreads();
-              }
-            }
+            min_active_cutoff = (int)total > cfg.min_active ? beam_cutoff : kth(cfg.min_active);
           }
         }
         if (min_active_cutoff > beam_cutoff) {

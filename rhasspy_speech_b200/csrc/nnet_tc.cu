@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   constexpr bool kStatic = PAT >= 0;
   constexpr int kT0 = kStatic ? ((PAT >> 0) & 15) - 1 : -1, kT1 = kStatic ? ((PAT >> 4) & 15) - 1 : -1;
   constexpr int kT2 = kStatic ? ((PAT >> 8) & 15) - 1 : -1, kT3 = kStatic ? ((PAT >> 12) & 15) - 1 : -1;
+  constexpr bool kPairLoads = PAT == 0;  // no tail ops (the 2048 -> 128 bottleneck layers)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
@@ -384,16 +385,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         cnt_par ^= 1u << set;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn + h * 64);
+        if constexpr (kPairLoads) {
+          // two TMEM loads in flight per wait (the load -> wait round trip, not the adds, bounds the fold); only where
+          // the tail leaves the registers for 64 raw values (measured with spills on the BatchNorm / bypass patterns)
 #pragma unroll
-        for (int jc = 0; jc < kTcChunks; jc++)
-          if (h * 64 + jc * 32 < p.bn) {
-            uint32_t raw[32];
-            tmem_ld32_nowait(taddr + jc * 32, raw);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int jc = 0; jc < kTcChunks; jc += 2)
+            if (h * 64 + jc * 32 < p.bn) {
+              uint32_t raw0[32], raw1[32];
+              const bool two = h * 64 + (jc + 1) * 32 < p.bn;
+              tmem_ld32_nowait(taddr + jc * 32, raw0);
+              if (two) tmem_ld32_nowait(taddr + (jc + 1) * 32, raw1);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 32; j += 2)
-              add2(acc[jc * 32 + j], acc[jc * 32 + j + 1], __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
-          }
+              for (int j = 0; j < 32; j += 2)
+                add2(acc[jc * 32 + j], acc[jc * 32 + j + 1], __uint_as_float(raw0[j]), __uint_as_float(raw0[j + 1]));
+              if (two) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2)
+                  add2(acc[(jc + 1) * 32 + j], acc[(jc + 1) * 32 + j + 1], __uint_as_float(raw1[j]), __uint_as_float(raw1[j + 1]));
+              }
+            }
+        } else {
+#pragma unroll
+          for (int jc = 0; jc < kTcChunks; jc++)
+            if (h * 64 + jc * 32 < p.bn) {
+              uint32_t raw[32];
+              tmem_ld32_nowait(taddr + jc * 32, raw);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 32; j += 2)
+                add2(acc[jc * 32 + j], acc[jc * 32 + j + 1], __uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
+            }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sete_bar(bsel));
