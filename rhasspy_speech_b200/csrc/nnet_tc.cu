@@ -28,6 +28,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -80,6 +81,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
+}
+// one lane of a converged warp (the same lane on every call)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -230,6 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       // ------------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      long long prof_wait = 0, prof_t0 = clock64();
       bool uniform = true;
       for (int s = 1; s < p.n_slabs; s++) uniform = uniform && p.slabs[s].kblocks == p.slabs[0].kblocks;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -248,7 +260,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             while (kb >= p.slabs[s].kblocks) kb -= p.slabs[s++].kblocks;
           }
           const TcSlab sl = p.slabs[s];
+          long long tw0 = p.profile ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (p.profile) prof_wait += clock64() - tw0;
           const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, fb = full_bar(stage);
           mbar_expect_tx(fb, stage_bytes);
           tma_load_2d(sa, &p.a_hi[s], kb * kTcBK, m0 + sl.yshift, fb);
@@ -261,24 +275,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           }
         }
       }
+      if (p.profile && blockIdx.x == 0)
+        printf("gemm_tc profile (n=%d k-blocks/tile=%d tiles=%d): TMA thread total %lld clk, waiting for a free stage %lld\n", p.n, total_kb,
+               num_tiles, clock64() - prof_t0, prof_wait);
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
+      // (Measured, RS_B200_TC_PROFILE: this thread spends 60-75 % of the kernel outside any wait.  Walking the loop with
+      // the whole warp and issuing from an elected lane removes the ELECT + R2UR sequences in front of every UTCHMMA but
+      // not the time: the MMA issue itself blocks -- three MMAs per K step read 24 KB of operands from shared memory
+      // next to 16 KB of TMA writes, and the tile is bound by that traffic, not by the tensor pipe.)
+      constexpr bool leader = true;
       // instruction descriptor: D fp32, A/B fp16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, kbc = 0;  // kbc: K blocks issued so far; physical main set = kbc & 1
       uint32_t use_par = 0;         // bit b: parity of the number of blocks committed on barrier pair b = group * 2 + set
       int last_b[2] = {-1, -1};     // barrier pair of the block that last occupied each physical set
+      long long prof_full = 0, prof_sete = 0, prof_cross = 0, prof_t0 = clock64();
       constexpr int fold = kTcFold;
       uint32_t tcount = 0;  // tiles issued so far: cross accumulator = tcount & 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
         const uint32_t d_cross = tmem_base + (uint32_t)((2 + (tcount & 1)) * p.bn);
-        mbar_wait(crosse_bar(tcount & 1), ((tcount >> 1) & 1u) ^ 1u);
+        {
+          const long long tw0 = p.profile ? clock64() : 0;
+          mbar_wait(crosse_bar(tcount & 1), ((tcount >> 1) & 1u) ^ 1u);
+          if (p.profile) prof_cross += clock64() - tw0;
+        }
         for (int kb = 0; kb < total_kb; kb++) {
-          mbar_wait(full_bar(stage), phase);
+          {
+            const long long tw0 = p.profile ? clock64() : 0;
+            mbar_wait(full_bar(stage), phase);
+            if (p.profile) prof_full += clock64() - tw0;
+          }
           tc_fence_after();
           const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
           const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kStageABytes);
@@ -288,16 +319,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < kTcBK / 16; k++) {  // 16 fp16 = 32 bytes per step inside the swizzle atom
             const int set = kbc & 1, bsel = (int)(tcount & 1) * 2 + set;
-            if (k % fold == 0 && last_b[set] >= 0)
+            if (k % fold == 0 && last_b[set] >= 0) {
+              const long long tw0 = p.profile ? clock64() : 0;
               mbar_wait(sete_bar(last_b[set]), ((use_par >> last_b[set]) & 1u) ^ 1u);  // set drained
+              if (p.profile) prof_sete += clock64() - tw0;
+            }
             const uint32_t d_main = tmem_base + (uint32_t)(set * p.bn);
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k % fold != 0 ? 1u : 0u);
-            tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-            tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
-            if (k == kTcBK / 16 - 1) tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+            if (leader) {
+              tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, k % fold != 0 ? 1u : 0u);
+              tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+              if (k == kTcBK / 16 - 1) tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+            }
             if (k % fold == fold - 1) {
-              tc_commit(setf_bar(bsel));  // this partial sum (and, on the last one, the cross sum) complete
+              if (leader) tc_commit(setf_bar(bsel));  // this partial sum (and, on the last one, the cross sum) complete
               use_par ^= 1u << bsel;
               last_b[set] = bsel;
               kbc++;
@@ -309,6 +345,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           }
         }
       }
+      if (p.profile && blockIdx.x == 0 && leader)
+        printf("gemm_tc profile: MMA thread total %lld clk, waiting for operands %lld, for a drained accumulator %lld, for the cross accumulator %lld\n",
+               clock64() - prof_t0, prof_full, prof_sete, prof_cross);
     }
     __syncwarp();
   }
@@ -324,6 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     // this warp's 32 x 32 fp32 staging tile (float4 columns XOR-swizzled by row: conflict-free both ways)
     float4 *stg = reinterpret_cast<float4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 4) * 4096u);
     uint32_t tcount = group;  // local index of this group's current tile: K-block ring position = tcount * total_kb
+    long long prof_setf = 0, prof_fold = 0, prof_tail = 0, prof_t0 = clock64();
     uint32_t cnt_par = 0;     // bit s: parity of the number of blocks this group has taken from physical set s
     int ib = -1;  // the op whose split bypass input is prefetched (first kAddScaled with a split source)
     for (int i = 0; i < p.n_ops && ib < 0; i++)
@@ -381,7 +421,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       for (int kb = 0; kb < total_sums; kb++, kbc++) {
         if (kb == total_sums - 1 && ib >= 0) prefetch(0);
         const int set = kbc & 1, bsel = group * 2 + set;
+        long long tw0 = p.profile ? clock64() : 0;
         mbar_wait(setf_bar(bsel), (cnt_par >> set) & 1u);
+        if (p.profile) {
+          const long long now = clock64();
+          prof_setf += now - tw0;
+          tw0 = now;
+        }
         cnt_par ^= 1u << set;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * p.bn + h * 64);
@@ -420,7 +466,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sete_bar(bsel));
+        if (p.profile) prof_fold += clock64() - tw0;
       }
+      const long long tail0 = p.profile ? clock64() : 0;
       {  // the tile's cross sum: acc += cross * 2^-11 (the last block's commit covers it)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 + (tcount & 1)) * p.bn + h * 64);
 #pragma unroll
@@ -627,7 +675,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         }
         __syncwarp();
       }
+      if (p.profile) prof_tail += clock64() - tail0;
     }
+    if (p.profile && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 8))
+      printf("gemm_tc profile: epilogue warp %d total %lld clk, waiting for partial sums %lld, folding %lld, cross fold + tail %lld\n", warp,
+             clock64() - prof_t0, prof_setf, prof_fold, prof_tail);
   }
   tc_fence_before();
   __syncthreads();
@@ -731,6 +783,8 @@ void TcConfigure(TcParams *p) {
   int cols = 32;
   while (cols < 4 * p->bn) cols <<= 1;
   p->tmem_cols = cols;
+  static const int prof = getenv("RS_B200_TC_PROFILE") != nullptr;
+  p->profile = prof;
   p->tiles_m = (p->m + kTcBM - 1) / kTcBM;
   p->tiles_n = (p->n + p->bn - 1) / p->bn;
 }

@@ -32,6 +32,7 @@ struct TcParams {
   int n_slabs;
   int bn;         // output columns per tile = UMMA N (multiple of 32, <= kTcMaxBN)
   int stages;     // smem pipeline depth
+  int profile;    // RS_B200_TC_PROFILE: block 0 prints where its TMA / MMA / epilogue threads spent their clocks
   int tmem_cols;  // power of two >= 4 * bn (two K-block accumulator pairs)
   int tiles_m, tiles_n;
   void *out_hi, *out_lo;  // out_lo == nullptr: plain fp32 output at out_hi, else two fp16 planes

@@ -22,6 +22,7 @@ def run(name, dec, fn, audio_s, reps=4):
     flags = {int(s): int((np.asarray(hyp.status) == s).sum()) for s in set(int(x) for x in hyp.status)}
     out = {"config": name, "audio_s": audio_s, "rtfx_device": audio_s / (dev / 1e3), "rtfx_e2e": audio_s / float(np.mean(wall)),
            "wall_ms": float(np.mean(wall)) * 1e3, "stages_ms": t, "status_counts": flags,
+           "strict_host_decoder": {"utterances": int(ts[-1]["strict_utts"]), "ms": float(np.mean([x["strict_ms"] for x in ts]))},
            "tokens_per_frame": ts[-1]["tokens_expanded"] / max(1, ts[-1]["frames_decoded"])}
     if ts[-1]["lattice_arcs"]:
         out["lattice"] = {k: ts[-1][k] for k in ("lattice_states", "lattice_arcs", "lattice_links_recorded", "d2h_bytes")}
@@ -50,7 +51,7 @@ def main():
             p = synth.write_model(os.path.join(tmp, "m%d" % i), spec)
             decs.append(_lib.Decoder(_lib.Model(p.final_mdl, p.online_conf, 0), _lib.Graph(p.hclg, p.words_txt, 0),
                                      max_tokens_per_utt=1 << 20))
-        utts = synth.make_utterances(256, seed=1234)
+        utts = synth.make_utterances(256, seed=1234, pool=synth.load_pool())
         parts = [utts[i::len(decs)] for i in range(len(decs))]
         audio_s = sum(len(u) for u in utts) / 16000.0
 
@@ -88,7 +89,7 @@ def main():
         import rhasspy_speech_b200 as pkg
         p = synth.write_model(os.path.join(tmp, "gram"), synth.ZAMIA_LIKE)
         st = pkg.KaldiNnet3StreamTranscriber(p.model_dir, os.path.dirname(p.hclg), None)
-        utts64 = synth.make_utterances(64, seed=4321)
+        utts64 = synth.make_utterances(64, seed=4321, pool=synth.load_pool())
         raws = [np.asarray(u, dtype="<i2").tobytes() for u in utts64]
 
         async def chunks(raw):
@@ -118,7 +119,7 @@ def main():
         # decode_kernel (+ lattice_prune_kernel), wall - total covers the host search
         p = synth.write_model(os.path.join(tmp, "gram"), synth.ZAMIA_LIKE)
         dec = _lib.Decoder(_lib.Model(p.final_mdl, p.online_conf, 0), _lib.Graph(p.hclg, p.words_txt, 0))
-        utts = synth.make_utterances(256, seed=1234)
+        utts = synth.make_utterances(256, seed=1234, pool=synth.load_pool())
         audio_s = sum(len(u) for u in utts) / 16000.0
         for n in (1, 5):
             dec.set_nbest(n)
@@ -127,21 +128,26 @@ def main():
     # config 3: zamia-like model, ARPA-shaped graph
     spec = dataclasses.replace(synth.ZAMIA_LIKE, name="zamia_arpa", graph="arpa", vocab_size=2000, bigrams_per_word=20, eps_hops=2)
     p = synth.write_model(os.path.join(tmp, "arpa"), spec)
-    utts = synth.make_utterances(256, seed=1234)
+    utts = synth.make_utterances(256, seed=1234, pool=synth.load_pool())
     for i in range(0, 256, 10):
         utts[i] = utts[i][::-1].copy()          # out-of-grammar audio: time-reversed
     m = _lib.Model(p.final_mdl, p.online_conf, 0)
     g = _lib.Graph(p.hclg, p.words_txt, 0)
-    dec = _lib.Decoder(m, g)
     audio_s = sum(len(u) for u in utts) / 16000.0
-    run("3: ARPA-shaped HCLG (%d states, %d arcs), batch 256, 10%% reversed audio" % (g.num_states, g.num_arcs), dec,
-        lambda: dec.decode_pcm(utts), audio_s)
+    # the device search alone (order-sensitive utterances only flagged), then with the strict-order host decoder on
+    dec0 = _lib.Decoder(m, g, strict_fallback=0, max_tokens_per_utt=1 << 21)
+    run("3 (device search only, flags not resolved): ARPA-shaped HCLG (%d states, %d arcs), batch 256, 10%% reversed audio"
+        % (g.num_states, g.num_arcs), dec0, lambda: dec0.decode_pcm(utts), audio_s, reps=3)
+    del dec0
+    dec = _lib.Decoder(m, g, max_tokens_per_utt=1 << 21)
+    run("3: ARPA-shaped HCLG (%d states, %d arcs), batch 256, 10%% reversed audio; order-sensitive utterances re-decoded by the "
+        "strict-order host decoder" % (g.num_states, g.num_arcs), dec, lambda: dec.decode_pcm(utts), audio_s, reps=3)
     # config 4: 64 streams, 80 ms chunks, grammar graph, online schedule
     p2 = synth.write_model(os.path.join(tmp, "gram"), synth.ZAMIA_LIKE)
     m2 = _lib.Model(p2.final_mdl, p2.online_conf, 0)
     g2 = _lib.Graph(p2.hclg, p2.words_txt, 0)
     dec2 = _lib.Decoder(m2, g2)
-    utts64 = synth.make_utterances(64, seed=4321)
+    utts64 = synth.make_utterances(64, seed=4321, pool=synth.load_pool())
     raws = [np.asarray(u, dtype="<i2").tobytes() for u in utts64]
     streams = [dec2.open_stream() for _ in utts64]
 
