@@ -32,6 +32,7 @@ struct TcParams {
   int n_slabs;
   int bn;         // output columns per tile = UMMA N (multiple of 32, <= kTcMaxBN)
   int stages;     // smem pipeline depth
+  int fold;       // main MMAs (K = 16 each) accumulated inside TMEM per published partial sum: 1, 2 or 4 (nnet_tc.cu)
   int profile;    // RS_B200_TC_PROFILE: block 0 prints where its TMA / MMA / epilogue threads spent their clocks
   int tmem_cols;  // power of two >= 4 * bn (two K-block accumulator pairs)
   int tiles_m, tiles_n;
@@ -54,5 +55,7 @@ void TcPackWeights(const float *w, int n, int ktot, const std::vector<std::pair<
                    std::vector<__half> *hi, std::vector<__half> *lo, std::vector<int> *k0, int *kp);
 void TcConfigure(TcParams *p);  // fills stages / tmem_cols / tiles_* from bn, m, n
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream);
+// second-generation kernel (nnet_tc2.cu): separate fold and tail warps
+void LaunchGemmTc2(const TcParams &p, int num_sms, int smem_limit, cudaStream_t stream);
 
 }  // namespace rs
