@@ -667,10 +667,15 @@ void TcConfigure(TcParams *p) {
   int cols = 32;
   while (cols < 4 * p->bn) cols <<= 1;
   p->tmem_cols = cols;
-  static const int prof = getenv("RS_B200_TC_PROFILE") != nullptr;
+  static const int prof = getenv("RS_B200_TC_PROFILE") ? atoi(getenv("RS_B200_TC_PROFILE")) : 0;
   p->profile = prof;
   static const int fold_env = getenv("RS_B200_TC_FOLD") ? atoi(getenv("RS_B200_TC_FOLD")) : 0;
   p->fold = fold_env == 1 || fold_env == 2 || fold_env == 4 ? fold_env : kTcFold;
+  // short contractions (the 128 -> 1024 layers: K = 256) may use a different fold: few partial sums per output
+  static const int fold_short = getenv("RS_B200_TC_FOLD_SHORT") ? atoi(getenv("RS_B200_TC_FOLD_SHORT")) : 0;
+  int total_kb = 0;
+  for (int s = 0; s < p->n_slabs; s++) total_kb += p->slabs[s].kblocks;
+  if (total_kb <= 8 && (fold_short == 1 || fold_short == 2 || fold_short == 4)) p->fold = fold_short;
   p->tiles_m = (p->m + kTcBM - 1) / kTcBM;
   p->tiles_n = (p->n + p->bn - 1) / p->bn;
 }

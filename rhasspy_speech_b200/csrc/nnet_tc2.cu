@@ -6,19 +6,24 @@
 //
 //   warp 0        TMA producer      (one lane)
 //   warp 1        MMA issuer        (one lane)
-//   warps 4..7    FOLD warps        a thread owns one output row and the 128 fp32 running sums of the tile; every
-//                                   published partial sum is tcgen05.ld-ed and added; at the end of the tile the
-//                                   cross accumulator is updated IN PLACE in TMEM to  sum + cross * 2^-11
-//                                   (tcgen05.st) and handed to the tail warps -- the fold warps go straight on to
-//                                   the next tile
-//   warps 8..15   TAIL warps        two per TMEM lane quadrant, each takes two 32-column chunks of the finished
-//                                   tile out of TMEM and runs ReLU / BatchNorm / bypass / split / store on them
+//   warps 4..7    FOLD warps        one per TMEM lane quadrant; a thread owns one output row and the 128 fp32 running
+//                                   sums of the tile; every published partial sum is tcgen05.ld-ed and added; at the
+//                                   end of the tile the cross accumulator is updated IN PLACE in TMEM to
+//                                   sum + cross * 2^-11  (tcgen05.st) and handed to the tail warps -- the fold warps
+//                                   go straight on to the next tile
+//   warps 8..15   TAIL warps        two per TMEM lane quadrant: each takes two 32-column chunks of the finished tile
+//                                   out of TMEM and runs ReLU / BatchNorm / bypass / split / store on them; the global
+//                                   inputs of the next chunk are requested while the current one is finished
+// (Measured: eight fold warps of 64 columns each + four tail warps: the K = 2048 layers do not change, 104 vs 103 us --
+//  they are not fold-bound -- and the 128 -> 1024 layers become tail-bound, 162-177 vs 146-155 us.)
 //
 // In gemm_tc_kernel the eight epilogue warps held the running sums AND ran the tail: 232 registers were not
 // enough (spills), the tail was unrolled four times (a 420 KB kernel, 14 % of the stalls were instruction
 // fetches), and with two warps per scheduler only 29 % of the issue slots were used (profiles/r2_gemm_details.txt).
 // Here the tail is one chunk long and loops, per-column vectors are warp-uniform 16-byte loads instead of
-// shuffles, and every scheduler has one fold warp and two tail warps to pick from.
+// shuffles.  Measured on the way (tools/ubench): a tcgen05.ld x32 round trip is ~160 clk and a second load in
+// flight adds ~70; the MMA rate in this operand pattern is 71 clk per 128x128x16 MMA alone and 90-110 with
+// concurrent shared-memory writes; FADD2 / FFMA2 have the result rate of FADD / FFMA (half the issue slots).
 #include <cuda.h>
 
 #include <cstdio>
@@ -63,15 +68,41 @@ __device__ __forceinline__ void split2x(float x0, float x1, uint32_t &hi, uint32
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
 }
 
+// {a0 * b0 + c0, a1 * b1 + c1}, one rounding each (FFMA2)
+__device__ __forceinline__ void fma2(float &a0, float &a1, float b0, float b1, float c0, float c1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+
 }  // namespace
 
 // PAT >= 0: the op sequence is a compile-time constant (4 bits per op: EpiOp::Type + 1, first op in the low
 // bits); PAT < 0: run-time op list.  FULL: bn == 128 and n % 128 == 0 (no column guards anywhere).
-template <int PAT, bool FULL>
+// PROF (RS_B200_TC_PROFILE=1, the two hot instantiations only): block 0 prints where each role spent its clocks.
+template <int PAT, bool FULL, bool PROF = false>
 __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  // mbarrier wait that adds the waiting time to a counter in the profiling build
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, long long &acc) {
+    if constexpr (PROF) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      acc += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  long long prof_t0 = 0, prof_a = 0, prof_b = 0, prof_c = 0;
+  if constexpr (PROF) prof_t0 = clock64();
   constexpr bool kStatic = PAT >= 0;
   constexpr int kTypes[4] = {kStatic ? ((PAT >> 0) & 15) - 1 : -1, kStatic ? ((PAT >> 4) & 15) - 1 : -1,
                              kStatic ? ((PAT >> 8) & 15) - 1 : -1, kStatic ? ((PAT >> 12) & 15) - 1 : -1};
+  // index of the (first) BatchNorm scale / offset op of a static list
+  constexpr int kSoIdx = kTypes[0] == EpiOp::kScaleOffset ? 0 : kTypes[1] == EpiOp::kScaleOffset ? 1 : kTypes[2] == EpiOp::kScaleOffset ? 2
+                         : kTypes[3] == EpiOp::kScaleOffset ? 3 : -1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
@@ -87,6 +118,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
   auto xfull_bar = [&](uint32_t a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 4 + a); }; // finished tile in TMEM
   auto xfree_bar = [&](uint32_t a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 6 + a); }; // ... taken by the tail warps
   const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 8);
+  // [2][128] floats: the bias slice of the fold warps' next tile (16-byte aligned: bar0 is, and the barrier block is 8 * even)
+  float *bias_s = reinterpret_cast<float *>(smem_raw + (bar0 - smem_u32(smem_raw)) + 8u * (uint32_t)(2 * p.stages + 10));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -146,7 +179,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
               while (kb >= p.slabs[s].kblocks) kb -= p.slabs[s++].kblocks;
             }
             const TcSlab sl = p.slabs[s];
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            timed_wait(empty_bar(stage), phase ^ 1u, prof_a);
             const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, fb = full_bar(stage);
             mbar_expect_tx(fb, stage_bytes);
             tma_load_2d(sa, &p.a_hi[s], kb * kTcBK, m0 + sl.yshift, fb);
@@ -159,6 +192,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
             }
           }
         }
+        if (PROF && blockIdx.x == 0)
+          printf("tc2 profile (n=%d k-blocks/tile=%d tiles=%d): TMA thread total %lld clk, waiting for a free stage %lld\n", p.n, total_kb,
+                 num_tiles, clock64() - prof_t0, prof_a);
       }
       __syncwarp();
     } else if (warp == 1) {
@@ -171,10 +207,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
           const uint32_t xb = tcount & 1u;
           const uint32_t d_cross = tmem_base + (2u + xb) * (uint32_t)p.bn;
-          mbar_wait(xfree_bar(xb), ((tcount >> 1) & 1u) ^ 1u);  // the tail warps have taken the tile before last
+          timed_wait(xfree_bar(xb), ((tcount >> 1) & 1u) ^ 1u, prof_c);  // the tail warps have taken the tile before last
           tc_fence_after();
           for (int kb = 0; kb < total_kb; kb++) {
-            mbar_wait(full_bar(stage), phase);
+            timed_wait(full_bar(stage), phase, prof_a);
             tc_fence_after();
             const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
             const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kT2StageA);
@@ -184,7 +220,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
               const uint32_t set = fcount & 1u;
               const bool first = (k & (fold - 1)) == 0, last = (k & (fold - 1)) == fold - 1;
               if (first) {
-                mbar_wait(sete_bar(set), ((fcount >> 1) & 1u) ^ 1u);  // the fold warps have drained this accumulator
+                timed_wait(sete_bar(set), ((fcount >> 1) & 1u) ^ 1u, prof_b);  // the fold warps have drained this accumulator
                 tc_fence_after();
               }
               const uint32_t d_main = tmem_base + set * (uint32_t)p.bn;
@@ -204,12 +240,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
             }
           }
         }
+        if (PROF && blockIdx.x == 0)
+          printf("tc2 profile: MMA thread total %lld clk, waiting for operands %lld, for a drained accumulator %lld, for the tail warps %lld\n",
+                 clock64() - prof_t0, prof_a, prof_b, prof_c);
       }
       __syncwarp();
     }
   } else if (warp < 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ------------------------------------------------------------------ fold warps
+    // ------------------------------------------------------------------ fold warps: one per lane quadrant
     const int q = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t fcount = 0, tcount = 0;
@@ -217,11 +256,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
       const int n0 = (tile % p.tiles_n) * p.bn;
       float acc[kTcMaxBN];
       if (bias_first) {
-        const float *bias = p.ops[0].v0;
+        // the bias slice was staged in shared memory during the previous tile (one column per fold thread), so the
+        // start values cost 32 broadcast LDS instead of 32 L2 round trips at the head of the tile
+        const float *bs = bias_s + (tcount & 1u) * 128u;
+        if (tcount == 0) {
+          const int c = n0 + (int)threadIdx.x - 128;
+          bias_s[threadIdx.x - 128] = (int)threadIdx.x - 128 < p.bn && c < p.n ? __ldg(p.ops[0].v0 + c) : 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
 #pragma unroll
         for (int j = 0; j < kTcMaxBN; j += 4) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (FULL || j < p.bn) b = ldvec4<FULL>(bias, n0 + j, p.n);
+          const float4 b = *reinterpret_cast<const float4 *>(bs + j);
           acc[j] = b.x;
           acc[j + 1] = b.y;
           acc[j + 2] = b.z;
@@ -231,10 +276,16 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < kTcMaxBN; j++) acc[j] = 0.f;
       }
+      float bias_next = 0.f;  // this thread's column of the next tile's bias slice
+      const int next_tile = tile + (int)gridDim.x;
+      if (bias_first && next_tile < num_tiles) {
+        const int c = (next_tile % p.tiles_n) * p.bn + (int)threadIdx.x - 128;
+        if ((int)threadIdx.x - 128 < p.bn && c < p.n) bias_next = __ldg(p.ops[0].v0 + c);
+      }
 #pragma unroll 1
       for (int f = 0; f < total_sums; f++, fcount++) {
         const uint32_t set = fcount & 1u;
-        mbar_wait(setf_bar(set), (fcount >> 1) & 1u);
+        timed_wait(setf_bar(set), (fcount >> 1) & 1u, prof_a);
         tc_fence_after();
         const uint32_t taddr = lane_base + set * (uint32_t)p.bn;
         // two TMEM loads in flight per wait: the load -> wait round trip, not the adds, bounds a fold
@@ -243,9 +294,21 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
           if (!FULL && jc * 32 >= p.bn) break;
           uint32_t raw0[32], raw1[32];
           const bool two = FULL || (jc + 1) * 32 < p.bn;
+          long long tl0 = 0;
+          if constexpr (PROF) tl0 = clock64();
+          if constexpr (PROF) {
+            if (p.profile & 2) continue;  // experiment: no TMEM loads at all (results are garbage)
+          }
           tmem_ld32_nowait(taddr + jc * 32, raw0);
           if (two) tmem_ld32_nowait(taddr + (jc + 1) * 32, raw1);
           tmem_wait_ld();
+          if constexpr (PROF) prof_b += clock64() - tl0;
+          if constexpr (PROF) {
+            if (p.profile & 4) {  // experiment: loads but one add per load instead of 32
+              acc[jc * 32] += __uint_as_float(raw0[0]) + __uint_as_float(raw1[1]);
+              continue;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 2)
             add2(acc[jc * 32 + j], acc[jc * 32 + j + 1], __uint_as_float(raw0[j]), __uint_as_float(raw0[j + 1]));
@@ -255,31 +318,47 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
               add2(acc[(jc + 1) * 32 + j], acc[(jc + 1) * 32 + j + 1], __uint_as_float(raw1[j]), __uint_as_float(raw1[j + 1]));
           }
         }
+        long long ta0 = 0;
+        if constexpr (PROF) ta0 = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sete_bar(set));
+        if constexpr (PROF) prof_c += clock64() - ta0;
       }
       // the tile's cross sum (the last partial sum's commit covers it): X <- sum + cross * 2^-11, in place
       const uint32_t xb = tcount & 1u;
       const uint32_t xaddr = lane_base + (2u + xb) * (uint32_t)p.bn;
 #pragma unroll
-      for (int jc = 0; jc < 4; jc++) {
+      for (int jc = 0; jc < 4; jc += 2) {  // two chunks per round trip
         if (!FULL && jc * 32 >= p.bn) break;
-        uint32_t raw[32];
-        tmem_ld32_nowait(xaddr + jc * 32, raw);
+        uint32_t raw0[32], raw1[32];
+        const bool two = FULL || (jc + 1) * 32 < p.bn;
+        tmem_ld32_nowait(xaddr + jc * 32, raw0);
+        if (two) tmem_ld32_nowait(xaddr + (jc + 1) * 32, raw1);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j++) raw[j] = __float_as_uint(fmaf(__uint_as_float(raw[j]), 1.f / kSplitScale, acc[jc * 32 + j]));
-        tmem_st32(xaddr + jc * 32, raw);
+        for (int j = 0; j < 32; j++) raw0[j] = __float_as_uint(fmaf(__uint_as_float(raw0[j]), 1.f / kSplitScale, acc[jc * 32 + j]));
+        tmem_st32(xaddr + jc * 32, raw0);
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) raw1[j] = __float_as_uint(fmaf(__uint_as_float(raw1[j]), 1.f / kSplitScale, acc[(jc + 1) * 32 + j]));
+          tmem_st32(xaddr + (jc + 1) * 32, raw1);
+        }
+      }
+      if (bias_first && next_tile < num_tiles) {
+        bias_s[((tcount + 1u) & 1u) * 128u + threadIdx.x - 128] = bias_next;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(xfull_bar(xb));
     }
+    if (PROF && blockIdx.x == 0 && threadIdx.x == 128)
+      printf("tc2 profile: fold warp total %lld clk, waiting for partial sums %lld, in TMEM loads %lld, fence + arrive %lld\n", clock64() - prof_t0, prof_a, prof_b, prof_c);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-    // ------------------------------------------------------------------ tail warps
+    // ------------------------------------------------------------------ tail warps: two per lane quadrant, two chunks each
     const int q = warp & 3, half = (warp - 8) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     // this warp's 32 x 32 fp32 staging tile (float4 columns XOR-swizzled by row: conflict-free both ways)
@@ -288,43 +367,74 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
     int ib = -1;  // the op whose split bypass input is prefetched (first kAddScaled with a split source)
     for (int i = 0; i < p.n_ops && ib < 0; i++)
       if (p.ops[i].type == EpiOp::kAddScaled && p.ops[i].buf_lo) ib = i;
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
-      const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
-      const uint32_t xb = tcount & 1u;
-      const uint32_t xaddr = lane_base + (2u + xb) * (uint32_t)p.bn;
-      const int r = m0 + q * 32 + lane;
-      const int rr = r < p.m ? r : p.m - 1;
-#pragma unroll 1
-      for (int jj = 0; jj < 2; jj++) {
-        const int jc = half * 2 + jj;
-        const int c0 = n0 + jc * 32;
-        const bool valid = FULL || (jc * 32 < p.bn && c0 < p.n);
-        // bypass input of the chunk: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B cover a row segment,
-        // 8 rows per instruction; issued before the wait for the tile so that HBM latency is hidden
-        uint4 pf_h[4], pf_l[4];
-        auto prefetch = [&](int i) {
-          const DevOp &op = p.ops[i];
-          const int c8 = lane & 3;
-          const bool ok = FULL || c0 + c8 * 8 < p.n;
+    // The warp walks "units" = (tile, 32-column chunk).  The global inputs of unit u + 1 -- the bypass rows and this
+    // lane's column of the BatchNorm vectors -- are requested in the middle of unit u, as soon as unit u has consumed
+    // its own, so that their latency hides behind the rest of unit u and the TMEM load of unit u + 1.
+    uint4 pf_h[4], pf_l[4];        // bypass input of the coming unit: 4 lanes x 16 B cover a row segment, 8 rows per instruction
+    float so_s = 0.f, so_o = 0.f;  // column `lane` of the BatchNorm scale / offset of the coming unit
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_units = my_tiles * 2;
+    // coordinates of a unit: one integer division per unit, shared by everything that needs them
+    struct Unit {
+      int m0, c0, jc;
+      bool valid;
+    };
+    auto unit_at = [&](int u) {
+      Unit w;
+      const int t = (int)blockIdx.x + (u >> 1) * (int)gridDim.x, tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+      w.jc = half * 2 + (u & 1);
+      w.m0 = tm * kTcBM;
+      w.c0 = tn * p.bn + w.jc * 32;
+      w.valid = u < n_units && (FULL || (w.jc * 32 < p.bn && w.c0 < p.n));
+      return w;
+    };
+    auto prefetch_bypass = [&](int i, const Unit &w) {
+      const DevOp &op = p.ops[i];
+      const int c8 = lane & 3;
+      const bool ok = FULL || w.c0 + c8 * 8 < p.n;
 #pragma unroll
-          for (int it = 0; it < 4; it++) {
-            int ri = m0 + q * 32 + it * 8 + (lane >> 2);
-            if (ri >= p.m) ri = p.m - 1;
-            long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
-            if (orow >= op.buf_rows) orow = op.buf_rows - 1;
-            const size_t off = (size_t)orow * op.buf_ld + c0 + c8 * 8;
-            pf_h[it] = make_uint4(0u, 0u, 0u, 0u);
-            pf_l[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) {
-              pf_h[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf) + off));
-              pf_l[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf_lo) + off));
-            }
-          }
-        };
-        if (valid && ib >= 0) prefetch(ib);
-        if (jj == 0) {
-          mbar_wait(xfull_bar(xb), (tcount >> 1) & 1u);
+      for (int it = 0; it < 4; it++) {
+        int ri = w.m0 + q * 32 + it * 8 + (lane >> 2);
+        if (ri >= p.m) ri = p.m - 1;
+        long long orow = op.den == op.num ? ri : ((long long)ri * op.num) / op.den;
+        if (orow >= op.buf_rows) orow = op.buf_rows - 1;
+        const size_t off = (size_t)orow * op.buf_ld + w.c0 + c8 * 8;
+        pf_h[it] = make_uint4(0u, 0u, 0u, 0u);
+        pf_l[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
+          pf_h[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf) + off));
+          pf_l[it] = __ldcs(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(op.buf_lo) + off));
+        }
+      }
+    };
+    auto prefetch_so = [&](const Unit &w) {
+      if constexpr (kStatic && kSoIdx >= 0) {
+        so_s = so_o = 0.f;
+        if (FULL || w.c0 + lane < p.n) {
+          so_s = __ldg(p.ops[kSoIdx].v0 + w.c0 + lane);
+          so_o = __ldg(p.ops[kSoIdx].v1 + w.c0 + lane);
+        }
+      }
+    };
+    Unit nxt = unit_at(0);
+    if (nxt.valid) {
+      if (ib >= 0) prefetch_bypass(ib, nxt);
+      prefetch_so(nxt);
+    }
+#pragma unroll 1
+    for (int u = 0; u < n_units; u++) {
+      {
+        const Unit cur = nxt;
+        nxt = unit_at(u + 1);
+        const int jc = cur.jc, m0 = cur.m0, c0 = cur.c0;
+        const uint32_t tcount = (uint32_t)(u >> 1);
+        const uint32_t xb = tcount & 1u;
+        const uint32_t xaddr = lane_base + (2u + xb) * (uint32_t)p.bn;
+        const int r = m0 + q * 32 + lane;
+        const int rr = r < p.m ? r : p.m - 1;
+        const bool valid = cur.valid, next_valid = nxt.valid;
+        if ((u & 1) == 0) {
+          timed_wait(xfull_bar(xb), (tcount >> 1) & 1u, prof_a);
           tc_fence_after();
         }
         float v[32];
@@ -335,12 +445,19 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = __uint_as_float(raw[j]);
         }
-        if (jj == 1) {  // both chunks are in registers: the MMA issuer may overwrite this accumulator
+        if ((u & 1) == 1) {  // this warp's last chunk of the tile is in registers: the MMA issuer may overwrite this accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(xfree_bar(xb));
         }
-        if (!valid) continue;
+        if (!valid) {
+          if (next_valid) {
+            if (ib >= 0) prefetch_bypass(ib, nxt);
+            prefetch_so(nxt);
+          }
+          continue;
+        }
+        bool bypass_requested = false;
 
         auto apply = [&](const int i, const int type) {
           const DevOp &op = p.ops[i];
@@ -358,13 +475,30 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
               for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : 0.f;
               break;
             case EpiOp::kScaleOffset:
+              // y = x * scale + offset as one fused multiply-add per element (the reference's MulColsVec + AddVecToRows
+              // round twice; the fused form is at most half an ulp closer to the exact value)
+              if constexpr (kStatic && kSoIdx >= 0) {
+                if (i == kSoIdx) {
+                  float *vs = reinterpret_cast<float *>(stg);
+                  __syncwarp();
+                  vs[lane] = so_s;
+                  vs[32 + lane] = so_o;
+                  __syncwarp();
+                  if (next_valid) prefetch_so(nxt);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {  // y = x * scale, then + offset: two roundings as the reference
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 s = *reinterpret_cast<const float4 *>(vs + j), o = *reinterpret_cast<const float4 *>(vs + 32 + j);
+                    fma2(v[j], v[j + 1], s.x, s.y, o.x, o.y);
+                    fma2(v[j + 2], v[j + 3], s.z, s.w, o.z, o.w);
+                  }
+                  break;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
                 const float4 s = ldvec4<FULL>(op.v0, c0 + j, p.n), o = ldvec4<FULL>(op.v1, c0 + j, p.n);
-                mul2(v[j], v[j + 1], s.x, s.y);
-                mul2(v[j + 2], v[j + 3], s.z, s.w);
-                add2(v[j], v[j + 1], o.x, o.y);
-                add2(v[j + 2], v[j + 3], o.z, o.w);
+                fma2(v[j], v[j + 1], s.x, s.y, o.x, o.y);
+                fma2(v[j + 2], v[j + 3], s.z, s.w, o.z, o.w);
               }
               break;
             case EpiOp::kScale:
@@ -377,7 +511,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
               __syncwarp();
               if (op.buf_lo) {
                 const int c8 = lane & 3;
-                if (i != ib) prefetch(i);  // a second bypass op: loaded now
+                if (i != ib) prefetch_bypass(i, cur);  // a second bypass op: loaded now
 #pragma unroll
                 for (int it = 0; it < 4; it++) {
                   const int ii = it * 8 + (lane >> 2);
@@ -391,6 +525,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
                   }
                   stg[ii * 8 + ((2 * c8) ^ (ii & 7))] = make_float4(x[0], x[1], x[2], x[3]);
                   stg[ii * 8 + ((2 * c8 + 1) ^ (ii & 7))] = make_float4(x[4], x[5], x[6], x[7]);
+                }
+                if (i == ib && next_valid) {  // registers free again: request the next unit's rows
+                  prefetch_bypass(ib, nxt);
+                  bypass_requested = true;
                 }
               } else {
                 // plain fp32 source: 8 lanes x 16 B cover a 128-byte row segment, 4 rows per instruction
@@ -444,6 +582,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
 #pragma unroll 1
           for (int i = first_op; i < p.n_ops; i++) apply(i, p.ops[i].type);
         }
+        if (next_valid) {
+          if (ib >= 0 && !bypass_requested) prefetch_bypass(ib, nxt);
+        }
         // store through the staging tile so that every instruction writes whole row segments
         __syncwarp();
         if (p.out_lo) {
@@ -491,6 +632,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
         __syncwarp();
       }
     }
+    if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 8 || warp == 12))
+      printf("tc2 profile: tail warp %d total %lld clk, waiting for a finished tile %lld\n", warp, clock64() - prof_t0, prof_a);
   }
   tc_fence_before();
   __syncthreads();
@@ -515,29 +658,31 @@ constexpr int kPatBias = PatOf(EpiOp::kBias);
 constexpr int kPatBRS = PatOf(EpiOp::kBias, EpiOp::kRelu, EpiOp::kScaleOffset);
 constexpr int kPatBRSA = PatOf(EpiOp::kBias, EpiOp::kRelu, EpiOp::kScaleOffset, EpiOp::kAddScaled);
 
-template <int PAT, bool FULL>
+template <int PAT, bool FULL, bool PROF = false>
 void Launch(const TcParams &p, int grid, int smem, int smem_limit, cudaStream_t stream) {
   static int configured_dev = -1;  // opt-in shared memory size is a per-device function attribute
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<PAT, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<PAT, FULL, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit);
     if (e != cudaSuccess) RS_FAIL("cudaFuncSetAttribute(gemm_tc2_kernel): " << cudaGetErrorString(e));
     configured_dev = dev;
   }
-  gemm_tc2_kernel<PAT, FULL><<<grid, kT2Threads, smem, stream>>>(p);
+  gemm_tc2_kernel<PAT, FULL, PROF><<<grid, kT2Threads, smem, stream>>>(p);
 }
 
 }  // namespace
 
 void LaunchGemmTc2(const TcParams &p, int num_sms, int smem_limit, cudaStream_t stream) {
   const int stage_bytes = 2 * kT2StageA + 2 * p.bn * 128;
-  const int smem = 1024 + p.stages * stage_bytes + 8 * 4096 + 8 * (2 * p.stages + 8) + 16;
+  const int smem = 1024 + p.stages * stage_bytes + 8 * 4096 + 8 * (2 * p.stages + 10) + 1024;
   int grid = p.tiles_m * p.tiles_n;
   if (grid > num_sms) grid = num_sms;
   const bool full = p.bn == 128 && p.n % 128 == 0;
   const int pat = Pattern(p);
-  if (full && pat == kPatNone) Launch<kPatNone, true>(p, grid, smem, smem_limit, stream);
+  if (p.profile && full && pat == kPatNone) Launch<kPatNone, true, true>(p, grid, smem, smem_limit, stream);
+  else if (p.profile && full && pat == kPatBRSA) Launch<kPatBRSA, true, true>(p, grid, smem, smem_limit, stream);
+  else if (full && pat == kPatNone) Launch<kPatNone, true>(p, grid, smem, smem_limit, stream);
   else if (full && pat == kPatBRS) Launch<kPatBRS, true>(p, grid, smem, smem_limit, stream);
   else if (full && pat == kPatBRSA) Launch<kPatBRSA, true>(p, grid, smem, smem_limit, stream);
   else if (pat == kPatNone) Launch<kPatNone, false>(p, grid, smem, smem_limit, stream);
