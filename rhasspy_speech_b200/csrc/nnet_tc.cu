@@ -710,8 +710,13 @@ static void LaunchPattern(const TcParams &p, int grid, int smem, cudaStream_t st
 
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream) {
   if (p.m <= 0 || p.n <= 0) return;
-  static const bool v1 = getenv("RS_B200_TC") && !strcmp(getenv("RS_B200_TC"), "v1");
-  if (!v1) {
+  // RS_B200_TC = v1 | v2 keep the earlier arrangements of the kernel selectable for A/B measurements
+  static const int ver = !getenv("RS_B200_TC") ? 3 : !strcmp(getenv("RS_B200_TC"), "v1") ? 1 : !strcmp(getenv("RS_B200_TC"), "v2") ? 2 : 3;
+  if (ver == 3) {
+    LaunchGemmTc3(p, num_sms, g_tc_smem_limit, stream);
+    return;
+  }
+  if (ver == 2) {
     LaunchGemmTc2(p, num_sms, g_tc_smem_limit, stream);
     return;
   }

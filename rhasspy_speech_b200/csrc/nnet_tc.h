@@ -57,5 +57,7 @@ void TcConfigure(TcParams *p);  // fills stages / tmem_cols / tiles_* from bn, m
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream);
 // second-generation kernel (nnet_tc2.cu): separate fold and tail warps
 void LaunchGemmTc2(const TcParams &p, int num_sms, int smem_limit, cudaStream_t stream);
+// third arrangement (nnet_tc3.cu): sixteen epilogue warps, 32 columns each, fold and tail in the same warp
+void LaunchGemmTc3(const TcParams &p, int num_sms, int smem_limit, cudaStream_t stream);
 
 }  // namespace rs

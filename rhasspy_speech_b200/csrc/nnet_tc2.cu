@@ -149,8 +149,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
   const int num_tiles = p.tiles_m * p.tiles_n;
   int total_kb = 0;
   for (int s = 0; s < p.n_slabs; s++) total_kb += p.slabs[s].kblocks;
-  const int fold = p.fold;                              // main MMAs (K = 16 each) per published partial sum: 1, 2 or 4
-  const int total_sums = total_kb * (kTcBK / 16 / fold);  // partial sums per tile
+  const int total_sums = total_kb * 2;  // partial sums per tile: one per two main MMAs (K = 16 each), see the MMA issuer
   // the bias, when it is the first op, is the start value of the running sums (AffineComponent / TdnnComponent::Propagate
   // copy the bias into the output and let the GEMM accumulate onto it)
   const bool bias_first = kStatic ? kTypes[0] == EpiOp::kBias : (p.n_ops > 0 && p.ops[0].type == EpiOp::kBias);
@@ -198,53 +197,58 @@ __global__ void __launch_bounds__(kT2Threads, 1) gemm_tc2_kernel(const __grid_co
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
-        // instruction descriptor: D fp32, A/B fp16, both K-major, N = bn, M = 128
-        const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-        int stage = 0;
-        uint32_t phase = 0, fcount = 0, tcount = 0;  // fcount: partial sums published so far (main set = fcount & 1)
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
-          const uint32_t xb = tcount & 1u;
-          const uint32_t d_cross = tmem_base + (2u + xb) * (uint32_t)p.bn;
-          timed_wait(xfree_bar(xb), ((tcount >> 1) & 1u) ^ 1u, prof_c);  // the tail warps have taken the tile before last
+      // ------------------------------------------------------------------ MMA issuer
+      // All 32 lanes walk the loop (warp-uniform control flow, so barrier addresses and matrix descriptors live in
+      // uniform registers) and one elected lane issues.  The issuing thread's own instruction stream is what bounds
+      // this kernel once the epilogue keeps up: measured with one lane walking the loop alone, ~78 instructions per MMA
+      // at ~5 clk per dependent instruction = 160 clk per MMA against 70-100 clk of tensor work (profiles/r2_gemm3_*).
+      // fold is fixed at 2 here: partial sums are published after MMAs 1 and 3 of a K block.
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      // upper word of a shared-memory matrix descriptor: SBO = 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      auto desc = [&](uint32_t lo) {
+        uint64_t d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi));
+        return d;
+      };
+      const uint32_t bn = (uint32_t)p.bn;
+      uint32_t stage = 0, phase = 0, fcount = 0, tcount = 0;  // fcount: partial sums published so far (main set = fcount & 1)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+        const uint32_t xb = tcount & 1u;
+        const uint32_t d_cross = tmem_base + (2u + xb) * bn;
+        mbar_wait_lean(xfree_bar(xb), ((tcount >> 1) & 1u) ^ 1u);  // the tail warps have taken the tile before last
+        tc_fence_after();
+        for (int kb = 0; kb < total_kb; kb++) {
+          mbar_wait_lean(full_bar(stage), phase);
           tc_fence_after();
-          for (int kb = 0; kb < total_kb; kb++) {
-            timed_wait(full_bar(stage), phase, prof_a);
+          const uint32_t sa = ((smem0 + stage * stage_bytes) & 0x3ffffu) >> 4;  // descriptor address field, 16-byte units
+          const uint32_t a_hi = sa, a_lo = sa + (kT2StageA >> 4), b_hi = sa + (2 * kT2StageA >> 4), b_lo = b_hi + (b_bytes >> 4);
+  #pragma unroll
+          for (int half = 0; half < 2; half++) {  // one published partial sum = two K steps of 16 (32 bytes inside the swizzle atom)
+            const uint32_t set = fcount & 1u;
+            mbar_wait_lean(sete_bar(set), ((fcount >> 1) & 1u) ^ 1u);  // the fold warps have drained this accumulator
             tc_fence_after();
-            const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
-            const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kT2StageA);
-            const uint64_t b_hi = smem_desc_sw128(sa + 2 * kT2StageA), b_lo = smem_desc_sw128(sa + 2 * kT2StageA + b_bytes);
-#pragma unroll
-            for (int k = 0; k < kTcBK / 16; k++) {  // 16 fp16 = 32 bytes per step inside the swizzle atom
-              const uint32_t set = fcount & 1u;
-              const bool first = (k & (fold - 1)) == 0, last = (k & (fold - 1)) == fold - 1;
-              if (first) {
-                timed_wait(sete_bar(set), ((fcount >> 1) & 1u) ^ 1u, prof_b);  // the fold warps have drained this accumulator
-                tc_fence_after();
+            const uint32_t d_main = tmem_base + set * bn;
+            if (elect_one()) {
+  #pragma unroll
+              for (int kk = 0; kk < 2; kk++) {
+                const uint32_t adv = (uint32_t)((half * 2 + kk) * 32 >> 4);
+                tc_mma_f16(d_main, desc(a_hi + adv), desc(b_hi + adv), idesc, kk);
+                tc_mma_f16(d_cross, desc(a_lo + adv), desc(b_hi + adv), idesc, (kb | half | kk) != 0 ? 1u : 0u);
+                tc_mma_f16(d_cross, desc(a_hi + adv), desc(b_lo + adv), idesc, 1u);
               }
-              const uint32_t d_main = tmem_base + set * (uint32_t)p.bn;
-              const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              tc_mma_f16(d_main, a_hi + adv, b_hi + adv, idesc, first ? 0u : 1u);
-              tc_mma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-              tc_mma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
-              if (k == kTcBK / 16 - 1) tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
-              if (last) {
-                tc_commit(setf_bar(set));  // this partial sum (and, on the tile's last one, the cross sum) complete
-                fcount++;
-              }
+              if (half == 1) tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
+              tc_commit(setf_bar(set));                    // this partial sum (and, on the tile's last one, the cross sum) complete
             }
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+            __syncwarp();
+            fcount++;
+          }
+          if (++stage == (uint32_t)p.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
-        if (PROF && blockIdx.x == 0)
-          printf("tc2 profile: MMA thread total %lld clk, waiting for operands %lld, for a drained accumulator %lld, for the tail warps %lld\n",
-                 clock64() - prof_t0, prof_a, prof_b, prof_c);
       }
-      __syncwarp();
     }
   } else if (warp < 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
