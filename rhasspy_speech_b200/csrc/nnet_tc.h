@@ -13,8 +13,6 @@ namespace rs {
 
 constexpr int kTcBM = 128;      // output rows (time steps) per tile = UMMA M
 constexpr int kTcBK = 64;       // fp16 columns per pipeline stage = one 128-byte swizzle atom
-constexpr int kTcThreads = 384; // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1, 2: the two epilogue groups
-constexpr int kTcChunks = 4;    // 32-column chunks of a tile handled by one epilogue thread
 constexpr int kTcMaxBN = 128;   // output columns per tile (fp32 running sums live in registers)
 constexpr int kTcMaxSlabs = 4;
 constexpr float kSplitScale = 2048.f;  // lo plane = (x - hi) * 2^11, see nnet_tc.cu

@@ -1,6 +1,14 @@
 set -x
-for v in v2 v3; do
+for v in v3 v4; do
 RS_B200_TC=$v timeout 300 python scripts/ncu_step.py 256 3 2>&1 | tail -1
 RS_B200_TC=$v bash scripts/launch_list.sh $v | grep gemm_tc
 done
-RS_B200_TC=v2 timeout 600 python -m pytest tests/test_gpu_zamia.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python scripts/gemm_probe.py 32768 > gpurun_out/probe_v3.jsonl 2>&1
+python - <<'PY'
+import json
+for l in open('gpurun_out/probe_v3.jsonl'):
+    if l.startswith('{'):
+        x=json.loads(l); print(x['k'],x['n'],x['offsets'],x['stride'],'tc ms %.3f max %.2e rms %.2e | simt max %.2e'%(x['tc_split']['ms'],x['tc_split']['max_abs'],x['tc_split']['rms'],x['simt']['max_abs']))
+    elif 'rror' in l or 'Traceback' in l: print(l.strip())
+PY
+timeout 600 python -m pytest tests/test_gpu_zamia.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
