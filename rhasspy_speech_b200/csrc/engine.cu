@@ -451,6 +451,7 @@ static void UploadModel(ModelImpl *mi) {
   f.shift = m.mfcc.WindowShift();
   f.length = m.mfcc.WindowSize();
   f.padded = m.mfcc.PaddedWindowSize();
+  if (f.padded > 512) RS_FAIL("frame lengths beyond 512 samples (padded) are not supported by the MFCC kernel: " << f.padded);
   f.logn = t.logn;
   f.preemph = m.mfcc.preemph_coeff;
   f.dither = m.mfcc.dither;
@@ -472,6 +473,21 @@ static void UploadModel(ModelImpl *mi) {
   f.mel_len = Upload(t.mel_len, &own);
   f.mel_start = Upload(t.mel_start, &own);
   f.mel_weights = Upload(t.mel_weights, &own);
+  {
+    // lane-friendly copies: tap-major mel weights [max_len][num_bins] and the DCT matrix transposed [num_bins][num_ceps],
+    // so that the 32 lanes of a warp (one mel bin / one cepstrum each) read consecutive addresses
+    const int Nb = (int)t.mel_len.size(), K = (int)(t.dct.size() / (size_t)Nb);
+    int max_len = 0;
+    for (int b = 0; b < Nb; b++) max_len = std::max(max_len, t.mel_len[b]);
+    std::vector<float> mel_t((size_t)max_len * Nb, 0.f), dct_t((size_t)Nb * K);
+    for (int b = 0; b < Nb; b++)
+      for (int i = 0; i < t.mel_len[b]; i++) mel_t[(size_t)i * Nb + b] = t.mel_weights[t.mel_start[b] + i];
+    for (int k = 0; k < K; k++)
+      for (int b = 0; b < Nb; b++) dct_t[(size_t)b * K + k] = t.dct[(size_t)k * Nb + b];
+    f.mel_weights_t = Upload(mel_t, &own);
+    f.mel_max_len = max_len;
+    f.dct_t = Upload(dct_t, &own);
+  }
   f.dct = Upload(t.dct, &own);
   f.lifter = t.lifter.empty() ? nullptr : Upload(t.lifter, &own);
   // --- ivector

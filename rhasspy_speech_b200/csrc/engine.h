@@ -31,6 +31,9 @@ struct FeatParams {
   const int *mel_offset, *mel_len, *mel_start;  // [num_bins]
   const float *mel_weights;
   const float *dct;             // [num_ceps, num_bins]
+  const float *mel_weights_t;   // [mel_max_len][num_bins] tap-major copy of mel_weights, zero beyond a bin's length
+  int mel_max_len;
+  const float *dct_t;           // [num_bins][num_ceps]
   const float *lifter;          // [num_ceps] or null
 };
 void LaunchMfcc(const FeatParams &p, int n_utts, int max_frames, cudaStream_t stream);

@@ -62,23 +62,39 @@ mfcc_kernel(FeatParams p) {
     }
     return x;
   };
+  // every lane keeps its samples (i = lane + 32 j) in registers: one load and one conversion per sample
+  // (frames of up to 512 samples; the buffers below already assume padded <= 512)
+  float sv[16];
   float part = 0.f;
-  for (int i = lane; i < L; i += 32) part += sample(i);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int i = lane + 32 * j;
+    sv[j] = i < L ? sample(i) : 0.f;
+    if (i < L) part += sv[j];
+  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   float dc = 0.f;
   if (p.remove_dc) dc = -part / (float)L;
   // interleaved complex input: sample 2j -> xr[j], sample 2j+1 -> xi[j]  (srfft.cc:147-156)
   const float pre = p.preemph;
-  for (int i = lane; i < N; i += 32) {
-    float v = 0.f;
-    if (i < L) {
-      float x = fadd(sample(i), dc);
-      float xm = fadd(sample(i > 0 ? i - 1 : 0), dc);
-      if (pre != 0.f) x = fsub(x, fmul(pre, xm));
-      v = fmul(x, p.window[i]);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int i = lane + 32 * j;
+    // the previous sample sits in the lane below, or for lane 0 in lane 31 one row up (sample 0 is its own predecessor)
+    float prev = __shfl_up_sync(0xffffffffu, sv[j], 1);
+    const float wrap = __shfl_sync(0xffffffffu, sv[j > 0 ? j - 1 : 0], 31);
+    if (lane == 0) prev = j > 0 ? wrap : sv[0];
+    if (i < N) {
+      float v = 0.f;
+      if (i < L) {
+        float x = fadd(sv[j], dc);
+        const float xm = fadd(prev, dc);
+        if (pre != 0.f) x = fsub(x, fmul(pre, xm));
+        v = fmul(x, p.window[i]);
+      }
+      if (i & 1) xi[i >> 1] = v; else xr[i >> 1] = v;
     }
-    if (i & 1) xi[i >> 1] = v; else xr[i >> 1] = v;
   }
   __syncwarp();
   // raw log-energy is only needed with --use-energy=true
@@ -260,20 +276,21 @@ mfcc_kernel(FeatParams p) {
   __syncwarp();
 
   // --- mel filterbank + log (mel-computations.cc:226-251, feature-mfcc.cc:57-58)
+  // (weights read tap-major: the lanes of a warp -- one bin each -- read consecutive addresses; same taps, same order)
   for (int b = lane; b < p.num_bins; b += 32) {
     int off = p.mel_offset[b], len = p.mel_len[b];
-    const float *w = p.mel_weights + p.mel_start[b];
+    const float *w = p.mel_weights_t + b;
     float e = 0.f;
-    for (int i = 0; i < len; i++) e = fmaf(w[i], xr[off + i], e);
+    for (int i = 0; i < len; i++) e = fmaf(w[(size_t)i * p.num_bins], xr[off + i], e);
     melv[b] = logf(fmaxf(e, 1.1920928955078125e-07f));
   }
   __syncwarp();
   // --- DCT + lifter (feature-mfcc.cc:61-66)
   float *out = p.mfcc + ((size_t)p.frame_offset[u] + t) * p.num_ceps;
   for (int c = lane; c < p.num_ceps; c += 32) {
-    const float *row = p.dct + (size_t)c * p.num_bins;
+    const float *col = p.dct_t + c;  // transposed: the lanes (one cepstrum each) read consecutive addresses
     float acc = 0.f;
-    for (int b = 0; b < p.num_bins; b++) acc = fmaf(row[b], melv[b], acc);
+    for (int b = 0; b < p.num_bins; b++) acc = fmaf(col[(size_t)b * p.num_ceps], melv[b], acc);
     if (p.lifter) acc = fmul(acc, p.lifter[c]);
     if (p.use_energy && c == 0) acc = log_energy;
     out[c] = acc;

@@ -150,11 +150,85 @@ __global__ void __launch_bounds__(256) splice_lda_kernel(IvecParams p) {
   }
 }
 
+// The same transform for the common layout (dim and ldim multiples of 4): CTA = 64 frames of one utterance, a thread
+// owns 4 frames x 4 output columns of both streams, so four weights (one 16-byte load) and eight 16-byte shared-memory
+// reads feed 128 FMAs.  Every sum runs over k in ascending order with one FMA per term, as in splice_lda_kernel.
+constexpr int kLdaFrames4 = 64;
+__global__ void __launch_bounds__(256) splice_lda4_kernel(IvecParams p) {
+  extern __shared__ float sm[];
+  const int u = blockIdx.y;
+  const int T = p.num_frames[u];
+  const int t0 = blockIdx.x * kLdaFrames4;
+  if (t0 >= T) return;
+  const int W = kLdaFrames4 + p.left + p.right;
+  float *sraw = sm, *snorm = sm + (size_t)W * p.dim;
+  const size_t base = (size_t)p.frame_offset[u];
+  const int dim4 = p.dim >> 2;
+  for (int i = threadIdx.x; i < W * dim4; i += blockDim.x) {
+    const int w = i / dim4, d4 = i - w * dim4;
+    int t = t0 - p.left + w;
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);  // OnlineSpliceFrames clamps at both ends
+    reinterpret_cast<float4 *>(sraw)[i] = __ldg(reinterpret_cast<const float4 *>(p.mfcc + (base + t) * p.dim) + d4);
+    reinterpret_cast<float4 *>(snorm)[i] = __ldg(reinterpret_cast<const float4 *>(p.mfcc_norm + (base + t) * p.dim) + d4);
+  }
+  __syncthreads();
+  const int K = p.dim * (p.left + 1 + p.right), jgroups = p.ldim >> 2;
+  for (int o = threadIdx.x; o < (kLdaFrames4 / 4) * jgroups; o += blockDim.x) {
+    const int fg = o / jgroups, j0 = (o - fg * jgroups) * 4;
+    if (t0 + fg * 4 >= T) continue;
+    const float *xr = sraw + (size_t)fg * 4 * p.dim, *xn = snorm + (size_t)fg * 4 * p.dim;
+    float ar[4][4], an[4][4];
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) ar[f][j] = an[f][j] = 0.f;
+    for (int k = 0; k < K; k += 4) {
+      float4 w[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[i] = __ldg(reinterpret_cast<const float4 *>(p.lda_t + (size_t)(k + i) * p.ldim + j0));
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        const float4 a = *reinterpret_cast<const float4 *>(xr + f * p.dim + k);
+        const float4 b = *reinterpret_cast<const float4 *>(xn + f * p.dim + k);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          ar[f][0] = fmaf(w[i].x, av[i], ar[f][0]);
+          ar[f][1] = fmaf(w[i].y, av[i], ar[f][1]);
+          ar[f][2] = fmaf(w[i].z, av[i], ar[f][2]);
+          ar[f][3] = fmaf(w[i].w, av[i], ar[f][3]);
+          an[f][0] = fmaf(w[i].x, bv[i], an[f][0]);
+          an[f][1] = fmaf(w[i].y, bv[i], an[f][1]);
+          an[f][2] = fmaf(w[i].z, bv[i], an[f][2]);
+          an[f][3] = fmaf(w[i].w, bv[i], an[f][3]);
+        }
+      }
+    }
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.lda_bias) bias = __ldg(reinterpret_cast<const float4 *>(p.lda_bias + j0));
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int t = t0 + fg * 4 + f;
+      if (t >= T) continue;
+      float4 r = make_float4(ar[f][0], ar[f][1], ar[f][2], ar[f][3]), n = make_float4(an[f][0], an[f][1], an[f][2], an[f][3]);
+      if (p.lda_bias) {
+        r.x += bias.x, r.y += bias.y, r.z += bias.z, r.w += bias.w;
+        n.x += bias.x, n.y += bias.y, n.z += bias.z, n.w += bias.w;
+      }
+      *reinterpret_cast<float4 *>(p.x_raw + (base + t) * p.ldim + j0) = r;
+      *reinterpret_cast<float4 *>(p.x_norm + (base + t) * p.ldim + j0) = n;
+    }
+  }
+}
+
 // -------------------------------------------------------------------- UBM posteriors
 // DiagGmm::LogLikelihoods (gmm/diag-gmm.cc:546-562) for a tile of kUbmFrames frames per CTA as a
 // register-tiled product [frames x D] x [D x G] (the UBM tables stream through L2 once per tile,
 // not once per frame), then VectorToPosteriorEntry (hmm/posterior.cc:440-508) with one warp per
 // frame over the log-likelihood row kept in shared memory.
+// (Measured in round 2: 32 frames per CTA, 8 frames x 8 consecutive Gaussians per thread with 16-byte table loads, one row
+//  ahead in registers or eight rows ahead through shared memory with cp.async: 205-217 registers, one CTA per SM, 676 / 743 us
+//  against 609 us -- the posterior selection below, one warp per frame, needs the occupancy more than the product needs the tile.)
 // (32 frames per CTA with 8 frames per thread was measured: 169 registers, one CTA per SM, feature stage 2.31 -> 2.59 ms)
 constexpr int kUbmFrames = 16;
 __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
@@ -503,9 +577,16 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
   if (p.n_utts == 0) return;
   const int G = p.num_gauss, D = p.ldim, R = p.ivector_dim, P = R * (R + 1) / 2;
   if (p.total_frames > 0) {
-    dim3 g1((p.max_frames + kLdaFrames - 1) / kLdaFrames, p.n_utts);
-    size_t sm1 = (size_t)2 * (kLdaFrames + p.left + p.right) * p.dim * sizeof(float);
-    splice_lda_kernel<<<g1, 256, sm1, stream>>>(p);
+    const int K = p.dim * (p.left + 1 + p.right);
+    if ((p.dim & 3) == 0 && (p.ldim & 3) == 0 && (K & 3) == 0) {
+      dim3 g1((p.max_frames + kLdaFrames4 - 1) / kLdaFrames4, p.n_utts);
+      size_t sm1 = (size_t)2 * (kLdaFrames4 + p.left + p.right) * p.dim * sizeof(float);
+      splice_lda4_kernel<<<g1, 256, sm1, stream>>>(p);
+    } else {
+      dim3 g1((p.max_frames + kLdaFrames - 1) / kLdaFrames, p.n_utts);
+      size_t sm1 = (size_t)2 * (kLdaFrames + p.left + p.right) * p.dim * sizeof(float);
+      splice_lda_kernel<<<g1, 256, sm1, stream>>>(p);
+    }
     size_t sm2 = (size_t)kUbmFrames * (2 * D + G) * sizeof(float);
     static size_t ubm_attr = 48 * 1024;
     if (sm2 > ubm_attr) {

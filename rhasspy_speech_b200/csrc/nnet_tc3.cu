@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) gemm_tc3_kernel(const __grid_co
               // split source, read with full-row coalescing (prefetch_bypass); each plane goes through the staging
               // tile so that a thread gets the 32 halves of its own row, then value = hi + lo / 2048 (exact)
               const int c8 = lane & 3;
-              prefetch_bypass(i);
+              prefetch_bypass(i);  // (requesting the rows before the cross fold / ReLU / BatchNorm was measured: slower, spills)
               uint4 rh[4], rl[4];
               __syncwarp();
 #pragma unroll

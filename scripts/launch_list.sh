@@ -1,5 +1,5 @@
 # per-launch device times of one step (batch 256), after one warm-up step
-ncu --metrics gpu__time_duration.sum --clock-control none -s 43 -c 43 --csv --log-file gpurun_out/launches_${1:-x}.csv python scripts/ncu_step.py 256 2 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 42 -c 44 --csv --log-file gpurun_out/launches_${1:-x}.csv python scripts/ncu_step.py 256 2 > /dev/null 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/launches_${1:-x}.csv')) if len(r)>5]
