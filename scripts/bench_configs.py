@@ -158,6 +158,30 @@ def main():
         return dec2.finish_streams(streams)
     run("4: 64 streams x 80 ms chunks, online iVector schedule, grammar HCLG", dec2, stream_pass,
         sum(len(u) for u in utts64) / 16000.0)
+    # latency from end of input to the result: all 64 streams ending in the same tick (one device batch),
+    # and streams ending one at a time (each its own batch of one); accept() only buffers, so this is the whole
+    # feature + nnet + search time of the utterance(s)
+    lat_all, lat_one = [], []
+    for _ in range(3):
+        for s, raw in zip(streams, raws):
+            for o in range(0, len(raw), 2560):
+                s.accept(raw[o:o + 2560])
+        t0 = time.perf_counter()
+        dec2.finish_streams(streams)
+        lat_all.append((time.perf_counter() - t0) * 1e3)
+    for rep in range(2):
+        for s, raw in zip(streams, raws):
+            for o in range(0, len(raw), 2560):
+                s.accept(raw[o:o + 2560])
+        for s in streams:
+            t0 = time.perf_counter()
+            dec2.finish_streams([s])
+            if rep:
+                lat_one.append((time.perf_counter() - t0) * 1e3)
+    print(json.dumps({"config": "4: latency from end of input to result", "all_64_end_together_ms": float(np.mean(lat_all)),
+                      "one_stream_ends_alone_ms": {"p50": float(np.percentile(lat_one, 50)), "p99": float(np.percentile(lat_one, 99)),
+                                                   "max": float(np.max(lat_one))},
+                      "utterance_seconds": {"min": min(len(u) for u in utts64) / 16000.0, "max": max(len(u) for u in utts64) / 16000.0}}), flush=True)
 
 
 if __name__ == "__main__":
