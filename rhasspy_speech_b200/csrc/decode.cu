@@ -44,6 +44,7 @@
 
 #include "decode_common.cuh"
 #include "engine.h"
+#include "smem_attr.h"
 
 namespace rs {
 
@@ -1098,14 +1099,10 @@ void LaunchDecode(const DecodeParams &p, int n_lanes, cudaStream_t stream, bool 
   size_t smem = 0;
   if (p.cfg.smem_slots) {
     smem = DecodeSmemBytes(p.cfg.smem_slots);
-    static size_t configured[2] = {48 * 1024, 48 * 1024};
-    if (smem > configured[lattice]) {
-      if (lattice)
-        cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      else
-        cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured[lattice] = smem;
-    }
+    if (lattice)
+      EnsureDynSmem(decode_kernel<true>, smem);
+    else
+      EnsureDynSmem(decode_kernel<false>, smem);
   }
   if (lattice)
     decode_kernel<true><<<n_lanes, DecodeCtaThreads(), smem, stream>>>(p);

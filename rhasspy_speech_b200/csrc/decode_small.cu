@@ -22,6 +22,7 @@
 
 #include "decode_common.cuh"
 #include "engine.h"
+#include "smem_attr.h"
 
 namespace rs {
 
@@ -764,14 +765,10 @@ void LaunchDecodeSmall(const DecodeParams &p_in, cudaStream_t stream, bool latti
   if (p_in.n_utts == 0) return;
   DecodeParams p = p_in;
   const size_t smem = SmallSmemPlan(p, &p.cfg.small_cache_arcs, &p.cfg.small_ll_stage);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[lattice]) {
-    if (lattice)
-      cudaFuncSetAttribute(decode_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else
-      cudaFuncSetAttribute(decode_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured[lattice] = smem;
-  }
+  if (lattice)
+    EnsureDynSmem(decode_small_kernel<true>, smem);
+  else
+    EnsureDynSmem(decode_small_kernel<false>, smem);
   if (lattice)
     decode_small_kernel<true><<<p.n_utts, kNT, smem, stream>>>(p);
   else

@@ -31,7 +31,7 @@ namespace rs {
 #define CUDA_OK(expr)                                                                         \
   do {                                                                                        \
     cudaError_t e_ = (expr);                                                                  \
-    if (e_ != cudaSuccess) RS_FAIL("CUDA error: " << cudaGetErrorString(e_) << " at " << #expr); \
+    if (e_ != cudaSuccess) RS_FAIL("CUDA error: " << cudaGetErrorString(e_) << " at " << #expr << " (engine.cu:" << __LINE__ << ")"); \
   } while (0)
 
 struct DevBuf {  // grow-only device allocation

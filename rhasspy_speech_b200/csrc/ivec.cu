@@ -9,12 +9,48 @@
 //   kaldi/src/ivector/ivector-extractor.cc:611-668, 732-756        AccStats, GetIvector
 //   kaldi/src/matrix/optimization.cc:453-560      LinearCgd
 #include <cfloat>
+#include <cstdio>
 
 #include "engine.h"
+#include "smem_attr.h"
 
 namespace rs {
 
+// names the kernel whose launch configuration the runtime rejected (the caller only sees cudaGetLastError later)
+#define RS_CHECK_LAUNCH(name)                                                                          \
+  do {                                                                                                \
+    cudaError_t e_ = cudaPeekAtLastError();                                                           \
+    if (e_ != cudaSuccess) fprintf(stderr, "rs_b200: launch of %s failed: %s\n", name, cudaGetErrorString(e_)); \
+  } while (0)
+
 // ------------------------------------------------------------------------------------ CMVN
+// SmoothOnlineCmvnStats with no speaker stats (spk == utt in the reference's invocation) + ApplyCmvn for one value
+__device__ __forceinline__ float CmvnApply(const CmvnParams &p, float xin, double s0, double s1, double cnt, double g0, double g1, double gcount) {
+  double a0 = s0, a1 = s1, c = cnt;
+  if (c < (double)p.cmn_window) {
+    double cg = (double)p.cmn_window - c;
+    if (cg > (double)p.global_frames) cg = (double)p.global_frames;
+    if (cg > 0.0) {
+      double f = cg / gcount;
+      a0 += f * g0;
+      a1 += f * g1;
+      c += f * gcount;
+    }
+  }
+  if (!p.normalize_mean) return xin;
+  if (!p.normalize_variance) {
+    float alpha = (float)(-1.0 / c);          // VectorBase<float>::AddVec(float alpha, Vector<double>)
+    float off = (float)((double)alpha * a0);
+    return __fadd_rn(xin, off);
+  }
+  double mean = a0 / c;
+  double var = a1 / c - mean * mean;
+  if (var < 1.0e-20) var = 1.0e-20;
+  double scale = 1.0 / sqrt(var);
+  float sc = (float)scale, off = (float)(-(mean * scale));
+  return __fadd_rn(__fmul_rn(xin, sc), off);
+}
+
 // One thread per (utterance, dim): the sliding-window sums are sequential in double exactly as
 // ComputeStatsForFrame accumulates them (add frame t, then subtract frame t - cmn_window).
 __global__ void cmvn_kernel(CmvnParams p) {
@@ -78,10 +114,76 @@ __global__ void cmvn_kernel(CmvnParams p) {
   }
 }
 
+// The same statistics for utterances no longer than the window (nothing is ever subtracted): thread (d, segment)
+// sums its segment of frames in double, the segment sums are prefix-summed, and every thread then walks its own segment
+// from that start value -- the sequential depth is T / segments instead of T.  The running sums are sums of floats in
+// double: no rounding happens for features of ordinary dynamic range, so they equal the reference's (and are within
+// 1e-16 relative otherwise); everything after the sums is the code above.
+constexpr int kCmvnMaxSeg = 32;
+__global__ void __launch_bounds__(1024) cmvn_seg_kernel(CmvnParams p, int nseg) {
+  extern __shared__ double segsum[];  // [2][nseg][dim]
+  const int u = blockIdx.x, d = threadIdx.x % p.dim, seg = threadIdx.x / p.dim;
+  const int T = p.num_frames[u];
+  const float *in = p.in + (size_t)p.frame_offset[u] * p.dim;
+  float *out = p.out + (size_t)p.frame_offset[u] * p.dim;
+  const double g0 = p.global_stats[d], g1 = p.global_stats[(p.dim + 1) + d], gcount = p.global_stats[p.dim];
+  if (T > p.cmn_window) {
+    // longer than the window: the sequential form (add frame t, subtract frame t - window)
+    if (seg != 0) return;
+    double s0 = 0.0, s1 = 0.0, cnt = 0.0;
+    for (int t = 0; t < T; t++) {
+      const float xin = in[(size_t)t * p.dim + d];
+      double x = (double)xin;
+      s0 += x;
+      if (p.normalize_variance) s1 += x * x;
+      cnt += 1.0;
+      const int prev = t - p.cmn_window;
+      if (prev >= 0) {
+        double y = (double)in[(size_t)prev * p.dim + d];
+        s0 -= y;
+        if (p.normalize_variance) s1 -= y * y;
+        cnt -= 1.0;
+      }
+      out[(size_t)t * p.dim + d] = CmvnApply(p, xin, s0, s1, cnt, g0, g1, gcount);
+    }
+    return;
+  }
+  const int per = (T + nseg - 1) / nseg, t0 = seg * per, t1 = min(T, t0 + per);
+  double a0 = 0.0, a1 = 0.0;
+  for (int t = t0; t < t1; t++) {
+    const double x = (double)in[(size_t)t * p.dim + d];
+    a0 += x;
+    if (p.normalize_variance) a1 += x * x;
+  }
+  segsum[seg * p.dim + d] = a0;
+  segsum[(nseg + seg) * p.dim + d] = a1;
+  __syncthreads();
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < seg; k++) {
+    s0 += segsum[k * p.dim + d];
+    s1 += segsum[(nseg + k) * p.dim + d];
+  }
+  for (int t = t0; t < t1; t++) {
+    const float xin = in[(size_t)t * p.dim + d];
+    const double x = (double)xin;
+    s0 += x;
+    if (p.normalize_variance) s1 += x * x;
+    out[(size_t)t * p.dim + d] = CmvnApply(p, xin, s0, s1, (double)(t + 1), g0, g1, gcount);
+  }
+}
+
 void LaunchCmvn(const CmvnParams &p, int n_utts, cudaStream_t stream) {
   if (n_utts == 0) return;
+  int nseg = 1024 / p.dim;
+  if (nseg > kCmvnMaxSeg) nseg = kCmvnMaxSeg;
+  if (nseg >= 2) {
+    cmvn_seg_kernel<<<n_utts, nseg * p.dim, (size_t)2 * nseg * p.dim * sizeof(double), stream>>>(p, nseg);
+    RS_CHECK_LAUNCH("cmvn_seg_kernel");
+    return;
+  }
   int threads = ((p.dim + 31) / 32) * 32;
   cmvn_kernel<<<n_utts, threads, 0, stream>>>(p);
+  RS_CHECK_LAUNCH("cmvn_kernel");
 }
 
 // ---------------------------------------------------------------------------- splice + LDA
@@ -359,15 +461,21 @@ __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
 // ---------------------------------------------------------------------------- statistics
 // wf[u][g][:] += w * x_t  (double; order-insensitive at 1e-16) ; gw[u][g] = float sum over frames in
 // frame order (GaussInfo::tot_weight is a float accumulated in frame order).
+// Solves of one utterance are cumulative (solve j covers the first v_num_frames[j] frames, online schedule): every frame
+// is accumulated ONCE, into the first solve that contains it, and ivec_prefix_kernel then adds the solves up in order.
+// (Round 1 re-accumulated all frames of every solve: 3.6 of the 6.8 ms of device time of 64 concurrent streams.)
 __global__ void __launch_bounds__(256) ivec_acc_kernel(IvecParams p) {
   const int u = blockIdx.y;  // solve index
   const int T = p.v_num_frames[u];
   const size_t base = (size_t)p.v_frame_offset[u];
+  // frames the previous solve of the same utterance already covers (same feature rows <=> same utterance; an utterance
+  // without frames shares its offset with the next one and contributes nothing either way)
+  const int T0 = u > 0 && p.v_frame_offset[u - 1] == p.v_frame_offset[u] ? min(p.v_num_frames[u - 1], T) : 0;
   const float *feats = p.online_cmvn_iextractor ? p.x_norm : p.x_raw;
   const int D = p.ldim, S = p.num_gselect;
   double *wf = p.wf + (size_t)u * p.num_gauss * D;
   const int per = S * D;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)T * per;
+  for (long long i = (long long)T0 * per + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)T * per;
        i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i / per), r = (int)(i - (long long)t * per);
     int s = r / D, d = r - s * D;
@@ -378,27 +486,51 @@ __global__ void __launch_bounds__(256) ivec_acc_kernel(IvecParams p) {
   }
 }
 
+// wf[j] += wf[j - 1] over the solves of an utterance, in order (one thread per (g, d) element)
+__global__ void __launch_bounds__(256) ivec_prefix_kernel(IvecParams p) {
+  const int u = blockIdx.y;  // utterance
+  const int j0 = p.v_begin[u], j1 = p.v_begin[u + 1];
+  const size_t n = (size_t)p.num_gauss * p.ldim;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    double run = p.wf[(size_t)j0 * n + e];
+    for (int j = j0 + 1; j < j1; j++) {
+      run += p.wf[(size_t)j * n + e];
+      p.wf[(size_t)j * n + e] = run;
+    }
+  }
+}
+
+// gw[j][g]: the float sum of the posteriors of Gaussian g over the first v_num_frames[j] frames IN FRAME ORDER
+// (GaussInfo::tot_weight): one thread per Gaussian walks the utterance once and records the running sum at every
+// solve boundary -- the same sequence of additions as a separate pass per solve.
 __global__ void __launch_bounds__(256) ivec_gw_kernel(IvecParams p) {
-  const int u = blockIdx.y;  // solve index
+  const int u = blockIdx.y;  // utterance
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int T = p.v_num_frames[u], S = p.num_gselect;
-  const size_t base = (size_t)p.v_frame_offset[u];
+  const int S = p.num_gselect;
+  const int j0 = p.v_begin[u], j1 = p.v_begin[u + 1];
+  if (j0 >= j1) return;
+  const size_t base = (size_t)p.v_frame_offset[j0];
   extern __shared__ int spost[];  // tile of posteriors: idx then weight bits
   float acc = 0.f;
   const int tile = 256;
-  for (int t0 = 0; t0 < T * S; t0 += tile) {
-    int n = min(tile, T * S - t0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      spost[i] = p.post_idx[base * S + t0 + i];
-      spost[tile + i] = __float_as_int(p.post_w[base * S + t0 + i]);
+  int done = 0;  // posteriors consumed so far
+  for (int j = j0; j < j1; j++) {
+    const int upto = max(p.v_num_frames[j], 0) * S;
+    while (done < upto) {
+      const int n = min(tile, upto - done);
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        spost[i] = p.post_idx[base * S + done + i];
+        spost[tile + i] = __float_as_int(p.post_w[base * S + done + i]);
+      }
+      __syncthreads();
+      if (g < p.num_gauss)
+        for (int i = 0; i < n; i++)
+          if (spost[i] == g) acc = __fadd_rn(acc, __int_as_float(spost[tile + i]));
+      done += n;
     }
-    __syncthreads();
-    if (g < p.num_gauss)
-      for (int i = 0; i < n; i++)
-        if (spost[i] == g) acc = __fadd_rn(acc, __int_as_float(spost[tile + i]));
+    if (g < p.num_gauss) p.gw[(size_t)j * p.num_gauss + g] = acc;
   }
-  if (g < p.num_gauss) p.gw[(size_t)u * p.num_gauss + g] = acc;
 }
 
 // linear[u][r] = prior + sum_g sum_d sigma_inv_m[g][d][r] * wf[u][g][d]
@@ -408,6 +540,8 @@ __global__ void __launch_bounds__(256) ivec_gw_kernel(IvecParams p) {
 // kernel folds the partials in a fixed order (deterministic, unlike atomics).
 constexpr int kUT = 8;
 constexpr int kLinChunk = 512;
+// (Round 2, measured and dropped: the per-solve factors laid out [term][solve] and read as 16-byte broadcasts -- 155 -> 210 us
+//  and 187 -> 211 us; sixteen solves per CTA -- 268 / 258 us, too few CTAs.)
 __global__ void __launch_bounds__(128) ivec_linear_kernel(IvecParams p) {
   const int r = threadIdx.x;
   const int u0 = blockIdx.y * kUT;
@@ -582,18 +716,17 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
       dim3 g1((p.max_frames + kLdaFrames4 - 1) / kLdaFrames4, p.n_utts);
       size_t sm1 = (size_t)2 * (kLdaFrames4 + p.left + p.right) * p.dim * sizeof(float);
       splice_lda4_kernel<<<g1, 256, sm1, stream>>>(p);
+      RS_CHECK_LAUNCH("splice_lda4_kernel");
     } else {
       dim3 g1((p.max_frames + kLdaFrames - 1) / kLdaFrames, p.n_utts);
       size_t sm1 = (size_t)2 * (kLdaFrames + p.left + p.right) * p.dim * sizeof(float);
       splice_lda_kernel<<<g1, 256, sm1, stream>>>(p);
+      RS_CHECK_LAUNCH("splice_lda_kernel");
     }
     size_t sm2 = (size_t)kUbmFrames * (2 * D + G) * sizeof(float);
-    static size_t ubm_attr = 48 * 1024;
-    if (sm2 > ubm_attr) {
-      cudaFuncSetAttribute(ubm_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-      ubm_attr = sm2;
-    }
+    EnsureDynSmem(ubm_post_kernel, sm2);
     ubm_post_kernel<<<(p.total_frames + kUbmFrames - 1) / kUbmFrames, 256, sm2, stream>>>(p);
+    RS_CHECK_LAUNCH("ubm_post_kernel");
   }
   cudaMemsetAsync(p.wf, 0, (size_t)p.v_n * G * D * sizeof(double), stream);
   if (p.total_frames > 0) {
@@ -601,18 +734,25 @@ void LaunchIvector(const IvecParams &p, cudaStream_t stream) {
     if (per_utt_blocks > 64) per_utt_blocks = 64;
     if (per_utt_blocks < 1) per_utt_blocks = 1;
     ivec_acc_kernel<<<dim3(per_utt_blocks, p.v_n), 256, 0, stream>>>(p);
+    RS_CHECK_LAUNCH("ivec_acc_kernel");
   }
-  ivec_gw_kernel<<<dim3((G + 255) / 256, p.v_n), 256, 2 * 256 * sizeof(int), stream>>>(p);
+  if (p.v_n > p.n_utts) {  // online schedule: several cumulative solves per utterance
+    ivec_prefix_kernel<<<dim3((G * D + 255) / 256, p.n_utts), 256, 0, stream>>>(p);
+    RS_CHECK_LAUNCH("ivec_prefix_kernel");
+  }
+  ivec_gw_kernel<<<dim3((G + 255) / 256, p.n_utts), 256, 2 * 256 * sizeof(int), stream>>>(p);
+  RS_CHECK_LAUNCH("ivec_gw_kernel");
   int groups = (p.v_n + kUT - 1) / kUT;
+  const size_t sm_quad = (size_t)kUT * G * sizeof(double);
+  EnsureDynSmem(ivec_quad_kernel, sm_quad);
   ivec_linear_kernel<<<dim3(p.linear_chunks, groups), 128, 0, stream>>>(p);
-  ivec_quad_kernel<<<dim3((P + 127) / 128, groups), 128, (size_t)kUT * G * sizeof(double), stream>>>(p);
+  RS_CHECK_LAUNCH("ivec_linear_kernel");
+  ivec_quad_kernel<<<dim3((P + 127) / 128, groups), 128, sm_quad, stream>>>(p);
+  RS_CHECK_LAUNCH("ivec_quad_kernel");
   size_t sm3 = ((size_t)R * R + 5 * R + 8) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ivec_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  EnsureDynSmem(ivec_cg_kernel, sm3);
   ivec_cg_kernel<<<p.n_utts, 128, sm3, stream>>>(p);
+  RS_CHECK_LAUNCH("ivec_cg_kernel");
 }
 
 }  // namespace rs
