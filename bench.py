@@ -33,8 +33,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BATCH = 256
-# DRAM bytes the nnet stage moved in one step under ncu (profiles/r1_launches_i_dram.csv): 7.39 GB read + 3.06 GB written
-NNET_DRAM_BYTES_PER_STEP = 10454000000
+# DRAM bytes the 30 launches of the nnet stage moved in one step under ncu (profiles/r2f_launches.csv, round 2;
+# round 1: 10.45 GB)
+NNET_DRAM_BYTES_PER_STEP = 9424915200
 METRIC = "RTFx (audio-sec/wall-sec) en_US-zamia 16kHz at 1/2/4/8 B200; WER vs ref"
 UNIT = "audio-sec/wall-sec"
 WORKLOAD = "configs[1]: batch=256 per GPU, grammar-HCLG, 3-5 s 16 kHz utterances cut from tests/en_US-zamia WAVs (+ sigma=2 noise)"
@@ -378,18 +379,18 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "stages_ms": {"feature": float(sm[:, 0].mean()), "nnet": nnet_ms, "decode": float(sm[:, 2].mean()),
                           "h2d": float(sm[:, 3].mean()), "d2h": float(sm[:, 4].mean())},
-            # dominant kernel = gemm_tc_kernel (30 launches per step, the whole nnet stage between two CUDA
+            # dominant kernel = gemm_tc3_kernel (30 launches per step, the whole nnet stage between two CUDA
             # events on the decoder's stream).  achieved = algorithmic FLOPs (2*rows*K*N per layer, counted
             # once although every product is 3 MMAs => attainable frac <= 1/3) / stage time.
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (TDNN-F affine layers, 30 launches = the nnet stage)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc3_kernel (TDNN-F affine layers, 30 launches = the nnet stage)",
                          "achieved": achieved, "peak": f16_peak, "unit": "TFLOP/s", "frac": achieved / f16_peak,
                          "traffic": NNET_DRAM_BYTES_PER_STEP,
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the stage's launches, "
-                                           "profiles/r1_launches_i_dram.csv (same command, batch 256)",
+                                           "profiles/r2f_launches.csv (same workload, batch 256)",
                          "peak_source": pk_kind + " bf16_tflops_sustained (fp16 tensor pipe)",
                          "note": "3 MMAs per algorithmic product: attainable frac <= 0.333"},
             # the same launches against HBM: the stage streams every layer's activations through HBM once
-            "roofline_hbm": {"bound": "hbm", "kernel": "gemm_tc_kernel (same 30 launches)", "achieved": hbm_achieved,
+            "roofline_hbm": {"bound": "hbm", "kernel": "gemm_tc3_kernel (same 30 launches)", "achieved": hbm_achieved,
                              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
                              "traffic": NNET_DRAM_BYTES_PER_STEP, "algorithmic_bytes": int(t["nnet_bytes"])},
             "decoder_counters": {k: int(t[k]) for k in ("frames_decoded", "tokens_expanded", "arcs_visited", "tokens_created")},

@@ -336,18 +336,67 @@ constexpr int kUbmFrames = 16;
 __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
   extern __shared__ float sm[];
   const int D = p.ldim, G = p.num_gauss;
-  float *sx = sm, *sxsq = sx + kUbmFrames * D, *sll = sxsq + kUbmFrames * D;  // [F][D], [F][D], [F][G]
+  float *sx = sm, *sxsq = sx + kUbmFrames * D, *sll = sxsq + kUbmFrames * D;  // [D][F], [D][F], [F][G]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kUbmFrames;
   const int nrows = min(kUbmFrames, p.total_frames - row0);
+  // features transposed [d][frame]: the eight frames of a thread are two 16-byte broadcast loads
   for (int i = tid; i < kUbmFrames * D; i += 256) {
-    const int f = i / D;
+    const int f = i / D, d = i - f * D;
     const float v = f < nrows ? p.x_norm[(size_t)row0 * D + i] : 0.f;
-    sx[i] = v;
-    sxsq[i] = __fmul_rn(v, v);
+    sx[d * kUbmFrames + f] = v;
+    sxsq[d * kUbmFrames + f] = __fmul_rn(v, v);
   }
   __syncthreads();
-  {
+  if ((G & 3) == 0) {
+    // 8 frames x 4 CONSECUTIVE Gaussians per thread: one 16-byte load per table row and table, prefetched one row
+    // ahead, and four 16-byte broadcast loads of the features feed 64 FMAs (round 1: 24 scalar loads per 64 FMAs, the
+    // FMAs waited for the table loads).  Every sum still runs over d in ascending order with one FMA per term.
+    const int tg = tid & 127, tf = tid >> 7;  // 128 groups of 4 Gaussians x 2 groups of 8 frames
+    for (int g0 = 0; g0 < G; g0 += 512) {
+      const int gb = g0 + tg * 4;
+      const bool on = gb < G;
+      float a1[8][4], a2[8][4];
+#pragma unroll
+      for (int f = 0; f < 8; f++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) a1[f][j] = a2[f][j] = 0.f;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 mn = on ? __ldg(reinterpret_cast<const float4 *>(p.means_invvars_t + gb)) : zero4;
+      float4 vn = on ? __ldg(reinterpret_cast<const float4 *>(p.inv_vars_t + gb)) : zero4;
+      for (int d = 0; d < D; d++) {
+        const float4 m4 = mn, v4 = vn;
+        if (d + 1 < D && on) {
+          mn = __ldg(reinterpret_cast<const float4 *>(p.means_invvars_t + (size_t)(d + 1) * G + gb));
+          vn = __ldg(reinterpret_cast<const float4 *>(p.inv_vars_t + (size_t)(d + 1) * G + gb));
+        }
+        const float4 xa = *reinterpret_cast<const float4 *>(sx + d * kUbmFrames + tf * 8), xb = *reinterpret_cast<const float4 *>(sx + d * kUbmFrames + tf * 8 + 4);
+        const float4 qa = *reinterpret_cast<const float4 *>(sxsq + d * kUbmFrames + tf * 8), qb = *reinterpret_cast<const float4 *>(sxsq + d * kUbmFrames + tf * 8 + 4);
+        const float xf[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w}, x2[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w}, iv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int f = 0; f < 8; f++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            a1[f][j] = fmaf(xf[f], m[j], a1[f][j]);
+            a2[f][j] = fmaf(x2[f], iv[j], a2[f][j]);
+          }
+      }
+      if (on) {
+        const float4 gc4 = __ldg(reinterpret_cast<const float4 *>(p.gconsts + gb));
+        const float gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
+#pragma unroll
+        for (int f = 0; f < 8; f++) {
+          float4 o;
+          o.x = __fadd_rn(__fadd_rn(gc[0], a1[f][0]), __fmul_rn(-0.5f, a2[f][0]));
+          o.y = __fadd_rn(__fadd_rn(gc[1], a1[f][1]), __fmul_rn(-0.5f, a2[f][1]));
+          o.z = __fadd_rn(__fadd_rn(gc[2], a1[f][2]), __fmul_rn(-0.5f, a2[f][2]));
+          o.w = __fadd_rn(__fadd_rn(gc[3], a1[f][3]), __fmul_rn(-0.5f, a2[f][3]));
+          *reinterpret_cast<float4 *>(sll + (size_t)(tf * 8 + f) * G + gb) = o;
+        }
+      }
+    }
+  } else {
     const int tg = tid & 63, tf = tid >> 6;  // 64 Gaussian lanes x 4 frame groups of 4 frames
     for (int g0 = 0; g0 < G; g0 += 512) {
       float a1[4][8], a2[4][8];
@@ -365,7 +414,7 @@ __global__ void __launch_bounds__(256) ubm_post_kernel(IvecParams p) {
         }
 #pragma unroll
         for (int f = 0; f < 4; f++) {
-          const float xf = sx[(tf * 4 + f) * D + d], x2 = sxsq[(tf * 4 + f) * D + d];
+          const float xf = sx[d * kUbmFrames + tf * 4 + f], x2 = sxsq[d * kUbmFrames + tf * 4 + f];
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             a1[f][j] = fmaf(xf, m[j], a1[f][j]);
