@@ -264,6 +264,28 @@ class _Engine:
         return " ".join(out)
 
 
+# Audio bytes outstanding per DEVICE, over all transcribers of the process: several (model, graph) pairs share the
+# devices, and a request list is only split over as many devices as it can fill.
+_DEVICE_BYTES: Dict[int, float] = {}
+_DEVICE_BYTES_LOCK = threading.Lock()
+# a share smaller than this no longer fills a GPU (8 MB of 16-bit 16 kHz PCM ~ 64 utterances of 4 s): shorter lists go
+# to fewer devices.  (Measured on 2 GPUs, 8 pairs x 256 short utterances = 16 MB each: split over both devices 37.9 ms,
+# whole lists on the less loaded device 45.5 ms per 2048 utterances -- run-to-run spread of the concurrent calls is
+# larger than the difference, scripts/debug_pool.py.)
+_SHARE_TARGET_BYTES = float(os.environ.get("RS_B200_SHARE_TARGET_MB", "8")) * (1 << 20)
+
+
+def plan_shares(sizes: Sequence[float], devices: Sequence[int], outstanding: Dict[int, float],
+                target: float) -> List[Tuple[int, List[int]]]:
+    """(position in `devices`, utterance indices) per share: the list goes to the k least-loaded devices, k = as many
+    as it can fill with `target` bytes each, dealt longest-first (shard.shard_utterances)."""
+    from .shard import shard_utterances
+    total = float(sum(sizes))
+    k = int(max(1, min(len(devices), round(total / target) if target > 0 else len(devices))))
+    order = sorted(range(len(devices)), key=lambda i: (outstanding.get(devices[i], 0.0), i))[:k]
+    return [(order[j], idx) for j, idx in enumerate(shard_utterances(sizes, k))]
+
+
 def _load(eng) -> int:
     b = getattr(eng, "batcher", None)
     return (len(b.pending) + getattr(b, "running", 0) if b is not None else 0) + getattr(eng, "open_streams", 0)
@@ -481,20 +503,27 @@ class KaldiNnet3WavTranscriber(_Base):
         """Batched extension: element i equals async_transcribe(wav_paths[i]).  One device batch per engine: with several
         devices the list is dealt longest-first (file size = duration) so that every GPU gets the same audio seconds, and
         the shares run concurrently (no collective -- the results are word ids gathered by this thread)."""
-        from .shard import shard_utterances
         loop = asyncio.get_running_loop()
-        engines = await loop.run_in_executor(None, self._get_engines)
+        all_engines = await loop.run_in_executor(None, self._get_engines)
         paths = [str(p) for p in wav_paths]
-        if len(engines) > 1:
+        if len(all_engines) > 1:
             sizes = []
             for p in paths:
                 try:
                     sizes.append(float(os.path.getsize(p)))
                 except OSError:
                     sizes.append(0.0)           # a missing file fails in its own share with the loader's message
-            shares = shard_utterances(sizes, len(engines))
+            # as many devices as the list can fill, the least-loaded ones first (other transcribers of the process --
+            # other (model, graph) pairs -- share the devices: _DEVICE_BYTES counts the audio outstanding on each)
+            with _DEVICE_BYTES_LOCK:
+                plan = plan_shares(sizes, [e.device for e in all_engines], _DEVICE_BYTES, _SHARE_TARGET_BYTES)
+                booked = [(all_engines[pos].device, float(sum(sizes[i] for i in idx))) for pos, idx in plan]
+                for dev, b in booked:
+                    _DEVICE_BYTES[dev] = _DEVICE_BYTES.get(dev, 0.0) + b
+            engines = [all_engines[pos] for pos, _ in plan]
+            shares = [idx for _, idx in plan]
         else:
-            shares = [list(range(len(paths)))]
+            engines, shares, booked = all_engines, [list(range(len(paths)))], []
 
         def run(eng, idx):
             if not idx:
@@ -505,7 +534,12 @@ class KaldiNnet3WavTranscriber(_Base):
                     return eng.decoder.decode_wavs([paths[i] for i in idx]), eng.decoder.graph
                 except _lib.RsError as e:
                     raise RuntimeError("Unexpected error running command online2-wav-nnet3-latgen-faster: %s" % e) from e
-        parts = await asyncio.gather(*[loop.run_in_executor(None, run, eng, idx) for eng, idx in zip(engines, shares)])
+        try:
+            parts = await asyncio.gather(*[loop.run_in_executor(None, run, eng, idx) for eng, idx in zip(engines, shares)])
+        finally:
+            with _DEVICE_BYTES_LOCK:
+                for dev, b in booked:
+                    _DEVICE_BYTES[dev] = max(0.0, _DEVICE_BYTES.get(dev, 0.0) - b)
         out: List[Optional[List[str]]] = [None] * len(paths)
         fuzzy = (Path(lang_dir) / "G.fuzzy.fst").exists()       # one stat for the whole list
         for eng, idx, (hyp, graph) in zip(engines, shares, parts):

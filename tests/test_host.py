@@ -371,9 +371,10 @@ def test_multi_device_pool_deals_requests_over_engines(tmp_path, monkeypatch):
     for k in range(3):
         dec = FakeDecoder("gpu%d" % k)
         lock = threading.Lock()
-        engines.append(SimpleNamespace(decoder=dec, lock=lock, graph=dec.graph, batcher=T._Batcher(dec, lock), open_streams=0,
+        engines.append(SimpleNamespace(decoder=dec, lock=lock, graph=dec.graph, batcher=T._Batcher(dec, lock), open_streams=0, device=k,
                                        words=lambda ids, graph=None: " ".join("w%d" % i for i in ids)))
     monkeypatch.setattr(T._Base, "_get_engines", lambda self: engines)
+    monkeypatch.setattr(T, "_SHARE_TARGET_BYTES", 8000.0)               # ~ a third of the list below: it fills three devices
     tr = T.KaldiNnet3WavTranscriber(tmp_path, tmp_path, None, device=[0, 1, 2])
     paths = []
     for i in range(20):
@@ -388,6 +389,20 @@ def test_multi_device_pool_deals_requests_over_engines(tmp_path, monkeypatch):
     loads = [sum(os.path.getsize(p) for p in s) for s in shares]
     assert max(loads) - min(loads) <= 11 * 977                           # equal audio per device (longest-first deal)
     assert time.monotonic() - t0 < 0.14                                  # the three shares ran side by side, not 3 x 50 ms
+    assert not any(T._DEVICE_BYTES.get(k, 0.0) for k in range(3))        # the booking is released
+    # a list too small to fill more than one device stays whole and goes to the least-loaded device: with several
+    # (model, graph) pairs active, every device then runs full batches instead of every pair splitting its list
+    monkeypatch.setattr(T, "_SHARE_TARGET_BYTES", 1.0e9)
+    for e in engines:
+        e.decoder.calls.clear()
+    async def two_lists():
+        return await asyncio.gather(tr.async_transcribe_many(paths[:10], tmp_path), tr.async_transcribe_many(paths[10:], tmp_path))
+    a, b = asyncio.run(two_lists())
+    assert a == [["w%d" % i] for i in range(10)] and b == [["w%d" % i] for i in range(10, 20)]
+    used = [e.decoder.calls for e in engines if e.decoder.calls]
+    assert len(used) == 2 and sorted(len(c[0]) for c in used) == [10, 10]   # two whole lists on two different devices
+    plan = T.plan_shares([5.0, 1.0, 4.0, 2.0], [7, 8, 9], {7: 100.0, 8: 0.0, 9: 3.0}, 6.0)
+    assert plan == [(1, [0, 1]), (2, [2, 3])]                            # two shares of 6 on the two least-loaded devices
     # single requests spread over the pool
     async def burst():
         return await asyncio.gather(*[tr.async_transcribe(paths[i], tmp_path) for i in range(9)])
