@@ -141,6 +141,12 @@ int rs_decoder_set_graph(rs_decoder *d, rs_graph *g, char *err, size_t errlen);
  * its best path and carries status bit 5. */
 int rs_decoder_set_nbest(rs_decoder *d, int32_t nbest, float acoustic_scale, char *err, size_t errlen);
 
+/* Host staging of a call (no reference counterpart: the reference reads one WAV per process, feat/wave-reader.cc).
+ * on != 0 (default): the audio goes to the device in a few items on a copy stream and the MFCC kernel of an item runs
+ * under the copy of the next; on == 0: one stream, copies first, then every kernel -- the stage times of rs_timings
+ * are then those of a batch already resident in device memory (what bench.py reports as `value`). */
+int rs_decoder_set_staging_overlap(rs_decoder *d, int32_t on, char *err, size_t errlen);
+
 /* Replaces one run of `online2-wav-nnet3-latgen-faster --online=false ... | lattice-to-nbest --n=1 |
  * nbest-to-linear` per utterance (transcribe_wav.py:45-75), for n utterances at once.
  * pcm[i] = 16 kHz mono s16 samples, unscaled as WaveData reads them (feat/wave-reader.cc:153-320). */

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("rs_fuzzy_word", C.c_char_p, [_P, C.c_int32]),
     ("rs_decoder_set_graph", C.c_int, [_P, _P] + _ERR),
     ("rs_decoder_set_nbest", C.c_int, [_P, C.c_int32, C.c_float] + _ERR),
+    ("rs_decoder_set_staging_overlap", C.c_int, [_P, C.c_int32] + _ERR),
     ("rs_debug_lattice_nbest", C.c_int, [_P] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, _P]),
     ("rs_debug_read_matrix", C.c_int, [C.c_char_p, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + _ERR),
     ("rs_debug_strict_decode", C.c_int, [C.c_char_p, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(DecoderOpts), C.c_int32,
@@ -429,6 +430,12 @@ class Decoder:
         """lattice-to-nbest --n / --acoustic-scale for every later decode call (rs_decoder_set_nbest)."""
         err = C.create_string_buffer(ERRLEN)
         rc = self.lib.rs_decoder_set_nbest(self.h, int(nbest), float(acoustic_scale), err, ERRLEN)
+        _check(rc == 0, err)
+
+    def set_staging_overlap(self, on: bool = True):
+        """Copy stream + per-item MFCC launches (default) or one stream with separate stage times (rs_decoder_set_staging_overlap)."""
+        err = C.create_string_buffer(ERRLEN)
+        rc = self.lib.rs_decoder_set_staging_overlap(self.h, 1 if on else 0, err, ERRLEN)
         _check(rc == 0, err)
 
     def _take(self, rc: int, res, err) -> Hypotheses:

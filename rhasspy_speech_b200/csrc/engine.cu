@@ -380,12 +380,20 @@ struct GraphImpl {
 
 struct StreamImpl;
 
+constexpr int kMaxStagingItems = 64;
+
 struct DecoderImpl {
   ModelImpl *model = nullptr;
   GraphImpl *graph = nullptr;
   rs_decoder_opts opts{};
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // audio H2D copies of a staged batch (the feature kernels of item k run under the copy of item k + 1)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t item_ev[kMaxStagingItems] = {};
+  bool staging_overlap = true;  // rs_decoder_set_staging_overlap
+  int *d_item_flag = nullptr;   // [kMaxStagingItems] written behind each item's copy, polled by that item's MFCC kernel
+  int *h_item_seq = nullptr;    // pinned source words of those flag copies
+  int staging_seq = 0;
   int n_lanes = 0;
   std::vector<void *> owned;
   DevBuf d_pcm, d_desc, d_mfcc, d_mfcc_norm, d_xraw, d_xnorm, d_post_idx, d_post_w, d_wf, d_gw, d_linear, d_quad;
@@ -429,8 +437,13 @@ struct DecoderImpl {
     for (void *p : lane_owned) cudaFree(p);
     for (auto &e : ev)
       if (e) cudaEventDestroy(e);
+    for (auto &e : item_ev)
+      if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
     if (h_range_flag) cudaFreeHost(h_range_flag);
+    if (h_item_seq) cudaFreeHost(h_item_seq);
+    if (d_item_flag) cudaFree(d_item_flag);
   }
 };
 
@@ -851,7 +864,12 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
   if (o.max_tokens_per_frame < 1024) o.max_tokens_per_frame = 1024;
   if (o.max_words < 1) o.max_words = 1;
   CUDA_OK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   for (auto &e : d->ev) CUDA_OK(cudaEventCreate(&e));
+  for (auto &e : d->item_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUDA_OK(cudaMalloc(&d->d_item_flag, sizeof(int) * kMaxStagingItems));
+  CUDA_OK(cudaMemset(d->d_item_flag, 0, sizeof(int) * kMaxStagingItems));
+  CUDA_OK(cudaHostAlloc(&d->h_item_seq, sizeof(int) * kMaxStagingItems, cudaHostAllocDefault));
   BindGraph(d.get(), gi);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
@@ -915,6 +933,15 @@ int rs_decoder_set_nbest(rs_decoder *d_, int32_t nbest, float acoustic_scale, ch
   if (nbest < 1 || !(acoustic_scale == acoustic_scale)) RS_FAIL("rs_decoder_set_nbest: n must be >= 1");
   d->nbest = nbest;
   d->nbest_scale = acoustic_scale;
+  return 0;
+  API_GUARD_END(1)
+}
+
+int rs_decoder_set_staging_overlap(rs_decoder *d_, int32_t on, char *err, size_t errlen) {
+  API_GUARD_BEGIN
+  DecoderImpl *d = reinterpret_cast<DecoderImpl *>(d_);
+  if (!d) RS_FAIL("rs_decoder_set_staging_overlap: null decoder");
+  d->staging_overlap = on != 0;
   return 0;
   API_GUARD_END(1)
 }
@@ -1471,8 +1498,12 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   // the device as soon as it is complete, so the H2D copies overlap the packing of the later items.
   static const int item_shift = getenv("RS_B200_PACK_ITEM_SHIFT") ? atoi(getenv("RS_B200_PACK_ITEM_SHIFT")) : 21;
   int n_items = (int)std::min<size_t>(std::max<size_t>(pcm_bytes >> item_shift, 1), 64);
+  // page-locked caller memory: nothing to pack, but the copy is still cut into a few items so that the MFCC kernel of
+  // one item runs under the copy of the next (RS_B200_DIRECT_ITEMS, default 4 items of at least 2 MB: the MFCC
+  // kernel of an eighth of batch 256 is a wave and a third of warps, and eight of those take longer than the copies)
+  static const int direct_items = getenv("RS_B200_DIRECT_ITEMS") ? std::max(1, std::min(kMaxStagingItems, atoi(getenv("RS_B200_DIRECT_ITEMS")))) : 4;
+  if (direct_base) n_items = d->staging_overlap ? std::min(n_items, direct_items) : 1;
   if (n_items > n) n_items = n;
-  if (direct_base) n_items = 1;  // one copy, nothing to pack
   std::vector<int> range_begin(n_items + 1, n);
   {
     int u = 0;
@@ -1557,31 +1588,83 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   fp.pcm = dpcm;
   fp.mfcc = d_mfcc;
   fp.seed = d->opts.dither_seed;
-  // RS_B200_OVERLAP_STAGING=1 launches the MFCC kernel of a staging item right behind the item's H2D copy, so
-  // the GPU computes features of the first items while the host is still packing the later ones.  Measured
-  // neutral at batch 256 (e2e 11.46 vs 11.36 ms: the copies, not the kernel, fill that window), so the default
-  // keeps the copy and the first kernel apart, which also keeps the per-stage event times clean.
-  const char *ov = getenv("RS_B200_OVERLAP_STAGING");
-  const bool overlap = pooled && ov && ov[0] == '1';
+  // The audio copies of a staged batch go through a second stream, item by item; the MFCC kernel of an item waits
+  // for that item's copy only, so it runs while the next item is still on the bus (and, for pageable input, while
+  // the host packs the later ones).  RS_B200_OVERLAP_STAGING=0 keeps copies and kernels on one stream (the stage
+  // times of rs_timings are then cleanly separated: with the overlap, h2d_ms ends when the last copy has landed and
+  // contains the MFCC kernels of the earlier items).
+  static const bool overlap_env = !(getenv("RS_B200_OVERLAP_STAGING") && getenv("RS_B200_OVERLAP_STAGING")[0] == '0');
+  const bool overlap = overlap_env && d->staging_overlap && n_items > 1;
+  std::vector<cudaEvent_t> prof_ev;  // RS_B200_HOST_PROFILE: (copy done, MFCC done) per item
+  // How the MFCC kernel of an item learns that its audio has landed.  A cross-stream event wait was measured first:
+  // the kernels then start only when the copy stream has run dry (all four quarter-batch kernels queue up behind the
+  // last copy, 1.13 ms for copies + three kernels against 0.62 + 0.45 one after the other).  So by default the kernels
+  // are launched without a stream dependency and every warp polls a flag word that a 4-byte copy writes behind the
+  // item's samples (RS_B200_STAGING_SYNC=event keeps the event form).
+  static const bool poll_env = !(getenv("RS_B200_STAGING_SYNC") && !strcmp(getenv("RS_B200_STAGING_SYNC"), "event"));
+  const bool poll = overlap && poll_env;
+  cudaEvent_t last_copy_ev = nullptr;
+  if (overlap) {
+    CUDA_OK(cudaStreamWaitEvent(d->copy_stream, d->ev[0], 0));
+    d->staging_seq = d->staging_seq == 0x7fffffff ? 1 : d->staging_seq + 1;
+  }
+  fp.wait_flag = nullptr;
+  fp.wait_value = 0;
   for (int w = 0; w < n_items; w++) {
     if (pooled) d->pool->WaitItem(w);
     else pack(w);
     const int u0 = range_begin[w], u1 = range_begin[w + 1];
     const int64_t s0 = u0 < n ? pcm_offset[u0] : total_samples;
     const int64_t s1 = u1 < n ? pcm_offset[u1] : total_samples;
-    if (s1 > s0)
-      CUDA_OK(cudaMemcpyAsync(dpcm + s0, hpcm + s0, sizeof(int16_t) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, d->stream));
-    if (overlap && u1 > u0) {
-      int mf = 0;
-      for (int u = u0; u < u1; u++) mf = std::max(mf, B.num_frames[u]);
-      fp.pcm_offset = d_pcm_off + u0;
-      fp.num_frames = d_nf + u0;
-      fp.frame_offset = d_fo + u0;
-      LaunchMfcc(fp, u1 - u0, mf, d->stream);
-      launches++;
+    cudaStream_t cs = overlap ? d->copy_stream : d->stream;
+    if (s1 > s0) CUDA_OK(cudaMemcpyAsync(dpcm + s0, hpcm + s0, sizeof(int16_t) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, cs));
+    if (overlap) {
+      if (poll) {
+        d->h_item_seq[w] = d->staging_seq;
+        CUDA_OK(cudaMemcpyAsync(d->d_item_flag + w, d->h_item_seq + w, sizeof(int), cudaMemcpyHostToDevice, d->copy_stream));
+      } else {
+        CUDA_OK(cudaEventRecord(d->item_ev[w], d->copy_stream));
+        CUDA_OK(cudaStreamWaitEvent(d->stream, d->item_ev[w], 0));
+      }
+      if (host_prof) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreate(&e));
+        CUDA_OK(cudaEventRecord(e, d->copy_stream));
+        prof_ev.push_back(e);
+      }
+      if (w == n_items - 1) {
+        if (poll) {  // the stage boundary (and everything behind the MFCC kernels) still waits for the last copy as an event
+          CUDA_OK(cudaEventRecord(d->item_ev[w], d->copy_stream));
+          last_copy_ev = d->item_ev[w];
+        } else {
+          CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+        }
+      }
+      if (u1 > u0) {
+        int mf = 0;
+        for (int u = u0; u < u1; u++) mf = std::max(mf, B.num_frames[u]);
+        fp.pcm_offset = d_pcm_off + u0;
+        fp.num_frames = d_nf + u0;
+        fp.frame_offset = d_fo + u0;
+        fp.wait_flag = poll ? d->d_item_flag + w : nullptr;
+        fp.wait_value = d->staging_seq;
+        LaunchMfcc(fp, u1 - u0, mf, d->stream);
+        launches++;
+      }
+      if (host_prof) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreate(&e));
+        CUDA_OK(cudaEventRecord(e, d->stream));
+        prof_ev.push_back(e);
+      }
     }
   }
-  CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  if (last_copy_ev) {
+    CUDA_OK(cudaStreamWaitEvent(d->stream, last_copy_ev, 0));
+    CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  }
+  if (!overlap) CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  fp.wait_flag = nullptr;
   {
     std::lock_guard<std::mutex> lk(pack_err_mu);
     if (!pack_err.empty()) {
@@ -1827,9 +1910,20 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   const double hp2 = now_ms();
   rs_result *r = RunDecodeStage(d, B.loglikes, B.ll_ld, d_r0, d_no, launches);
   FinishTimings(d, launches);
-  if (host_prof)
+  if (host_prof) {
     fprintf(stderr, "host ms: layout+pack+h2d issue %.3f | feature+nnet launches %.3f | decode launch+wait+result %.3f\n", hp1 - hp0,
             hp2 - hp1, now_ms() - hp2);
+    if (!prof_ev.empty()) {
+      fprintf(stderr, "staging items (ms after the call's first event): ");
+      for (size_t i = 0; i < prof_ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, d->ev[0], prof_ev[i]);
+        fprintf(stderr, i % 2 ? "mfcc %.3f | " : "copy %.3f ", ms);
+        cudaEventDestroy(prof_ev[i]);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   if (*d->h_range_flag) {
     rs_result_free(r);
     RS_FAIL("an activation exceeded the fp16 range (+-65504) of the tensor-core path; set RS_B200_GEMM=simt for this model");
