@@ -391,8 +391,8 @@ struct DecoderImpl {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t item_ev[kMaxStagingItems] = {};
   bool staging_overlap = true;  // rs_decoder_set_staging_overlap
-  int *d_item_flag = nullptr;   // [kMaxStagingItems] written behind each item's copy, polled by that item's MFCC kernel
-  int *h_item_seq = nullptr;    // pinned source words of those flag copies
+  int *d_item_flag = nullptr;   // written behind the first item's copy; staging_spin_kernel watches it
+  int *h_item_seq = nullptr;    // pinned source word of that flag copy
   int staging_seq = 0;
   int n_lanes = 0;
   std::vector<void *> owned;
@@ -451,6 +451,21 @@ struct StreamImpl {
   DecoderImpl *dec;
   std::vector<int16_t> pcm;
 };
+
+// One warp that keeps the decoder's stream busy until the first staged item has landed (or max_clk has passed).
+// Measured: a kernel that arrives on an idle stream while the copy stream still has copies queued is not started before
+// the last of them is done; with this warp in front, the stream is running when the first MFCC kernel arrives and the
+// kernels do run under the copies.  Nothing depends on what it sees (the host launches every MFCC kernel only after its
+// item's copy event), it holds one warp slot, and it leaves after max_clk whatever happens.
+__global__ void staging_spin_kernel(const int *flag, int value, long long max_clk) {
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.relaxed.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == value) break;
+    __nanosleep(128);
+  } while (clock64() - t0 < max_clk);
+}
 
 static int RoundUp(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -867,9 +882,10 @@ rs_decoder *rs_decoder_create(rs_model *m_, rs_graph *g_, const rs_decoder_opts 
   CUDA_OK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   for (auto &e : d->ev) CUDA_OK(cudaEventCreate(&e));
   for (auto &e : d->item_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CUDA_OK(cudaMalloc(&d->d_item_flag, sizeof(int) * kMaxStagingItems));
-  CUDA_OK(cudaMemset(d->d_item_flag, 0, sizeof(int) * kMaxStagingItems));
-  CUDA_OK(cudaHostAlloc(&d->h_item_seq, sizeof(int) * kMaxStagingItems, cudaHostAllocDefault));
+  CUDA_OK(cudaMalloc(&d->d_item_flag, sizeof(int)));
+  CUDA_OK(cudaMemset(d->d_item_flag, 0, sizeof(int)));
+  CUDA_OK(cudaHostAlloc(&d->h_item_seq, sizeof(int), cudaHostAllocDefault));
+
   BindGraph(d.get(), gi);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, mi->device));
@@ -1595,76 +1611,77 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
   // contains the MFCC kernels of the earlier items).
   static const bool overlap_env = !(getenv("RS_B200_OVERLAP_STAGING") && getenv("RS_B200_OVERLAP_STAGING")[0] == '0');
   const bool overlap = overlap_env && d->staging_overlap && n_items > 1;
-  std::vector<cudaEvent_t> prof_ev;  // RS_B200_HOST_PROFILE: (copy done, MFCC done) per item
-  // How the MFCC kernel of an item learns that its audio has landed.  A cross-stream event wait was measured first:
-  // the kernels then start only when the copy stream has run dry (all four quarter-batch kernels queue up behind the
-  // last copy, 1.13 ms for copies + three kernels against 0.62 + 0.45 one after the other).  So by default the kernels
-  // are launched without a stream dependency and every warp polls a flag word that a 4-byte copy writes behind the
-  // item's samples (RS_B200_STAGING_SYNC=event keeps the event form).
-  static const bool poll_env = !(getenv("RS_B200_STAGING_SYNC") && !strcmp(getenv("RS_B200_STAGING_SYNC"), "event"));
-  const bool poll = overlap && poll_env;
-  cudaEvent_t last_copy_ev = nullptr;
-  if (overlap) {
-    CUDA_OK(cudaStreamWaitEvent(d->copy_stream, d->ev[0], 0));
+  std::vector<cudaEvent_t> prof_ev;  // RS_B200_HOST_PROFILE: a mark behind every copy and every MFCC kernel
+  std::string prof_tag;
+  // How the MFCC kernel of an item learns that its audio has landed: the HOST waits for the item's copy event and then
+  // launches the kernel without any stream dependency.  Two device-side forms were measured and dropped: a cross-stream
+  // cudaStreamWaitEvent (the kernels then start only when the copy stream has run dry -- copies + three quarter-batch
+  // kernels 1.13 ms, against 0.62 + 0.45 one after the other), and kernels that poll a flag word written behind the
+  // samples (0.90 ms, but a spinning grid that fills the SMs deadlocks as soon as its copy shares a hardware queue with
+  // another decoder's kernels: eight engines per device in the pool).  RS_B200_STAGING_SYNC=event keeps the first form.
+  static const bool host_sync_env = !(getenv("RS_B200_STAGING_SYNC") && !strcmp(getenv("RS_B200_STAGING_SYNC"), "event"));
+  const bool host_sync = overlap && host_sync_env;
+  static const bool spin_env = !(getenv("RS_B200_STAGING_SPIN") && getenv("RS_B200_STAGING_SPIN")[0] == '0');
+  const bool spin = host_sync && spin_env;
+  if (overlap) CUDA_OK(cudaStreamWaitEvent(d->copy_stream, d->ev[0], 0));
+  if (spin) {
     d->staging_seq = d->staging_seq == 0x7fffffff ? 1 : d->staging_seq + 1;
+    staging_spin_kernel<<<1, 32, 0, d->stream>>>(d->d_item_flag, d->staging_seq, 2000000ll /* ~1 ms */);
+    launches++;
   }
-  fp.wait_flag = nullptr;
-  fp.wait_value = 0;
-  for (int w = 0; w < n_items; w++) {
-    if (pooled) d->pool->WaitItem(w);
-    else pack(w);
+  auto prof_mark = [&](cudaStream_t st) {
+    if (!host_prof) return;
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaEventRecord(e, st));
+    prof_ev.push_back(e);
+    prof_tag.push_back(st == d->stream ? 'k' : 'c');
+  };
+  auto queue_copy = [&](int w) {
     const int u0 = range_begin[w], u1 = range_begin[w + 1];
     const int64_t s0 = u0 < n ? pcm_offset[u0] : total_samples;
     const int64_t s1 = u1 < n ? pcm_offset[u1] : total_samples;
     cudaStream_t cs = overlap ? d->copy_stream : d->stream;
     if (s1 > s0) CUDA_OK(cudaMemcpyAsync(dpcm + s0, hpcm + s0, sizeof(int16_t) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, cs));
     if (overlap) {
-      if (poll) {
-        d->h_item_seq[w] = d->staging_seq;
-        CUDA_OK(cudaMemcpyAsync(d->d_item_flag + w, d->h_item_seq + w, sizeof(int), cudaMemcpyHostToDevice, d->copy_stream));
-      } else {
-        CUDA_OK(cudaEventRecord(d->item_ev[w], d->copy_stream));
-        CUDA_OK(cudaStreamWaitEvent(d->stream, d->item_ev[w], 0));
+      CUDA_OK(cudaEventRecord(d->item_ev[w], d->copy_stream));
+      if (spin && w == 0) {
+        *d->h_item_seq = d->staging_seq;
+        CUDA_OK(cudaMemcpyAsync(d->d_item_flag, d->h_item_seq, sizeof(int), cudaMemcpyHostToDevice, d->copy_stream));
       }
-      if (host_prof) {
-        cudaEvent_t e;
-        CUDA_OK(cudaEventCreate(&e));
-        CUDA_OK(cudaEventRecord(e, d->copy_stream));
-        prof_ev.push_back(e);
-      }
-      if (w == n_items - 1) {
-        if (poll) {  // the stage boundary (and everything behind the MFCC kernels) still waits for the last copy as an event
-          CUDA_OK(cudaEventRecord(d->item_ev[w], d->copy_stream));
-          last_copy_ev = d->item_ev[w];
-        } else {
-          CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
-        }
-      }
-      if (u1 > u0) {
-        int mf = 0;
-        for (int u = u0; u < u1; u++) mf = std::max(mf, B.num_frames[u]);
-        fp.pcm_offset = d_pcm_off + u0;
-        fp.num_frames = d_nf + u0;
-        fp.frame_offset = d_fo + u0;
-        fp.wait_flag = poll ? d->d_item_flag + w : nullptr;
-        fp.wait_value = d->staging_seq;
-        LaunchMfcc(fp, u1 - u0, mf, d->stream);
-        launches++;
-      }
-      if (host_prof) {
-        cudaEvent_t e;
-        CUDA_OK(cudaEventCreate(&e));
-        CUDA_OK(cudaEventRecord(e, d->stream));
-        prof_ev.push_back(e);
-      }
+      prof_mark(d->copy_stream);
     }
-  }
-  if (last_copy_ev) {
-    CUDA_OK(cudaStreamWaitEvent(d->stream, last_copy_ev, 0));
-    CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+  };
+  auto launch_item = [&](int w) {  // overlap only: the MFCC kernel of item w, once its copy is known to be done
+    if (host_sync) CUDA_OK(cudaEventSynchronize(d->item_ev[w]));
+    else CUDA_OK(cudaStreamWaitEvent(d->stream, d->item_ev[w], 0));
+    if (w == n_items - 1) CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
+    const int u0 = range_begin[w], u1 = range_begin[w + 1];
+    if (u1 > u0) {
+      int mf = 0;
+      for (int u = u0; u < u1; u++) mf = std::max(mf, B.num_frames[u]);
+      fp.pcm_offset = d_pcm_off + u0;
+      fp.num_frames = d_nf + u0;
+      fp.frame_offset = d_fo + u0;
+      LaunchMfcc(fp, u1 - u0, mf, d->stream);
+      launches++;
+    }
+    prof_mark(d->stream);
+  };
+  if (overlap && !pooled) {
+    // nothing to pack (page-locked caller memory): every copy is queued at once, the kernels follow them one by one
+    for (int w = 0; w < n_items; w++) queue_copy(w);
+    for (int w = 0; w < n_items; w++) launch_item(w);
+  } else {
+    for (int w = 0; w < n_items; w++) {
+      if (pooled) d->pool->WaitItem(w);
+      else pack(w);
+      queue_copy(w);
+      if (overlap && w > 0) launch_item(w - 1);  // while the copy of item w is on the bus
+    }
+    if (overlap) launch_item(n_items - 1);
   }
   if (!overlap) CUDA_OK(cudaEventRecord(d->ev[1], d->stream));
-  fp.wait_flag = nullptr;
   {
     std::lock_guard<std::mutex> lk(pack_err_mu);
     if (!pack_err.empty()) {
@@ -1914,11 +1931,11 @@ static rs_result *DecodePcm(DecoderImpl *d, const int16_t *const *pcm, const int
     fprintf(stderr, "host ms: layout+pack+h2d issue %.3f | feature+nnet launches %.3f | decode launch+wait+result %.3f\n", hp1 - hp0,
             hp2 - hp1, now_ms() - hp2);
     if (!prof_ev.empty()) {
-      fprintf(stderr, "staging items (ms after the call's first event): ");
+      fprintf(stderr, "staging marks in host order (ms after the call's first event; c = copy stream, k = kernel stream): ");
       for (size_t i = 0; i < prof_ev.size(); i++) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, d->ev[0], prof_ev[i]);
-        fprintf(stderr, i % 2 ? "mfcc %.3f | " : "copy %.3f ", ms);
+        fprintf(stderr, "%c %.3f ", prof_tag[i], ms);
         cudaEventDestroy(prof_ev[i]);
       }
       fprintf(stderr, "\n");

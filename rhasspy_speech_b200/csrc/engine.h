@@ -35,10 +35,6 @@ struct FeatParams {
   int mel_max_len;
   const float *dct_t;           // [num_bins][num_ceps]
   const float *lifter;          // [num_ceps] or null
-  // staged input (engine.cu): when set, every warp first waits until *wait_flag == wait_value -- the word is written
-  // by a 4-byte copy queued behind the audio copy of this launch's utterances on the copy stream
-  const int *wait_flag;
-  int wait_value;
 };
 void LaunchMfcc(const FeatParams &p, int n_utts, int max_frames, cudaStream_t stream);
 

@@ -40,20 +40,6 @@ mfcc_kernel(FeatParams p) {
   const int T = p.num_frames[u];
   const int t = blockIdx.x * kWarpsPerCta + warp;
   if (t >= T) return;  // whole warp exits together; only __syncwarp is used below
-  if (p.wait_flag) {
-    // the audio of this launch may still be on its way: the copy stream writes the flag word after the samples
-    if (lane == 0) {
-      const long long t0 = clock64();
-      int v;
-      for (;;) {
-        asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p.wait_flag) : "memory");
-        if (v == p.wait_value) break;
-        __nanosleep(256);
-        if (clock64() - t0 > (1ll << 33)) __trap();  // ~4 s: the copy never arrived
-      }
-    }
-    __syncwarp();
-  }
   const int N = p.padded, NH = N >> 1;
   float *xr = smem + (size_t)warp * (N + p.num_bins + 8);
   float *xi = xr + NH;

@@ -777,6 +777,10 @@ void LoadModel(const std::string &final_mdl, const std::string &online_conf, Mod
     bool umr = true, greedy = false;
     Take(iv, "use-most-recent-ivector", &umr);
     Take(iv, "greedy-ivector-extractor", &greedy);
+    // the two iVector schedules built here are the defaults of online-ivector-feature.h:93-112: the most recent estimate
+    // for every frame, no greedy history (online-ivector-feature.cc:348-353); anything else must not be answered silently
+    if (!umr) RS_FAIL(ivector_config << ": --use-most-recent-ivector=false (periodic iVector history) is not supported");
+    if (greedy) RS_FAIL(ivector_config << ": --greedy-ivector-extractor=true is not supported");
     if (!iv.empty()) RS_FAIL(ivector_config << ": unsupported option --" << iv.begin()->first);
     if (lda.empty() || gstats.empty() || ubm.empty() || ie.empty())
       RS_FAIL(ivector_config << ": --lda-matrix, --global-cmvn-stats, --diag-ubm and --ivector-extractor are required");

@@ -2,7 +2,8 @@
 differ the way the reference's language models do, every pair served by one transcriber over ALL visible GPUs
 (KaldiNnet3WavTranscriber(device="all"): one engine per device, request list dealt longest-first by shard.py, shares run
 concurrently, no collective).  Prints one JSON line: whole-job RTFx end to end from WAV paths to strings, and the same
-job on one device for the scaling efficiency.    python scripts/bench_config5.py [n_utts]"""
+job on one device for the scaling efficiency.    python scripts/bench_config5.py [n_utts | weak]
+"weak" = 2048 utterances per visible GPU (fixed work per device; the one-device run then decodes its 2048 only)."""
 import asyncio, dataclasses, json, os, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +14,8 @@ from tools import synth
 
 
 def main():
-    n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    weak = len(sys.argv) > 1 and sys.argv[1] == "weak"
+    n_utts = 2048 * _lib.device_count() if weak else int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     tmp = tempfile.mkdtemp()
     Z = synth.ZAMIA_LIKE
     variants = [Z, dataclasses.replace(Z, name="v1", seed=11), dataclasses.replace(Z, name="v2", seed=12, priors=True),
@@ -32,7 +34,7 @@ def main():
     parts = [wavs[i::len(models)] for i in range(len(models))]
     n_dev = _lib.device_count()
 
-    def run(device):
+    def run(device, parts=parts):
         trs = [pkg.KaldiNnet3WavTranscriber(p.model_dir, os.path.dirname(p.hclg), None, device=device) for p in models]
 
         async def job():
@@ -48,9 +50,16 @@ def main():
     line = {"config": "5: %d utterances over 8 (model, HCLG) pairs, product pool over %d GPU(s)" % (n_utts, n_dev), "audio_s": audio_s,
             "n_gpus": n_dev, "wall_ms": w_all * 1e3, "rtfx_e2e_paths_to_strings": audio_s / w_all,
             "decoded": int(sum(1 for part in out_all for o in part if o))}
-    if n_dev > 1:
+    if n_dev > 1 and weak:
+        # fixed work per device: one device decodes the first 2048 utterances, the pool all of them
+        sub = wavs[:2048]
+        sub_audio = sum(len(u) for u in utts[:2048]) / 16000.0
+        w_one, out_one = run(0, [sub[i::len(models)] for i in range(len(models))])
+        line.update({"scaling": "weak", "wall_ms_one_gpu_2048": w_one * 1e3, "rtfx_one_gpu": sub_audio / w_one,
+                     "efficiency": (audio_s / w_all) / (n_dev * sub_audio / w_one)})
+    elif n_dev > 1:
         w_one, out_one = run(0)
-        line.update({"wall_ms_one_gpu": w_one * 1e3, "rtfx_one_gpu": audio_s / w_one, "speedup": w_one / w_all,
+        line.update({"scaling": "strong", "wall_ms_one_gpu": w_one * 1e3, "rtfx_one_gpu": audio_s / w_one, "speedup": w_one / w_all,
                      "efficiency": w_one / w_all / n_dev, "identical_to_one_gpu": out_one == out_all})
     print(json.dumps(line), flush=True)
 
