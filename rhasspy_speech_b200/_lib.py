@@ -288,9 +288,9 @@ class Hypotheses:
         off = arr(r.word_offset, n + 1) if n else np.zeros(1, np.int32)
         ids = arr(r.word_ids, int(off[-1]))
         self.n_hyp = arr(r.n_hyp, n)
-        self.words: List[Optional[List[int]]] = []
-        for u in range(n):
-            self.words.append([int(x) for x in ids[off[u]:off[u + 1]]] if self.n_hyp[u] else None)
+        # Python lists once (tolist), then plain slices: ~3x cheaper per utterance than converting numpy slices
+        ids_l, off_l, nh_l = ids.tolist(), off.tolist(), self.n_hyp.tolist()
+        self.words: List[Optional[List[int]]] = [ids_l[off_l[u]:off_l[u + 1]] if nh_l[u] else None for u in range(n)]
         self.graph_cost = arr(r.graph_cost, n)
         self.acoustic_cost = arr(r.acoustic_cost, n)
         self.num_frames = arr(r.num_frames, n)
@@ -311,14 +311,14 @@ class Hypotheses:
         if self._nbest is None:
             out: List[List[tuple]] = [[] for _ in range(self.n_utts)]
             if self._hyp is not None:
-                ho, wo, wid, gc, ac = self._hyp
+                ho, wo, wid, gc, ac = [a.tolist() for a in self._hyp]
                 for u in range(self.n_utts):
-                    out[u] = [([int(x) for x in wid[wo[h]:wo[h + 1]]], float(gc[h]), float(ac[h]))
-                              for h in range(int(ho[u]), int(ho[u + 1]))]
+                    out[u] = [(wid[wo[h]:wo[h + 1]], gc[h], ac[h]) for h in range(ho[u], ho[u + 1])]
             else:
+                gc, ac, nh = self.graph_cost.tolist(), self.acoustic_cost.tolist(), self.n_hyp.tolist()
                 for u in range(self.n_utts):
-                    if self.n_hyp[u]:
-                        out[u] = [(self.words[u], float(self.graph_cost[u]), float(self.acoustic_cost[u]))]
+                    if nh[u]:
+                        out[u] = [(self.words[u], gc[u], ac[u])]
             self._nbest = out
         return self._nbest
 
@@ -393,8 +393,17 @@ class Graph:
         self.num_states, self.num_arcs, self.num_words = ns.value, na.value, nw.value
 
     def word(self, i: int) -> Optional[str]:
-        w = self.lib.rs_graph_word(self.h, i)
-        return w.decode() if w is not None else None
+        # symbols seen before come out of a dict (one ctypes call + decode per word is ~1.5 us; a transcript repeats
+        # the same few hundred words); the table of a loaded graph never changes
+        try:
+            return self._word_cache[i]
+        except (KeyError, AttributeError):
+            w = self.lib.rs_graph_word(self.h, i)
+            w = w.decode() if w is not None else None
+            if not hasattr(self, "_word_cache"):
+                self._word_cache = {}
+            self._word_cache[i] = w
+            return w
 
     def close(self):
         if getattr(self, "h", None):

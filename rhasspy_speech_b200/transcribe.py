@@ -44,8 +44,14 @@ def decode_meta_single(text: str) -> str:
     return base64.b32decode(text.encode("utf-8")).strip().decode("utf-8")
 
 
+_OUTPUT_RE = re.compile(re.escape(OUTPUT_PREFIX) + "([0-9A-Z=]+)")
+_SENTENCE_RE = re.compile(re.escape(SENTENCE_OUTPUT) + "([0-9A-Z=]+)")
+
+
 def decode_meta(text: str) -> str:
     """Restatement of reference hassil_fst.py:849-868 (output words carry base32 JSON metadata)."""
+    if "__" not in text:        # neither marker can match (both start with two underscores): the common transcript
+        return text
     slots: Dict[str, str] = {}
 
     def handle_match(m: "re.Match") -> str:
@@ -56,8 +62,8 @@ def decode_meta(text: str) -> str:
             slots[slot_name] = slot_value
         return slot_value
 
-    text = re.sub(re.escape(OUTPUT_PREFIX) + "([0-9A-Z=]+)", handle_match, text)
-    match = re.search(re.escape(SENTENCE_OUTPUT) + "([0-9A-Z=]+)", text)
+    text = _OUTPUT_RE.sub(handle_match, text)
+    match = _SENTENCE_RE.search(text)
     if match is None:
         return text
     return decode_meta_single(match.group(1)).format(**slots)
