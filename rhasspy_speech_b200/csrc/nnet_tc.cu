@@ -144,6 +144,8 @@ void TcConfigure(TcParams *p) {
   p->fold = 2;
   p->tiles_m = (p->m + kTcBM - 1) / kTcBM;
   p->tiles_n = (p->n + p->bn - 1) / p->bn;
+  p->total_kb = 0;
+  for (int s = 0; s < p->n_slabs; s++) p->total_kb += p->slabs[s].kblocks;
 }
 
 void LaunchGemmTc(const TcParams &p, int num_sms, cudaStream_t stream) {

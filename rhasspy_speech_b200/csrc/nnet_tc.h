@@ -34,6 +34,7 @@ struct TcParams {
   int profile;    // RS_B200_TC_PROFILE: block 0 prints where its TMA / MMA / epilogue threads spent their clocks
   int tmem_cols;  // power of two >= 4 * bn (two K-block accumulator pairs)
   int tiles_m, tiles_n;
+  int total_kb;   // sum of the slabs' K blocks (TcConfigure): a launch constant the kernels read from the parameter bank
   void *out_hi, *out_lo;  // out_lo == nullptr: plain fp32 output at out_hi, else two fp16 planes
   int out_ld, m, n;
   DevOp ops[kMaxOps];

@@ -128,8 +128,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) gemm_tc3_kernel(const __grid_co
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int num_tiles = p.tiles_m * p.tiles_n;
-  int total_kb = 0;
-  for (int s = 0; s < p.n_slabs; s++) total_kb += p.slabs[s].kblocks;
+  const int total_kb = p.total_kb;      // host-computed: summed here it was spilled to local memory and re-read in the fold loop
   const int total_sums = total_kb * 2;  // partial sums per tile: one per two main MMAs (K = 16 each), see the MMA issuer
   // the bias, when it is the first op, is the start value of the running sums (AffineComponent / TdnnComponent::Propagate
   // copy the bias into the output and let the GEMM accumulate onto it)
@@ -144,8 +143,16 @@ __global__ void __launch_bounds__(kT3Threads, 1) gemm_tc3_kernel(const __grid_co
       uint32_t phase = 0;
       bool uniform = true;
       for (int s = 1; s < p.n_slabs; s++) uniform = uniform && p.slabs[s].kblocks == p.slabs[0].kblocks;
+      const int step_m = (int)gridDim.x / p.tiles_n, step_n = (int)gridDim.x % p.tiles_n;
+      int tm = (int)blockIdx.x / p.tiles_n, tn = (int)blockIdx.x % p.tiles_n;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
+        const int m0 = tm * kTcBM, n0 = tn * p.bn;
+        tm += step_m;
+        tn += step_n;
+        if (tn >= p.tiles_n) {
+          tn -= p.tiles_n;
+          tm++;
+        }
         // K blocks block-major across equally long slabs: the time-offset slabs of a TDNN layer read the same
         // source rows shifted by a few rows, so back-to-back loads hit in L2
         for (int it = 0; it < total_kb; it++) {
@@ -243,14 +250,20 @@ __global__ void __launch_bounds__(kT3Threads, 1) gemm_tc3_kernel(const __grid_co
     uint4 *st16 = reinterpret_cast<uint4 *>(smem_raw + (epi0 - smem_u32(smem_raw)) + (uint32_t)(warp - 4) * kT3StagingBytes);
     const int first_op = bias_first ? 1 : 0;
     int ib = -1;  // the op whose split bypass input is prefetched (first kAddScaled with a split source)
-    for (int i = 0; i < p.n_ops && ib < 0; i++)
-      if (p.ops[i].type == EpiOp::kAddScaled && p.ops[i].buf_lo) ib = i;
+    if constexpr (kStatic) {
+      constexpr int kAs = kTypes[0] == EpiOp::kAddScaled ? 0 : kTypes[1] == EpiOp::kAddScaled ? 1 : kTypes[2] == EpiOp::kAddScaled ? 2
+                          : kTypes[3] == EpiOp::kAddScaled ? 3 : -1;
+      if constexpr (kAs >= 0) ib = p.ops[kAs].buf_lo ? kAs : -1;
+    } else {
+      for (int i = 0; i < p.n_ops && ib < 0; i++)
+        if (p.ops[i].type == EpiOp::kAddScaled && p.ops[i].buf_lo) ib = i;
+    }
     const bool chunk_in_tile = FULL || jc * 32 < p.bn;
     uint32_t fcount = 0, tcount = 0;
     // per-lane column of the per-column vectors of the coming tile: bias (start value), BatchNorm scale / offset
-    auto load_cols = [&](int tile, float &b, float &s, float &o) {
-      const int c = (tile % p.tiles_n) * p.bn + jc * 32 + lane;
-      const bool ok = tile < num_tiles && chunk_in_tile && (FULL || c < p.n);
+    auto load_cols = [&](int tile_n, bool in_range, float &b, float &s, float &o) {
+      const int c = tile_n * p.bn + jc * 32 + lane;
+      const bool ok = in_range && chunk_in_tile && (FULL || c < p.n);
       b = ok && bias_first ? __ldg(p.ops[0].v0 + c) : 0.f;
       s = o = 0.f;
       if constexpr (kStatic && kSoIdx >= 0) {
@@ -261,9 +274,18 @@ __global__ void __launch_bounds__(kT3Threads, 1) gemm_tc3_kernel(const __grid_co
       }
     };
     float col_b, col_s, col_o;
-    load_cols(blockIdx.x, col_b, col_s, col_o);
+    // tile coordinates advance by a fixed (rows, columns) step: no division per tile
+    const int step_m = (int)gridDim.x / p.tiles_n, step_n = (int)gridDim.x % p.tiles_n;
+    int tm = (int)blockIdx.x / p.tiles_n, tn = (int)blockIdx.x % p.tiles_n;
+    load_cols(tn, blockIdx.x < num_tiles, col_b, col_s, col_o);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
-      const int m0 = (tile / p.tiles_n) * kTcBM, n0 = (tile % p.tiles_n) * p.bn;
+      const int m0 = tm * kTcBM, n0 = tn * p.bn;
+      tm += step_m;
+      tn += step_n;
+      if (tn >= p.tiles_n) {
+        tn -= p.tiles_n;
+        tm++;
+      }
       const int c0 = n0 + jc * 32;
       const bool valid = chunk_in_tile && (FULL || c0 < p.n);
       const int r = m0 + q * 32 + lane;
@@ -272,7 +294,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) gemm_tc3_kernel(const __grid_co
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = __shfl_sync(0xffffffffu, col_b, j);
       const float so_s = col_s, so_o = col_o;
-      load_cols(tile + (int)gridDim.x, col_b, col_s, col_o);  // next tile's columns: a whole tile of latency to hide in
+      load_cols(tn, tile + (int)gridDim.x < num_tiles, col_b, col_s, col_o);  // next tile's columns: a whole tile of latency to hide in
       // bypass input of the chunk: 32 columns = 64 bytes per plane and row; 4 lanes x 16 B cover a row segment,
       // 8 rows per instruction
       uint4 pf_h[4], pf_l[4];

@@ -1,1 +1,2 @@
-for k in 3 6 10 14; do RS_B200_PACK_THREADS=$k timeout 300 python scripts/api_probe.py 2>&1 | tail -1; done
+timeout 300 python scripts/ncu_step.py 256 4 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_zamia.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
