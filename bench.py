@@ -236,7 +236,7 @@ def parity_and_cpu_baseline(p, utts, hyp, tmp):
     return parity, cb
 
 
-def e2e_api(p, utts, tmp, reps=4):
+def e2e_api(p, utts, tmp, reps=6):
     """The reference's API shape: 256 WAV *paths* -> strings through KaldiNnet3WavTranscriber.async_transcribe_many
     (file reads, H2D, kernels, D2H, word-id -> text, decode_meta)."""
     import asyncio
@@ -245,12 +245,16 @@ def e2e_api(p, utts, tmp, reps=4):
     lang_dir = os.path.join(tmp, "lang")
     os.makedirs(lang_dir, exist_ok=True)
     tr = pkg.KaldiNnet3WavTranscriber(p.model_dir, os.path.dirname(p.hclg), None)
-    asyncio.run(tr.async_transcribe_many(wavs, lang_dir))
-    walls = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        out = asyncio.run(tr.async_transcribe_many(wavs, lang_dir))
-        walls.append(time.perf_counter() - t0)
+
+    async def job(n):       # one event loop for all repetitions, as a long-lived service has (loop set-up is not the call)
+        walls, out = [], None
+        for _ in range(n):
+            t0 = time.perf_counter()
+            out = await tr.async_transcribe_many(wavs, lang_dir)
+            walls.append(time.perf_counter() - t0)
+        return walls, out
+    asyncio.run(job(2))
+    walls, out = asyncio.run(job(reps))
     return float(np.mean(walls)), sum(1 for o in out if o)
 
 
