@@ -3,7 +3,9 @@ differ the way the reference's language models do, every pair served by one tran
 (KaldiNnet3WavTranscriber(device="all"): one engine per device, request list dealt longest-first by shard.py, shares run
 concurrently, no collective).  Prints one JSON line: whole-job RTFx end to end from WAV paths to strings, and the same
 job on one device for the scaling efficiency.    python scripts/bench_config5.py [n_utts | weak]
-"weak" = 2048 utterances per visible GPU (fixed work per device; the one-device run then decodes its 2048 only)."""
+"weak" = 2048 utterances per visible GPU (fixed work per device; the one-device run then decodes its 2048 only).
+"procs" = one PROCESS per visible GPU (the layout bench.py uses under torchrun), each with its own 8 transcribers and
+2048 utterances, started together through a file barrier: whole-job RTFx = all audio / slowest rank's mean wall time."""
 import asyncio, dataclasses, json, os, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +15,34 @@ from rhasspy_speech_b200 import _lib
 from tools import synth
 
 
+def procs_mode():
+    """Parent: one child per GPU (CUDA_VISIBLE_DEVICES), file barrier, aggregate of the children's JSON lines."""
+    import subprocess
+    n_dev = _lib.device_count()
+    bar = tempfile.mkdtemp(prefix="c5bar_")
+    kids = []
+    for r in range(n_dev):
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(r), RS_C5_BARRIER=bar, RS_C5_RANK=str(r),
+                   RS_B200_PACK_THREADS=str(max(1, min(3, (os.cpu_count() or 8) // n_dev - 1))))
+        kids.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "2048"], env=env, stdout=subprocess.PIPE, text=True))
+    t0 = time.time()
+    while sum(os.path.exists(os.path.join(bar, "ready%d" % r)) for r in range(n_dev)) < n_dev:
+        if any(k.poll() is not None for k in kids) or time.time() - t0 > 600:
+            raise SystemExit("a rank ended before the barrier")
+        time.sleep(0.05)
+    open(os.path.join(bar, "go"), "w").close()
+    lines = [json.loads([l for l in k.communicate()[0].splitlines() if l.startswith("{")][-1]) for k in kids]
+    audio = sum(l["audio_s"] for l in lines)
+    wall = max(l["wall_ms_mean"] for l in lines)
+    print(json.dumps({"config": "5: %d processes (one per GPU) x 2048 utterances over 8 (model, HCLG) pairs each, WAV paths -> strings" % n_dev,
+                      "n_gpus": n_dev, "audio_s": audio, "wall_ms_slowest_rank_mean_of_3": wall, "rtfx_e2e_paths_to_strings": audio / wall * 1e3,
+                      "per_rank_rtfx": [round(l["audio_s"] / l["wall_ms_mean"] * 1e3) for l in lines],
+                      "decoded": sum(l["decoded"] for l in lines)}), flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "procs":
+        return procs_mode()
     weak = len(sys.argv) > 1 and sys.argv[1] == "weak"
     n_utts = 2048 * _lib.device_count() if weak else int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     tmp = tempfile.mkdtemp()
@@ -40,14 +69,24 @@ def main():
         async def job():
             return await asyncio.gather(*[t.async_transcribe_many(pt, tmp) for t, pt in zip(trs, parts)])
         asyncio.run(job())                      # loads every replica, warms the kernels
-        walls = []
-        for _ in range(3):
-            t0 = time.perf_counter()
-            out = asyncio.run(job())
-            walls.append(time.perf_counter() - t0)
+        bar = os.environ.get("RS_C5_BARRIER")
+        if bar:                                 # "procs" mode: every rank starts its timed repetitions together
+            asyncio.run(job())
+            open(os.path.join(bar, "ready" + os.environ["RS_C5_RANK"]), "w").close()
+            while not os.path.exists(os.path.join(bar, "go")):
+                time.sleep(0.0005)
+        async def timed():                      # one event loop for the repetitions (a service keeps its loop)
+            walls, out = [], None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                out = await job()
+                walls.append(time.perf_counter() - t0)
+            return walls, out
+        walls, out = asyncio.run(timed())
+        run.mean = float(np.mean(walls))
         return float(np.min(walls)), out
     w_all, out_all = run("all")
-    line = {"config": "5: %d utterances over 8 (model, HCLG) pairs, product pool over %d GPU(s)" % (n_utts, n_dev), "audio_s": audio_s,
+    line = {"wall_ms_mean": run.mean * 1e3, "config": "5: %d utterances over 8 (model, HCLG) pairs, product pool over %d GPU(s)" % (n_utts, n_dev), "audio_s": audio_s,
             "n_gpus": n_dev, "wall_ms": w_all * 1e3, "rtfx_e2e_paths_to_strings": audio_s / w_all,
             "decoded": int(sum(1 for part in out_all for o in part if o))}
     if n_dev > 1 and weak:

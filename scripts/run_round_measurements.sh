@@ -9,7 +9,7 @@ python scripts/bench_configs.py 2>&1 | grep "^{" > gpurun_out/${T}_configs_3_4.j
 python scripts/bench_configs.py --surface 2>&1 | grep "^{" > gpurun_out/${T}_config4_python_surface.jsonl
 python scripts/bench_configs.py --nbest 2>&1 | grep "^{" > gpurun_out/${T}_nbest_batch256.jsonl
 python scripts/bench_config5.py 2048 2>&1 | grep "^{" > gpurun_out/${T}_config5_pool_1gpu.jsonl
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 42 -c 44 --csv --log-file gpurun_out/${T}_launches.csv python scripts/ncu_step.py 256 2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc3 -s 8 -c 4 -o gpurun_out/${T}_gemm python scripts/ncu_step.py 256 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"mfcc_kernel|ubm_post|splice_lda4|decode_small" -s 4 -c 4 -o gpurun_out/${T}_others python scripts/ncu_step.py 256 2 > /dev/null 2>&1
+RS_B200_OVERLAP_STAGING=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 42 -c 44 --csv --log-file gpurun_out/${T}_launches.csv python scripts/ncu_step.py 256 2 > /dev/null 2>&1
+RS_B200_OVERLAP_STAGING=0 ncu --set full --clock-control none --import-source on -k regex:gemm_tc3 -s 8 -c 4 -o gpurun_out/${T}_gemm python scripts/ncu_step.py 256 1 > /dev/null 2>&1
+RS_B200_OVERLAP_STAGING=0 ncu --set full --clock-control none --import-source on -k regex:"mfcc_kernel|ubm_post|splice_lda4|decode_small" -s 4 -c 4 -o gpurun_out/${T}_others python scripts/ncu_step.py 256 2 > /dev/null 2>&1
 for f in gpurun_out/${T}_bench_full.json gpurun_out/${T}_bench_reference_arm.json gpurun_out/${T}_configs_3_4.jsonl gpurun_out/${T}_config4_python_surface.jsonl gpurun_out/${T}_nbest_batch256.jsonl gpurun_out/${T}_config5_pool_1gpu.jsonl; do echo "== $f"; cut -c1-700 $f; done

@@ -157,6 +157,36 @@ def test_bench_config_transcripts_and_costs_match_reference(lib, ref, grammar, w
             assert [h[0] for h in got3.nbest[u]] == want, (u, got3.nbest[u], want)
 
 
+def test_staged_input_paths_give_the_same_result(lib, grammar, workload):
+    """The batch (8 MB of audio: several staging items) through every host path of a call: ordinary arrays (packed by
+    the staging threads), one page-locked block (copied straight from the caller's memory), WAV files, each with the
+    copy / MFCC overlap on and off (rs_decoder_set_staging_overlap).  Words, costs and frame counts must not depend
+    on the path; the overlapped calls launch one MFCC kernel per item plus the keep-alive warp."""
+    utts, wavs = workload
+    p = grammar
+    dec = lib.Decoder(lib.Model(p.final_mdl, p.online_conf, 0), lib.Graph(p.hclg, p.words_txt, 0))
+    pinned = lib.PinnedAudio.from_utterances(utts)
+    results, launches = {}, {}
+    for on in (False, True):
+        dec.set_staging_overlap(on)
+        for name, call in (("arrays", lambda: dec.decode_pcm(utts)), ("pinned", lambda: dec.decode_pcm(pinned)),
+                           ("wavs", lambda: dec.decode_wavs(wavs))):
+            h = call()
+            assert all(int(s) & 15 == 0 for s in h.status)
+            results[(name, on)] = (h.words, h.graph_cost.tolist(), h.acoustic_cost.tolist(), h.num_frames.tolist())
+            launches[(name, on)] = dec.timings()["kernel_launches"]
+    first = results[("arrays", False)]
+    assert sum(1 for w in first[0] if w) >= N_UTTS // 2
+    for key, r in results.items():
+        assert r == first, key
+    for name in ("arrays", "pinned", "wavs"):
+        assert launches[(name, True)] > launches[(name, False)], (name, launches)
+    # a short list (one staging item) takes the plain path whatever the setting
+    dec.set_staging_overlap(True)
+    h4 = dec.decode_pcm(utts[:4])
+    assert (h4.words, h4.graph_cost.tolist()) == (first[0][:4], first[1][:4])
+
+
 @pytest.mark.parametrize("max_active", [7000, 1000])
 def test_arpa_graph_at_bench_scale_matches_reference(lib, ref, synth, workload, tmp_path_factory, max_active):
     """configs[2]: the zamia-shaped model on the 127 k-state ARPA-shaped HCLG; ~6 k tokens per frame, --max-active

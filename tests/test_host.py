@@ -114,6 +114,9 @@ def test_decode_meta_and_nbest_text():
     sent = T.SENTENCE_OUTPUT + enc("lights on in {area}")
     assert T.decode_meta("turn on " + word) == "turn on kitchen"
     assert T.decode_meta("turn on " + word + " " + sent) == "lights on in kitchen"
+    # the fast path (no "__" in the text) must not swallow look-alikes; a lone marker prefix without payload is text
+    assert T.decode_meta("under_score and double__underscore stay") == "under_score and double__underscore stay"
+    assert T.decode_meta("set " + word + " " + word) == "set kitchen kitchen"
 
     class H:
         words = [[12, 45, 7], None, [], [3, 4]]
