@@ -423,6 +423,8 @@ struct DecoderImpl {
   DevBuf d_earc_buf;                // graph arcs with ilabel mapped to pdf for this model
   const int4 *d_earc = nullptr;
   std::vector<int32_t> h_epdf;      // the same map on the host, for the strict-order decoder (strict_decode.cc)
+  StrictArcs strict_arcs;           // its arc records, built when the first utterance needs them
+  bool strict_arcs_ready = false;
   rs_timings last{};
   // layout of the last batch (for rs_debug_fetch)
   struct Batch {
@@ -800,6 +802,7 @@ static void BindGraph(DecoderImpl *d, GraphImpl *gi) {
   std::swap(d->d_earc_buf.cap, fresh.cap);
   d->d_earc = d->d_earc_buf.as<int4>();
   d->h_epdf.swap(epdf);
+  d->strict_arcs_ready = false;
   d->graph = gi;
 }
 
@@ -1250,6 +1253,10 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     so.max_active = o.max_active;
     so.min_active = o.min_active;
     so.max_words = W;
+    if (!d->strict_arcs_ready) {
+      BuildStrictArcs(d->graph->g, d->h_epdf.data(), &d->strict_arcs);
+      d->strict_arcs_ready = true;
+    }
     const int nthreads = std::max(1, std::min(ns, (int)std::thread::hardware_concurrency()));
     std::atomic<int> next{0};
     std::string fail;
@@ -1257,7 +1264,8 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     auto work = [&]() {
       try {
         for (int i = next++; i < ns; i = next++)
-          StrictDecode(d->graph->g, d->h_epdf.data(), ll[i].data(), ld, d->batch.n_out[strict_list[i]], so, lattice, &strict_res[i]);
+          StrictDecode(d->graph->g, d->h_epdf.data(), d->strict_arcs, ll[i].data(), ld, d->batch.n_out[strict_list[i]], so, lattice,
+                       &strict_res[i]);
       } catch (const std::exception &e) {
         std::lock_guard<std::mutex> lk(fail_mu);
         fail = e.what();

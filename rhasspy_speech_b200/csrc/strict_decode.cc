@@ -48,15 +48,21 @@ class OrderedStateMap {
   };
   void SetSize(size_t n) {
     hash_size_ = n;
+    // state % hash_size without a division per look-up (Lemire's fastmod: exact for 32-bit operands)
+    mod_m_ = n ? ~uint64_t(0) / n + 1 : 0;
     if (n > buckets_.size()) buckets_.resize(n);
   }
   size_t Size() const { return hash_size_; }
   int Head() const { return head_; }
+  size_t Index(int state) const {  // state % hash_size
+    return hash_size_ <= 0xffffffffu ? (size_t)(((unsigned __int128)(mod_m_ * (uint32_t)state) * hash_size_) >> 64)
+                                     : static_cast<size_t>(state) % hash_size_;
+  }
   const Elem &At(int e) const { return pool_[e]; }
   void SetTok(int e, int tok) { pool_[e].tok = tok; }
   // element of `state`, created (tok = -1) behind the last element of its bucket when absent
   int Insert(int state) {
-    const size_t idx = static_cast<size_t>(state) % hash_size_;
+    const size_t idx = Index(state);
     Bucket &b = buckets_[idx];
     const bool occupied = b.epoch == epoch_;
     if (occupied) {
@@ -71,7 +77,7 @@ class OrderedStateMap {
       b.last = e;
       b.prev = tail_bucket_;
       b.epoch = epoch_;
-      tail_bucket_ = (long)idx;
+      tail_bucket_ = (int)idx;
     } else {
       pool_[e].tail = pool_[b.last].tail;
       pool_[b.last].tail = e;
@@ -86,21 +92,25 @@ class OrderedStateMap {
     pool_.clear();
     head_ = -1;
     tail_bucket_ = -1;
-    epoch_++;
+    if (++epoch_ == 0) {  // 2^32 releases: start over with clean buckets
+      for (auto &b : buckets_) b.epoch = 0;
+      epoch_ = 1;
+    }
   }
 
  private:
-  struct Bucket {
-    long prev = -1;
+  struct Bucket {  // 12 bytes: the table of a 7000-token frame (14 k buckets) stays in the L2 of a core
+    int prev = -1;
     int last = -1;
-    uint64_t epoch = 0;
+    uint32_t epoch = 0;
   };
   std::vector<Elem> pool_;
   std::vector<Bucket> buckets_;
   size_t hash_size_ = 0;
+  uint64_t mod_m_ = 0;
   int head_ = -1;
-  long tail_bucket_ = -1;
-  uint64_t epoch_ = 1;
+  int tail_bucket_ = -1;
+  uint32_t epoch_ = 1;
 };
 
 inline bool ApproxEq(float a, float b, float tol) {  // kaldi/src/base/kaldi-math.h:265-273
@@ -112,12 +122,16 @@ inline bool ApproxEq(float a, float b, float tol) {  // kaldi/src/base/kaldi-mat
 
 class Search {
  public:
-  Search(const Graph &g, const int32_t *e_pdf, const float *ll, int ld, const StrictOptions &o, bool lattice)
-      : g_(g), e_pdf_(e_pdf), ll_(ll), ld_(ld), o_(o), lattice_(lattice), NE_((int)g.e_next.size()) {}
+  Search(const Graph &g, const int32_t *e_pdf, const StrictArcs &arcs, const float *ll, int ld, const StrictOptions &o, bool lattice)
+      : g_(g), e_pdf_(e_pdf), ea_(arcs.emitting.data()), pa_(arcs.epsilon.data()), ll_(ll), ld_(ld), o_(o), lattice_(lattice),
+        NE_((int)g.e_next.size()) {}
 
   void Run(int n_frames, StrictResult *out) {
     map_.SetSize(1000);  // the constructor's toks_.SetSize(1000)
     // InitDecoding :56-73
+    // (room for a max-active frontier on every frame: the token array of a 4 s utterance on an LM-sized graph reaches
+    //  ~600 k entries and was copied five times over while it grew)
+    toks_.reserve((size_t)(n_frames + 1) * (size_t)std::min(std::max(o_.max_active, 256), 6000));
     frame_begin_.push_back(0);
     {
       const int e = map_.Insert((int)g_.start);
@@ -228,7 +242,7 @@ class Search {
       const float tot = toks_[list_[best].second].tot;
       cost_offset = -tot;
       for (uint32_t a = g_.e_begin[state]; a < g_.e_begin[state + 1]; a++) {
-        const float new_weight = g_.e_weight[a] + cost_offset - ll[e_pdf_[a]] + tot;
+        const float new_weight = ea_[a].weight + cost_offset - ll[ea_[a].pdf] + tot;
         if (new_weight + adaptive_beam < next_cutoff) next_cutoff = new_weight + adaptive_beam;
       }
     }
@@ -245,17 +259,26 @@ class Search {
             }
           }
     }
-    for (const auto &st : list_) {
+    const size_t n_list = list_.size();
+    for (size_t li = 0; li < n_list; li++) {
+      const auto &st = list_[li];
+      // the list is known in advance and the graph is far larger than a core's caches: the CSR offsets of the token
+      // eight places ahead and the arc records of the token four places ahead are requested now
+      if (li + 8 < n_list) __builtin_prefetch(&g_.e_begin[list_[li + 8].first]);
+      if (li + 4 < n_list) __builtin_prefetch(&ea_[g_.e_begin[list_[li + 4].first]]);
       const int state = st.first, tok = st.second;
-      if (toks_[tok].tot <= cur_cutoff) {
+      const float cur_cost = toks_[tok].tot;  // (a token of this frame is never the target of an arc of this frame)
+      if (cur_cost <= cur_cutoff) {
         expanded_++;
-        for (uint32_t a = g_.e_begin[state]; a < g_.e_begin[state + 1]; a++) {
-          arcs_++;
-          const float ac_cost = cost_offset - ll[e_pdf_[a]], graph_cost = g_.e_weight[a], cur_cost = toks_[tok].tot;
+        const uint32_t a_end = g_.e_begin[state + 1];
+        arcs_ += a_end - g_.e_begin[state];
+        for (uint32_t a = g_.e_begin[state]; a < a_end; a++) {
+          const StrictArcs::Arc arc = ea_[a];  // {next, pdf, weight} side by side: one cache line per state's arcs
+          const float ac_cost = cost_offset - ll[arc.pdf], graph_cost = arc.weight;
           const float tot_cost = cur_cost + ac_cost + graph_cost;
           if (tot_cost >= next_cutoff) continue;
           else if (tot_cost + adaptive_beam < next_cutoff) next_cutoff = tot_cost + adaptive_beam;
-          const int e = FindOrAdd(g_.e_next[a], tot_cost, tok, (int)a, nullptr);
+          const int e = FindOrAdd(arc.next, tot_cost, tok, (int)a, nullptr);
           if (lattice_) AddLink(tok, map_.At(e).tok, (int)a, graph_cost, ac_cost);
         }
       }
@@ -331,12 +354,13 @@ class Search {
       toks_[tok].links = -1;  // DeleteForwardLinks: they are regenerated below
       for (uint32_t a = g_.p_begin[state]; a < g_.p_begin[state + 1]; a++) {
         arcs_++;
-        const float graph_cost = g_.p_weight[a], tot_cost = cur_cost + graph_cost;
+        const StrictArcs::Arc arc = pa_[a];
+        const float graph_cost = arc.weight, tot_cost = cur_cost + graph_cost;
         if (tot_cost < cutoff) {
           bool changed;
-          const int e_new = FindOrAdd(g_.p_next[a], tot_cost, tok, NE_ + (int)a, &changed);
+          const int e_new = FindOrAdd(arc.next, tot_cost, tok, NE_ + (int)a, &changed);
           if (lattice_) AddLink(tok, map_.At(e_new).tok, NE_ + (int)a, graph_cost, 0.f);
-          if (changed && HasEps(g_.p_next[a])) queue_.push_back(e_new);
+          if (changed && HasEps(arc.next)) queue_.push_back(e_new);
         }
       }
     }
@@ -489,6 +513,7 @@ class Search {
 
   const Graph &g_;
   const int32_t *e_pdf_;
+  const StrictArcs::Arc *ea_, *pa_;  // emitting / epsilon arcs as records (the search loops read nothing else of an arc)
   const float *ll_;
   const int ld_;
   const StrictOptions o_;
@@ -511,12 +536,28 @@ class Search {
 
 }  // namespace
 
-void StrictDecode(const Graph &g, const int32_t *e_pdf, const float *loglikes, int ld, int n_frames,
+void BuildStrictArcs(const Graph &g, const int32_t *e_pdf, StrictArcs *out) {
+  out->emitting.resize(g.e_next.size());
+  for (size_t a = 0; a < g.e_next.size(); a++) out->emitting[a] = StrictArcs::Arc{g.e_next[a], e_pdf[a], g.e_weight[a]};
+  out->epsilon.resize(g.p_next.size());
+  for (size_t a = 0; a < g.p_next.size(); a++) out->epsilon[a] = StrictArcs::Arc{g.p_next[a], -1, g.p_weight[a]};
+}
+
+void StrictDecode(const Graph &g, const int32_t *e_pdf, const StrictArcs &arcs, const float *loglikes, int ld, int n_frames,
                   const StrictOptions &opt, bool want_lattice, StrictResult *out) {
   *out = StrictResult();
   if (n_frames <= 0 || g.num_states <= 0) return;
-  Search s(g, e_pdf, loglikes, ld, opt, want_lattice);
+  if (arcs.emitting.size() != g.e_next.size() || arcs.epsilon.size() != g.p_next.size())
+    throw Error("StrictDecode: the arc records do not belong to this graph");
+  Search s(g, e_pdf, arcs, loglikes, ld, opt, want_lattice);
   s.Run(n_frames, out);
+}
+
+void StrictDecode(const Graph &g, const int32_t *e_pdf, const float *loglikes, int ld, int n_frames,
+                  const StrictOptions &opt, bool want_lattice, StrictResult *out) {
+  StrictArcs arcs;
+  BuildStrictArcs(g, e_pdf, &arcs);
+  StrictDecode(g, e_pdf, arcs, loglikes, ld, n_frames, opt, want_lattice, out);
 }
 
 }  // namespace rs

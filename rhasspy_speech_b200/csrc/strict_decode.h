@@ -27,7 +27,21 @@ struct StrictResult {
   uint64_t tokens_expanded = 0, arcs_visited = 0, tokens_created = 0;
 };
 
+// The arcs of a graph as 12-byte records in CSR order (Graph keeps one array per field; the search touches next state,
+// pdf and weight of every arc it visits and nothing else): built once per (graph, model) pair.
+struct StrictArcs {
+  struct Arc {
+    int32_t next, pdf;  // pdf = -1 on epsilon arcs
+    float weight;
+  };
+  std::vector<Arc> emitting, epsilon;
+};
+void BuildStrictArcs(const Graph &g, const int32_t *e_pdf, StrictArcs *out);
+
 // e_pdf[a] = pdf of emitting arc a (transition-id -> pdf applied); loglikes [n_frames x ld]
+void StrictDecode(const Graph &g, const int32_t *e_pdf, const StrictArcs &arcs, const float *loglikes, int ld, int n_frames,
+                  const StrictOptions &opt, bool want_lattice, StrictResult *out);
+// the same, building the arc records for this one call
 void StrictDecode(const Graph &g, const int32_t *e_pdf, const float *loglikes, int ld, int n_frames,
                   const StrictOptions &opt, bool want_lattice, StrictResult *out);
 
