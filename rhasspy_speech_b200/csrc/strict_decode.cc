@@ -45,6 +45,11 @@ class OrderedStateMap {
  public:
   struct Elem {
     int state, tok, tail;
+    float tot;  // the token's current cost, kept next to the key: a hit on an existing token does not touch the token array
+  };
+  struct Item {  // one entry of a released list: (state, token, cost)
+    int first, second;
+    float tot;
   };
   void SetSize(size_t n) {
     hash_size_ = n;
@@ -59,7 +64,11 @@ class OrderedStateMap {
                                      : static_cast<size_t>(state) % hash_size_;
   }
   const Elem &At(int e) const { return pool_[e]; }
-  void SetTok(int e, int tok) { pool_[e].tok = tok; }
+  void SetTok(int e, int tok, float tot) {
+    pool_[e].tok = tok;
+    pool_[e].tot = tot;
+  }
+  void SetTot(int e, float tot) { pool_[e].tot = tot; }
   // element of `state`, created (tok = -1) behind the last element of its bucket when absent
   int Insert(int state) {
     const size_t idx = Index(state);
@@ -71,7 +80,7 @@ class OrderedStateMap {
         if (pool_[e].state == state) return e;
     }
     const int e = (int)pool_.size();
-    pool_.push_back(Elem{state, -1, -1});
+    pool_.push_back(Elem{state, -1, -1, kInf});
     if (!occupied) {  // the bucket joins the end of the bucket chain, its element the end of the list
       if (tail_bucket_ < 0) head_ = e; else pool_[buckets_[tail_bucket_].last].tail = e;
       b.last = e;
@@ -86,9 +95,9 @@ class OrderedStateMap {
     return e;
   }
   // the (state, token) pairs in list order; the map is left empty
-  void Release(std::vector<std::pair<int, int>> *out) {
+  void Release(std::vector<Item> *out) {
     out->clear();
-    for (int e = head_; e >= 0; e = pool_[e].tail) out->push_back({pool_[e].state, pool_[e].tok});
+    for (int e = head_; e >= 0; e = pool_[e].tail) out->push_back(Item{pool_[e].state, pool_[e].tok, pool_[e].tot});
     pool_.clear();
     head_ = -1;
     tail_bucket_ = -1;
@@ -136,7 +145,7 @@ class Search {
     {
       const int e = map_.Insert((int)g_.start);
       toks_.push_back(Tok{0.f, 0.f, (int)g_.start, -1, -1, -1});
-      map_.SetTok(e, 0);
+      map_.SetTok(e, 0, 0.f);
     }
     ProcessNonemitting(o_.beam);
     for (int f = 0; f < n_frames; f++) {
@@ -162,9 +171,10 @@ class Search {
     const int t = map_.At(e).tok;
     if (t < 0) {
       toks_.push_back(Tok{tot, 0.f, state, back, back_arc, -1});
-      map_.SetTok(e, (int)toks_.size() - 1);
+      map_.SetTok(e, (int)toks_.size() - 1, tot);
       if (changed) *changed = true;
-    } else if (toks_[t].tot > tot) {
+    } else if (map_.At(e).tot > tot) {
+      map_.SetTot(e, tot);
       toks_[t].tot = tot;
       toks_[t].back = back;
       toks_[t].back_arc = back_arc;
@@ -180,12 +190,12 @@ class Search {
   }
 
   // GetCutoff :644-711
-  float GetCutoff(const std::vector<std::pair<int, int>> &list, float *adaptive_beam, int *best) {
+  float GetCutoff(const std::vector<OrderedStateMap::Item> &list, float *adaptive_beam, int *best) {
     float best_w = kInf;
     *best = -1;
     tmp_.clear();
     for (size_t i = 0; i < list.size(); i++) {
-      const float w = toks_[list[i].second].tot;
+      const float w = list[i].tot;
       tmp_.push_back(w);
       if (w < best_w) {
         best_w = w;
@@ -198,9 +208,22 @@ class Search {
     }
     const float beam_cutoff = best_w + o_.beam;
     float min_active_cutoff = kInf, max_active_cutoff = kInf;
-    if (tmp_.size() > (size_t)o_.max_active) {
+    // The reference runs nth_element for both limits on every frame and then only COMPARES the two order statistics
+    // with the beam cutoff.  With s = the sorted costs: s[max_active] < beam_cutoff  <=>  more than max_active costs lie
+    // below the beam cutoff, and s[min_active] > beam_cutoff  <=>  at most min_active costs lie at or below it.  Two
+    // counts (one branch-free pass) decide both; a selection only runs when its limit binds -- same values, and the
+    // selection was an eighth of the search time on an LM-sized graph.
+    size_t below = 0, at_or_below = 0;
+    for (const float w : tmp_) {
+      below += w < beam_cutoff;
+      at_or_below += w <= beam_cutoff;
+    }
+    const bool over_max = tmp_.size() > (size_t)o_.max_active;
+    bool selected_max = false;
+    if (over_max && below > (size_t)o_.max_active) {
       std::nth_element(tmp_.begin(), tmp_.begin() + o_.max_active, tmp_.end());
       max_active_cutoff = tmp_[o_.max_active];
+      selected_max = true;
     }
     if (max_active_cutoff < beam_cutoff) {
       *adaptive_beam = max_active_cutoff - best_w + o_.beam_delta;
@@ -209,10 +232,12 @@ class Search {
     if (tmp_.size() > (size_t)o_.min_active) {
       if (o_.min_active == 0) {
         min_active_cutoff = best_w;
-      } else {
-        std::nth_element(tmp_.begin(), tmp_.begin() + o_.min_active,
-                         tmp_.size() > (size_t)o_.max_active ? tmp_.begin() + o_.max_active : tmp_.end());
+      } else if (at_or_below <= (size_t)o_.min_active) {
+        // (after a max-active selection the min_active smallest costs sit in front of position max_active)
+        std::nth_element(tmp_.begin(), tmp_.begin() + o_.min_active, selected_max ? tmp_.begin() + o_.max_active : tmp_.end());
         min_active_cutoff = tmp_[o_.min_active];
+      } else {
+        min_active_cutoff = -kInf;  // s[min_active] <= beam_cutoff: the beam decides below
       }
     }
     if (min_active_cutoff > beam_cutoff) {
@@ -239,7 +264,7 @@ class Search {
     float next_cutoff = kInf, cost_offset = 0.f;
     if (best >= 0) {
       const int state = list_[best].first;
-      const float tot = toks_[list_[best].second].tot;
+      const float tot = list_[best].tot;
       cost_offset = -tot;
       for (uint32_t a = g_.e_begin[state]; a < g_.e_begin[state + 1]; a++) {
         const float new_weight = ea_[a].weight + cost_offset - ll[ea_[a].pdf] + tot;
@@ -267,7 +292,7 @@ class Search {
       if (li + 8 < n_list) __builtin_prefetch(&g_.e_begin[list_[li + 8].first]);
       if (li + 4 < n_list) __builtin_prefetch(&ea_[g_.e_begin[list_[li + 4].first]]);
       const int state = st.first, tok = st.second;
-      const float cur_cost = toks_[tok].tot;  // (a token of this frame is never the target of an arc of this frame)
+      const float cur_cost = st.tot;  // (a token of this frame is never the target of an arc of this frame)
       if (cur_cost <= cur_cutoff) {
         expanded_++;
         const uint32_t a_end = g_.e_begin[state + 1];
@@ -349,7 +374,7 @@ class Search {
       const int e = queue_.back();
       queue_.pop_back();
       const int state = map_.At(e).state, tok = map_.At(e).tok;
-      const float cur_cost = toks_[tok].tot;
+      const float cur_cost = map_.At(e).tot;
       if (cur_cost >= cutoff) continue;
       toks_[tok].links = -1;  // DeleteForwardLinks: they are regenerated below
       for (uint32_t a = g_.p_begin[state]; a < g_.p_begin[state + 1]; a++) {
@@ -524,7 +549,7 @@ class Search {
   std::vector<Link> links_;
   std::vector<int> frame_begin_;
   std::vector<float> cost_offsets_, tmp_;
-  std::vector<std::pair<int, int>> list_;
+  std::vector<OrderedStateMap::Item> list_;
   std::vector<int> queue_;
   bool any_final_ = false;
   std::map<int, float> sup_;
