@@ -75,8 +75,10 @@ class OrderedStateMap {
     Bucket &b = buckets_[idx];
     const bool occupied = b.epoch == epoch_;
     if (occupied) {
-      const int first = b.prev < 0 ? head_ : pool_[buckets_[b.prev].last].tail, stop = pool_[b.last].tail;
-      for (int e = first; e != stop; e = pool_[e].tail)
+      // the bucket's elements are a run of the list: from its first element (fixed when the bucket was opened: later
+      // elements of the previous bucket are spliced in before it) to the one behind its last
+      const int stop = pool_[b.last].tail;
+      for (int e = b.first; e != stop; e = pool_[e].tail)
         if (pool_[e].state == state) return e;
     }
     const int e = (int)pool_.size();
@@ -84,7 +86,7 @@ class OrderedStateMap {
     if (!occupied) {  // the bucket joins the end of the bucket chain, its element the end of the list
       if (tail_bucket_ < 0) head_ = e; else pool_[buckets_[tail_bucket_].last].tail = e;
       b.last = e;
-      b.prev = tail_bucket_;
+      b.first = e;
       b.epoch = epoch_;
       tail_bucket_ = (int)idx;
     } else {
@@ -109,8 +111,7 @@ class OrderedStateMap {
 
  private:
   struct Bucket {  // 12 bytes: the table of a 7000-token frame (14 k buckets) stays in the L2 of a core
-    int prev = -1;
-    int last = -1;
+    int first = -1, last = -1;
     uint32_t epoch = 0;
   };
   std::vector<Elem> pool_;
