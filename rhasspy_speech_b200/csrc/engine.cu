@@ -413,6 +413,7 @@ struct DecoderImpl {
   DevBuf d_tid_pdf;
   DevBuf d_loglikes_ext;
   PinBuf h_in, h_out;
+  PinBuf h_ll;  // log-likelihoods of the utterances the strict-order host decoder takes over
   LaneWorkspace *d_lanes = nullptr;   // general decode kernel only; see EnsureLaneWorkspace
   int lanes_allocated = 0;
   std::vector<void *> lane_owned;
@@ -1237,13 +1238,21 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     const auto t0 = std::chrono::steady_clock::now();
     const int ns = (int)strict_list.size();
     strict_res.resize(ns);
-    std::vector<std::vector<float>> ll(ns);
-    for (int i = 0; i < ns; i++) {
-      const int u = strict_list[i];
-      ll[i].resize((size_t)d->batch.n_out[u] * ld);
-      CUDA_OK(cudaMemcpyAsync(ll[i].data(), loglikes + (size_t)d->batch.ll_row0[u] * ld, ll[i].size() * sizeof(float),
-                              cudaMemcpyDeviceToHost, d->stream));
-      d->last.d2h_bytes += ll[i].size() * sizeof(float);
+    // the log-likelihood rows of the flagged utterances, back to back in page-locked memory (into ordinary vectors the
+    // 412 MB of a fully flagged batch of 256 were a synchronous, staged copy)
+    std::vector<const float *> ll(ns);
+    {
+      std::vector<size_t> off(ns + 1, 0);
+      for (int i = 0; i < ns; i++) off[i + 1] = off[i] + (size_t)d->batch.n_out[strict_list[i]] * ld;
+      float *base = (float *)d->h_ll.ensure(std::max<size_t>(off[ns], 1) * sizeof(float));
+      for (int i = 0; i < ns; i++) {
+        const int u = strict_list[i];
+        ll[i] = base + off[i];
+        const size_t bytes = (off[i + 1] - off[i]) * sizeof(float);
+        if (bytes)
+          CUDA_OK(cudaMemcpyAsync(base + off[i], loglikes + (size_t)d->batch.ll_row0[u] * ld, bytes, cudaMemcpyDeviceToHost, d->stream));
+        d->last.d2h_bytes += bytes;
+      }
     }
     CUDA_OK(cudaStreamSynchronize(d->stream));
     StrictOptions so;
@@ -1264,7 +1273,7 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
     auto work = [&]() {
       try {
         for (int i = next++; i < ns; i = next++)
-          StrictDecode(d->graph->g, d->h_epdf.data(), d->strict_arcs, ll[i].data(), ld, d->batch.n_out[strict_list[i]], so, lattice,
+          StrictDecode(d->graph->g, d->h_epdf.data(), d->strict_arcs, ll[i], ld, d->batch.n_out[strict_list[i]], so, lattice,
                        &strict_res[i]);
       } catch (const std::exception &e) {
         std::lock_guard<std::mutex> lk(fail_mu);
