@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BATCH = 256
-# DRAM bytes the 30 launches of the nnet stage moved in one step under ncu (profiles/r2f_launches.csv, round 2;
+# DRAM bytes the 30 launches of the nnet stage moved in one step under ncu (profiles/r2g_launches.csv, round 2;
 # round 1: 10.45 GB)
-NNET_DRAM_BYTES_PER_STEP = 9424915200
+NNET_DRAM_BYTES_PER_STEP = 9391758592
 METRIC = "RTFx (audio-sec/wall-sec) en_US-zamia 16kHz at 1/2/4/8 B200; WER vs ref"
 UNIT = "audio-sec/wall-sec"
 WORKLOAD = "configs[1]: batch=256 per GPU, grammar-HCLG, 3-5 s 16 kHz utterances cut from tests/en_US-zamia WAVs (+ sigma=2 noise)"
@@ -407,7 +407,7 @@ def run_ours(args):
                          "achieved": achieved, "peak": f16_peak, "unit": "TFLOP/s", "frac": achieved / f16_peak,
                          "traffic": NNET_DRAM_BYTES_PER_STEP,
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the stage's launches, "
-                                           "profiles/r2f_launches.csv (same workload, batch 256)",
+                                           "profiles/r2g_launches.csv (same workload, batch 256)",
                          "peak_source": pk_kind + " bf16_tflops_sustained (fp16 tensor pipe)",
                          "note": "3 MMAs per algorithmic product: attainable frac <= 0.333"},
             # the same launches against HBM: the stage streams every layer's activations through HBM once
