@@ -127,6 +127,37 @@ def test_decode_meta_and_nbest_text():
     assert T.nbest_text(H, 3) == b"utt-1 3 4 \nutt-2 3 \nutt-3 \n"   # lattice-to-nbest.cc:104-107 keys
 
 
+def test_python_copy_of_a_result_block():
+    """Hypotheses(rs_result): the one-best and the n-best views of a fabricated result block (plain ints and floats out,
+    utterances without a hypothesis as None / [], n-best lists in the order the library wrote them)."""
+    import ctypes as C
+    from rhasspy_speech_b200 import _lib
+
+    def ptr(a):
+        return a.ctypes.data_as(C.POINTER(C.c_int32 if a.dtype == np.int32 else C.c_float))
+    n_hyp = np.array([1, 0, 1], np.int32)
+    off = np.array([0, 3, 3, 5], np.int32)
+    ids = np.array([12, 45, 7, 3, 4], np.int32)
+    gc, ac = np.array([1.5, 0.0, 2.25], np.float32), np.array([-10.0, 0.0, -20.5], np.float32)
+    frames, status = np.array([100, 90, 80], np.int32), np.array([0, 4, 64], np.int32)
+    r = _lib.Result(3, ptr(n_hyp), ptr(off), ptr(ids), ptr(gc), ptr(ac), ptr(frames), ptr(status))
+    h = _lib.Hypotheses(r)
+    assert h.words == [[12, 45, 7], None, [3, 4]] and all(type(x) is int for w in h.words if w for x in w)
+    assert h.nbest == [[([12, 45, 7], 1.5, -10.0)], [], [([3, 4], 2.25, -20.5)]]
+    assert list(h.status) == [0, 4, 64] and list(h.num_frames) == [100, 90, 80]
+    # n-best block: utterance 0 has three hypotheses, utterance 2 two; the first of each is the one-best
+    n_hyp = np.array([3, 0, 2], np.int32)
+    ho = np.array([0, 3, 3, 5], np.int32)
+    wo = np.array([0, 3, 5, 5, 7, 8], np.int32)
+    wid = np.array([12, 45, 7, 12, 45, 3, 4, 3], np.int32)
+    hg, ha = np.arange(5, dtype=np.float32), -np.arange(5, dtype=np.float32)
+    r = _lib.Result(3, ptr(n_hyp), ptr(off), ptr(ids), ptr(gc), ptr(ac), ptr(frames), ptr(status), ptr(ho), ptr(wo), ptr(wid), ptr(hg), ptr(ha))
+    h = _lib.Hypotheses(r)
+    assert h.nbest[0] == [([12, 45, 7], 0.0, -0.0), ([12, 45], 1.0, -1.0), ([], 2.0, -2.0)]
+    assert h.nbest[1] == [] and h.nbest[2] == [([3, 4], 3.0, -3.0), ([3], 4.0, -4.0)]
+    assert all(type(c) is float for u in h.nbest for _, g, a in u for c in (g, a))
+
+
 def test_shard_utterances_balances_audio():
     from rhasspy_speech_b200.shard import shard_utterances
     rng = np.random.default_rng(3)
