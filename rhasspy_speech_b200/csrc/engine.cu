@@ -1267,14 +1267,21 @@ static rs_result *RunDecodeStage(DecoderImpl *d, const float *loglikes, int ld, 
       d->strict_arcs_ready = true;
     }
     const int nthreads = std::max(1, std::min(ns, (int)std::thread::hardware_concurrency()));
+    // longest utterances first: the threads draw from one counter, and the last draws should be the short ones
+    std::vector<int> order(ns);
+    for (int i = 0; i < ns; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return d->batch.n_out[strict_list[a]] > d->batch.n_out[strict_list[b]]; });
     std::atomic<int> next{0};
     std::string fail;
     std::mutex fail_mu;
     auto work = [&]() {
       try {
-        for (int i = next++; i < ns; i = next++)
+        for (int k = next++; k < ns; k = next++) {
+          const int i = order[k];
           StrictDecode(d->graph->g, d->h_epdf.data(), d->strict_arcs, ll[i], ld, d->batch.n_out[strict_list[i]], so, lattice,
                        &strict_res[i]);
+        }
       } catch (const std::exception &e) {
         std::lock_guard<std::mutex> lk(fail_mu);
         fail = e.what();

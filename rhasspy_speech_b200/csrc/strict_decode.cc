@@ -133,7 +133,8 @@ inline bool ApproxEq(float a, float b, float tol) {  // kaldi/src/base/kaldi-mat
 class Search {
  public:
   Search(const Graph &g, const int32_t *e_pdf, const StrictArcs &arcs, const float *ll, int ld, const StrictOptions &o, bool lattice)
-      : g_(g), e_pdf_(e_pdf), ea_(arcs.emitting.data()), pa_(arcs.epsilon.data()), ll_(ll), ld_(ld), o_(o), lattice_(lattice),
+      : g_(g), e_pdf_(e_pdf), ea_(arcs.emitting.data()), pa_(arcs.epsilon.data()), eps_bits_(arcs.has_epsilon.data()), ll_(ll),
+        ld_(ld), o_(o), lattice_(lattice),
         NE_((int)g.e_next.size()) {}
 
   void Run(int n_frames, StrictResult *out) {
@@ -164,7 +165,7 @@ class Search {
   }
 
  private:
-  bool HasEps(int s) const { return g_.p_begin[s + 1] > g_.p_begin[s]; }
+  bool HasEps(int s) const { return (eps_bits_[(size_t)s >> 6] >> (s & 63)) & 1u; }
 
   // FindOrAddToken :252-293
   int FindOrAdd(int state, float tot, int back, int back_arc, bool *changed) {
@@ -540,6 +541,7 @@ class Search {
   const Graph &g_;
   const int32_t *e_pdf_;
   const StrictArcs::Arc *ea_, *pa_;  // emitting / epsilon arcs as records (the search loops read nothing else of an arc)
+  const uint64_t *eps_bits_;         // "state has epsilon arcs", asked for every token of every frame
   const float *ll_;
   const int ld_;
   const StrictOptions o_;
@@ -567,13 +569,17 @@ void BuildStrictArcs(const Graph &g, const int32_t *e_pdf, StrictArcs *out) {
   for (size_t a = 0; a < g.e_next.size(); a++) out->emitting[a] = StrictArcs::Arc{g.e_next[a], e_pdf[a], g.e_weight[a]};
   out->epsilon.resize(g.p_next.size());
   for (size_t a = 0; a < g.p_next.size(); a++) out->epsilon[a] = StrictArcs::Arc{g.p_next[a], -1, g.p_weight[a]};
+  out->has_epsilon.assign(((size_t)g.num_states + 63) / 64 + 1, 0);
+  for (int s = 0; s < g.num_states; s++)
+    if (g.p_begin[s + 1] > g.p_begin[s]) out->has_epsilon[(size_t)s >> 6] |= uint64_t(1) << (s & 63);
 }
 
 void StrictDecode(const Graph &g, const int32_t *e_pdf, const StrictArcs &arcs, const float *loglikes, int ld, int n_frames,
                   const StrictOptions &opt, bool want_lattice, StrictResult *out) {
   *out = StrictResult();
   if (n_frames <= 0 || g.num_states <= 0) return;
-  if (arcs.emitting.size() != g.e_next.size() || arcs.epsilon.size() != g.p_next.size())
+  if (arcs.emitting.size() != g.e_next.size() || arcs.epsilon.size() != g.p_next.size() ||
+      arcs.has_epsilon.size() != ((size_t)g.num_states + 63) / 64 + 1)
     throw Error("StrictDecode: the arc records do not belong to this graph");
   Search s(g, e_pdf, arcs, loglikes, ld, opt, want_lattice);
   s.Run(n_frames, out);

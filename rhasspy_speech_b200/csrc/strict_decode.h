@@ -35,6 +35,7 @@ struct StrictArcs {
     float weight;
   };
   std::vector<Arc> emitting, epsilon;
+  std::vector<uint64_t> has_epsilon;  // one bit per state: it has epsilon-input arcs (16 KB for 127 k states)
 };
 void BuildStrictArcs(const Graph &g, const int32_t *e_pdf, StrictArcs *out);
 
