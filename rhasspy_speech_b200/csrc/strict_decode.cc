@@ -143,6 +143,7 @@ class Search {
     // (room for a max-active frontier on every frame: the token array of a 4 s utterance on an LM-sized graph reaches
     //  ~600 k entries and was copied five times over while it grew)
     toks_.reserve((size_t)(n_frames + 1) * (size_t)std::min(std::max(o_.max_active, 256), 6000));
+    if (lattice_) links_.reserve(toks_.capacity() * 2);  // one link per admitted arc, ~2.5 per token on an LM-sized graph
     frame_begin_.push_back(0);
     {
       const int e = map_.Insert((int)g_.start);
